@@ -1,0 +1,194 @@
+/*
+ * lrvb_b200.h -- C ABI of the B200-native logistic-GLMM LRVB hot path.
+ *
+ * Drop-in boundary for rgiordan/LinearResponseVariationalBayes.py (reference paths are
+ * relative to /root/reference/LinearResponseVariationalBayes/).  The reference has no FFI:
+ * its "operator interface" for this path is the Python class Objective
+ * (SparseObjectives.py:95-240), the sparse-Hessian helpers (SparseObjectives.py:581-657),
+ * ConjugateGradientSolver (ConjugateGradient.py:63-105) and the closed-form terms in
+ * Modeling.py:35-52 / ExponentialFamilies.py:5-120.  Every entry point below names the
+ * reference call it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *  - plain C types only; every `const double*` / `double*` / `int32_t*` named "dev" is a
+ *    CUDA device pointer on the current device, borrowed for the duration of the call
+ *    (X, y, g, w are borrowed for the lifetime of the handle);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *    enqueued on it, nothing synchronises unless the comment says "syncs";
+ *  - every function returns 0 on success; otherwise a negative code and
+ *    lrvb_last_error() holds a message (thread-local).
+ *      LRVB_EINVAL (-1): bad size / shape / argument  -> ValueError in the reference
+ *      LRVB_ECUDA  (-2): CUDA runtime failure         -> RuntimeError
+ *      LRVB_ESTATE (-3): call order (e.g. HVP before a Hessian was evaluated)
+ *  - all floating point is IEEE fp64.
+ *
+ * Flat parameter layout (ParameterDictionary.py:39-46, 64-65), D = Dg + 2G,
+ * Dg = 4 + 2K:   [mu.mean, mu.info, tau.shape, tau.rate, beta.mean[K], beta.info[K],
+ *                 u.mean[G], u.info[G]]
+ * "free" coordinates are the reference's unconstrained ones (Parameters.py:31-61):
+ * identity for means, log(value - lb) for info / shape / rate.
+ */
+#ifndef LRVB_B200_H
+#define LRVB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRVB_OK 0
+#define LRVB_EINVAL (-1)
+#define LRVB_ECUDA (-2)
+#define LRVB_ESTATE (-3)
+
+typedef struct lrvb_glmm lrvb_glmm;
+
+/* Priors: mu ~ N(mu_mean, 1/mu_info), beta_k ~ N(beta_mean, 1/beta_info), tau ~ Gamma(shape, rate)
+ * (ExponentialFamilies.py:191-195 uvn_prior / gamma_prior). */
+typedef struct {
+  double mu_mean, mu_info, beta_mean, beta_info, tau_shape, tau_rate;
+} lrvb_glmm_prior;
+
+/* Lower bounds of the constrained sub-parameters (NormalParams.py:29,56 min_info;
+ * GammaParams.py:7-8 min_shape / min_rate). */
+typedef struct {
+  double mu_info, tau_shape, tau_rate, beta_info, u_info;
+} lrvb_glmm_bounds;
+
+const char* lrvb_last_error(void);
+int lrvb_version(void);
+
+/* ---- model handle ---------------------------------------------------------------------
+ * Binds the data the reference's objective closure would capture (the zero-argument `fun`
+ * handed to Objective(par, fun), SparseObjectives.py:95-100).
+ *  X  dev (N,K) row-major fp64 (the reference's C-order ndarray), y dev (N,) fp64 in {0,1},
+ *  g  dev (N,) int32 group id in [0,G), NON-DECREASING (group-sorted); w dev (N,) or NULL.
+ *  gh_x, gh_w HOST (Q,) numpy.polynomial.hermite.hermgauss(Q) nodes / weights
+ *  (Modeling.py:35-37 takes them from the caller), Q <= 64.
+ *  include_global_terms: 1 = this handle also owns the terms that do not depend on any
+ *  group (priors and entropies of mu, beta, tau); ranks > 0 of an observation-sharded job
+ *  pass 0 so that the all-reduced sum counts them once.
+ * Validates sizes and the sortedness / range of g (syncs). */
+int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q,
+                     const double* X_dev, const double* y_dev, const int32_t* g_dev,
+                     const double* w_dev, const double* gh_x_host, const double* gh_w_host,
+                     const lrvb_glmm_prior* prior, const lrvb_glmm_bounds* bounds,
+                     int32_t include_global_terms, void* stream);
+int lrvb_glmm_destroy(lrvb_glmm* h);
+/* Coordinates of the evaluation point and of every derivative returned afterwards:
+ * 0 (default) = free / unconstrained (Objective.fun_free*, SparseObjectives.py:120-158),
+ * 1 = constrained "vector" coordinates (Objective.fun_vector*, :127-181).  Invalidates the
+ * cached Hessian. */
+int lrvb_glmm_set_coords(lrvb_glmm* h, int32_t vector_coords);
+/* D = 4 + 2K + 2G, Dg = 4 + 2K. */
+int lrvb_glmm_dims(const lrvb_glmm* h, int64_t* D, int32_t* Dg);
+
+/* ---- value / gradient / Hessian ---------------------------------------------------------
+ * Replaces Objective.fun_free, fun_free_grad, fun_free_hessian (SparseObjectives.py:120-158)
+ * for the composed GLMM KL.  order 0: KL; 1: + gradient; 2: + Hessian blocks.
+ *  free_dev      (D,)  evaluation point in free coordinates
+ *  out_global    dev, 1 + Dg + Dg*Dg doubles: [KL, grad[0:Dg], A (Dg,Dg) row-major]; only the
+ *                parts `order` asks for are written.  This packed buffer is exactly what an
+ *                observation-sharded job all-reduces (sum) across ranks.
+ *  grad_local    dev (2G,) = grad[Dg:D] (u.mean then u.info) or NULL; written when order >= 1.
+ * With order 2 the Hessian is kept inside the handle as arrowhead blocks
+ * (A (Dg,Dg); B (G,2,Dg): rows u.mean_g / u.info_g against the globals; L (G,3): the 2x2
+ * local block as (mm, mi, ii)) for the calls below. */
+int lrvb_glmm_eval(lrvb_glmm* h, const double* free_dev, int32_t order, double* out_global_dev,
+                   double* grad_local_dev, void* stream);
+/* Device pointers of the cached blocks (borrowed; valid until the next eval / destroy). */
+int lrvb_glmm_blocks(lrvb_glmm* h, double** A_dev, double** B_dev, double** L_dev);
+/* Overwrite the cached global block (after the all-reduce of out_global in a sharded job). */
+int lrvb_glmm_set_global_block(lrvb_glmm* h, const double* A_dev, void* stream);
+/* Per-observation derivative weights of the last eval: dev (5,N) rows
+ * [dl/dz_mean, dl/dz_var, d2l/dz_mean2, d2l/dz_mean dz_var, d2l/dz_var2];
+ * rows 2-4 only after order 2.  Borrowed pointer. */
+int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev);
+
+/* ---- sparse Hessian export ------------------------------------------------------------
+ * Replaces get_sparse_sub_hessian + csr_matrix summation (SparseObjectives.py:591-619):
+ * exact zeros dropped, columns sorted, int32 indices, one entry per coordinate.
+ * _nnz counts (syncs; returns nnz of the cached Hessian), _fill writes
+ * indptr (D+1,), indices (nnz,), data (nnz,) -- all dev. */
+int lrvb_glmm_hessian_csr_nnz(lrvb_glmm* h, int64_t* nnz, void* stream);
+int lrvb_glmm_hessian_csr_fill(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
+                               double* data_dev, void* stream);
+
+/* ---- Hessian-vector product -------------------------------------------------------------
+ * Replaces Objective.fun_free_hvp (SparseObjectives.py:183-187) at the point of the last
+ * order-2 eval.  v_dev, out_dev (D,).  include_A = 0 leaves the A v_g term out of out[0:Dg]
+ * (ranks > 0 of a sharded job, whose A is a replica). */
+int lrvb_glmm_hvp(lrvb_glmm* h, const double* v_dev, double* out_dev, int32_t include_A,
+                  void* stream);
+
+/* ---- conjugate gradient -----------------------------------------------------------------
+ * Replaces ConjugateGradientSolver.get_hinv_vec (ConjugateGradient.py:81-85), i.e.
+ * scipy.sparse.linalg.cg(A, b, x0, rtol, atol=0, M): stops when ||r|| <= rtol * ||b||.
+ *  precond: 0 = none, 1 = M = inverse of the block-diagonal of H (diag of A, 2x2 local blocks).
+ *  x0_dev NULL = zeros.  info: 0 converged, >0 = maxiter reached (scipy convention).
+ * Single-GPU handle only.  Syncs. */
+int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_t precond,
+                 double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
+                 void* stream);
+
+/* ---- direct arrowhead solve / LRVB covariance -------------------------------------------
+ * Schur complement of the local blocks:
+ *   S = [include_A ? A : 0] - sum_g B_g^T L_g^{-1} B_g     (Dg,Dg) row-major, dev.
+ * A sharded job all-reduces S.  lrvb_spd_inverse then gives (H^{-1})_gg = S^{-1}, the
+ * linear-response covariance of the global parameters (the role of
+ * -cho_solve(cho_factor(H), .) in ModelSensitivity.py:594-602). */
+int lrvb_glmm_schur(lrvb_glmm* h, double* S_dev, int32_t include_A, void* stream);
+/* In-place Cholesky inverse of an SPD (n,n) matrix on the device.  info_host: 0 ok,
+ * k>0 = leading minor k not positive.  Syncs. */
+int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream);
+/* x = H^{-1} b for nrhs right-hand sides (row-major (nrhs, D), dev) by block elimination,
+ * given Sinv = S^{-1} from above.  The local part uses this handle's groups; a sharded job
+ * first all-reduces rhs_g = b_g - sum_g B_g^T L_g^{-1} b_l (lrvb_glmm_solve_reduce_rhs). */
+int lrvb_glmm_solve_reduce_rhs(lrvb_glmm* h, const double* b_dev, int32_t nrhs,
+                               double* rhs_g_dev, int32_t include_bg, void* stream);
+int lrvb_glmm_solve_finish(lrvb_glmm* h, const double* Sinv_dev, const double* rhs_g_dev,
+                           const double* b_dev, int32_t nrhs, double* x_dev, void* stream);
+/* Marginal LRVB covariance of every group's (u.mean_g, u.info_g): (G,3) as (mm, mi, ii):
+ *   L_g^{-1} + L_g^{-1} B_g S^{-1} B_g^T L_g^{-1}. */
+int lrvb_glmm_local_cov(lrvb_glmm* h, const double* Sinv_dev, double* cov_dev, void* stream);
+
+/* ---- batched exponential-family terms (ExponentialFamilies.py) --------------------------
+ * All pointers dev; M = number of factors. */
+/* :33-35 gamma_entropy per factor, out (M,). */
+int lrvb_ef_gamma_entropy(const double* shape, const double* rate, int64_t M, double* out,
+                          void* stream);
+/* :111-112 get_e_log_gamma, out (M,). */
+int lrvb_ef_e_log_gamma(const double* shape, const double* rate, int64_t M, double* out,
+                        void* stream);
+/* :23-25 univariate_normal_entropy per factor (the reference sums them), out (M,). */
+int lrvb_ef_uvn_entropy(const double* info, int64_t M, double* out, void* stream);
+/* :43-52 dirichlet_entropy: alpha (d, M) row-major, simplex dimension is axis 0; out (M,). */
+int lrvb_ef_dirichlet_entropy(const double* alpha, int32_t d, int64_t M, double* out,
+                              void* stream);
+/* :118-120 get_e_log_dirichlet: out (d, M). */
+int lrvb_ef_e_log_dirichlet(const double* alpha, int32_t d, int64_t M, double* out,
+                            void* stream);
+/* :54-69 beta_entropy per row of tau (M,2) row-major (the reference sums them); out (M,). */
+int lrvb_ef_beta_entropy(const double* tau, int64_t M, double* out, void* stream);
+/* :72-82 wishart_entropy, :88-94 e_log_det_wishart, :97-102 e_log_inv_wishart_diag batched
+ * over M factors: df (M,), v (M,k,k) row-major SPD, k <= 8.
+ * entropy (M,) / e_log_det (M,) / e_log_inv_diag (M,k); any output may be NULL. */
+int lrvb_ef_wishart(const double* df, const double* v, int32_t k, int64_t M, double* entropy,
+                    double* e_log_det, double* e_log_inv_diag, void* stream);
+/* :20-21 multinoulli_entropy: p (M, d) row-major, out (M,). */
+int lrvb_ef_multinoulli_entropy(const double* p, int32_t d, int64_t M, double min_prob,
+                                double* out, void* stream);
+/* Modeling.py:35-52 get_e_logistic_term_guass_hermite with aggregate_all=False:
+ * z_mean, z_sd dev (M,), gh_x / gh_w HOST (Q,), out dev (M,). */
+int lrvb_gh_logistic_term(const double* z_mean, const double* z_sd, int64_t M,
+                          const double* gh_x_host, const double* gh_w_host, int32_t Q,
+                          double* out, void* stream);
+/* Deterministic sum of a device vector into out_dev[0] (used to aggregate the terms above
+ * the way the reference's np.sum does). */
+int lrvb_sum(const double* x_dev, int64_t M, double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRVB_B200_H */

@@ -1,0 +1,406 @@
+"""Logistic GLMM variational objective bound to the CUDA library (single GPU).
+
+The reference has no GLMM class: its users compose this KL from ``UVNParam`` / ``GammaParam`` /
+``UVNParamVector`` bundles, ``Modeling.get_e_logistic_term_guass_hermite`` (Modeling.py:35-52)
+and ``ExponentialFamilies`` terms inside a zero-argument ``fun`` handed to
+``Objective(par, fun)`` (SparseObjectives.py:95-100), and autograd differentiates it.  Here the
+same composition is a model object: it owns the ``ModelParamsDict`` (so the flat layout is the
+reference's, ParameterDictionary.py:39-46) and evaluates value / gradient / arrowhead Hessian /
+HVP / solves by calling ``liblrvb_b200.so`` through ctypes.  ``SparseObjectives.Objective``
+accepts it in place of ``fun``.
+
+    KL(free) = -( sum_n w_n [y_n z_n - GH(z_mean_n, z_sd_n)]
+                  + sum_g [-1/2 E[tau]((E mu - E u_g)^2 + Var mu + Var u_g) + 1/2 E log tau]
+                  + entropies(mu, beta, u, tau) + priors(mu, beta, tau) )
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as nat
+from ._tensors import is_torch, to_device
+from .GammaParams import GammaParam
+from .NormalParams import UVNParam, UVNParamVector
+from .ParameterDictionary import ModelParamsDict
+
+
+@dataclass
+class GLMMPrior:
+    """mu ~ N(mu_mean, 1/mu_info), beta_k ~ N(beta_mean, 1/beta_info), tau ~ Gamma(shape, rate)
+    (ExponentialFamilies.py:191-195)."""
+    mu_mean: float = 0.0
+    mu_info: float = 0.01
+    beta_mean: float = 0.0
+    beta_info: float = 0.01
+    tau_shape: float = 3.0
+    tau_rate: float = 3.0
+
+
+class _DevView(object):
+    """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape), "typestr": typestr,
+            "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def _view(ptr, shape, owner):
+    torch = nat.require_cuda()
+    n = int(np.prod(shape))
+    if n == 0:
+        return torch.empty(tuple(shape), dtype=torch.float64, device="cuda")
+    t = torch.as_tensor(_DevView(ptr, shape), device="cuda")
+    t._lrvb_owner = owner  # keep the handle alive as long as the view
+    return t
+
+
+class DeviceCSR(object):
+    """CSR Hessian resident on the device: ``crow_indices`` (D+1) int32, ``col_indices`` (nnz)
+    int32 sorted within each row, ``values`` (nnz) float64 -- the canonical form scipy produces
+    from get_sparse_sub_hessian triplets (SparseObjectives.py:591-619)."""
+
+    def __init__(self, crow, col, val, shape):
+        self.crow_indices, self.col_indices, self.values, self.shape = crow, col, val, tuple(shape)
+
+    @property
+    def nnz(self):
+        return int(self.values.numel())
+
+    def to_scipy(self):
+        import scipy.sparse
+        m = scipy.sparse.csr_matrix(
+            (self.values.cpu().numpy(), self.col_indices.cpu().numpy(),
+             self.crow_indices.cpu().numpy()), shape=self.shape)
+        m.has_sorted_indices = True
+        return m
+
+    def toarray(self):
+        return self.to_scipy().toarray()
+
+    def to_torch_sparse_csr(self):
+        torch = nat.require_cuda()
+        return torch.sparse_csr_tensor(self.crow_indices, self.col_indices, self.values,
+                                       size=self.shape)
+
+
+def group_sort(groups):
+    """Stable sort of group ids -> (sorted ids, permutation).  Bit-exact with
+    ``numpy.argsort(kind='stable')`` for host input; device input uses torch's stable sort."""
+    if is_torch(groups) and groups.is_cuda:
+        import torch
+        s, perm = torch.sort(groups.to(torch.int64), stable=True)
+        return s, perm
+    g = np.asarray(groups).astype(np.int64)
+    perm = np.argsort(g, kind="stable")
+    return g[perm], perm
+
+
+class LogisticGLMM(object):
+    """Data + variational parameters + device handle of one logistic GLMM (or one shard of it).
+
+    X (N,K) float64, y (N,) in {0,1}, groups (N,) integer ids in [0, num_groups); observations
+    are stably sorted by group if they are not already (``self.perm`` records the permutation).
+    ``gh_x, gh_w``: Gauss-Hermite nodes/weights (default ``hermgauss(num_gh_points)``).
+    """
+
+    _lrvb_device_model = True
+
+    def __init__(self, X, y, groups, num_gh_points=8, gh_x=None, gh_w=None, weights=None,
+                 prior=None, num_groups=None, min_info=0.0, min_shape=0.0, min_rate=0.0,
+                 include_global_terms=True, name="glmm_par"):
+        torch = nat.require_cuda()
+        lib = nat.load()
+        if gh_x is None or gh_w is None:
+            gh_x, gh_w = np.polynomial.hermite.hermgauss(int(num_gh_points))
+        self.gh_x = np.ascontiguousarray(np.asarray(gh_x, dtype=np.float64))
+        self.gh_w = np.ascontiguousarray(np.asarray(gh_w, dtype=np.float64))
+        if self.gh_x.shape != self.gh_w.shape or self.gh_x.ndim != 1:
+            raise ValueError("gh_x and gh_w must be 1-d arrays of the same length")
+        self.prior = prior or GLMMPrior()
+
+        Xs = X.shape
+        if len(Xs) != 2:
+            raise ValueError("X must be (N, K)")
+        N, K = int(Xs[0]), int(Xs[1])
+        for nm, v in (("y", y), ("groups", groups)) + ((("weights", weights),) if weights is not None else ()):
+            if int(np.prod(v.shape)) != N:
+                raise ValueError("Wrong size for {}.  Expected {}, got {}".format(
+                    nm, N, int(np.prod(v.shape))))
+
+        g_sorted, perm = self._sorted_groups(groups)
+        self.perm = perm
+        self.X = to_device(X)
+        self.y = to_device(y).reshape(-1)
+        self.w = None if weights is None else to_device(weights).reshape(-1)
+        if perm is not None:
+            pd = to_device(perm, torch.int64)
+            self.X = self.X.index_select(0, pd).contiguous()
+            self.y = self.y.index_select(0, pd).contiguous()
+            if self.w is not None:
+                self.w = self.w.index_select(0, pd).contiguous()
+        self.g = to_device(g_sorted, torch.int32).reshape(-1)
+        if num_groups is None:
+            num_groups = int(self.g.max().item()) + 1 if N > 0 else 0
+        self.N, self.K, self.G = N, K, int(num_groups)
+        self.Dg = 4 + 2 * K
+        self.D = self.Dg + 2 * self.G
+
+        # variational parameters; push order = flat layout (ParameterDictionary.py:39-46)
+        self.glmm_par = ModelParamsDict(name)
+        self.glmm_par.push_param(UVNParam("mu", min_info=min_info))
+        self.glmm_par.push_param(GammaParam("tau", min_shape=min_shape, min_rate=min_rate))
+        self.glmm_par.push_param(UVNParamVector("beta", K, min_info=min_info))
+        self.glmm_par.push_param(UVNParamVector("u", self.G, min_info=min_info))
+        assert self.glmm_par.free_size() == self.D
+
+        self._prior_c = nat.Prior(self.prior.mu_mean, self.prior.mu_info, self.prior.beta_mean,
+                                  self.prior.beta_info, self.prior.tau_shape, self.prior.tau_rate)
+        self._bounds_c = nat.Bounds(min_info, min_shape, min_rate, min_info, min_info)
+        self.lower_bounds = dict(mu_info=min_info, tau_shape=min_shape, tau_rate=min_rate,
+                                 beta_info=min_info, u_info=min_info)
+        h = ctypes.c_void_p()
+        nat.check(lib.lrvb_glmm_create(
+            ctypes.byref(h), N, K, self.G, self.gh_x.size, nat.ptr(self.X), nat.ptr(self.y),
+            nat.ptr(self.g), nat.ptr(self.w), nat.darray(self.gh_x), nat.darray(self.gh_w),
+            ctypes.byref(self._prior_c), ctypes.byref(self._bounds_c),
+            1 if include_global_terms else 0, nat.stream_ptr()))
+        self._h = h
+        self._lib = lib
+        dev = self.X.device
+        self._out_global = torch.zeros(1 + self.Dg + self.Dg * self.Dg, dtype=torch.float64,
+                                       device=dev)
+        self._grad_local = torch.zeros(2 * self.G, dtype=torch.float64, device=dev)
+        self._x_dev = torch.zeros(self.D, dtype=torch.float64, device=dev)
+        self._x_pin = torch.zeros(self.D, dtype=torch.float64).pin_memory()
+        self._x_event = None
+        self._cache = dict(x=None, order=-1, coords=None)
+        self._coords = "free"
+        self.device = dev
+
+    # ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _sorted_groups(groups):
+        if is_torch(groups):
+            import torch
+            gl = groups.reshape(-1).to(torch.int64)
+            if gl.numel() < 2 or bool((gl[1:] >= gl[:-1]).all()):
+                return gl, None
+            return group_sort(gl)
+        g = np.asarray(groups).reshape(-1)
+        if not np.issubdtype(g.dtype, np.integer):
+            gi = g.astype(np.int64)
+            if not np.array_equal(gi, g):
+                raise ValueError("group ids must be integers")
+            g = gi
+        if g.size < 2 or np.all(g[1:] >= g[:-1]):
+            return g.astype(np.int64), None
+        return group_sort(g)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.lrvb_glmm_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- evaluation -------------------------------------------------------------------------
+    def _stage_x(self, x):
+        """Evaluation point -> device tensor (pinned staging for host input)."""
+        torch = nat.require_cuda()
+        if is_torch(x):
+            if x.numel() != self.D:
+                raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
+                    self.glmm_par.name, self.D, x.numel()))
+            if x.is_cuda:
+                self._x_dev.copy_(x.reshape(-1))
+            else:
+                self._x_dev.copy_(x.reshape(-1))
+            return
+        xa = np.asarray(x, dtype=np.float64).reshape(-1)
+        if xa.size != self.D:
+            raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
+                self.glmm_par.name, self.D, xa.size))
+        if self._x_event is not None:
+            self._x_event.synchronize()  # the previous async copy has left the pinned buffer
+        self._x_pin.numpy()[:] = xa
+        self._x_dev.copy_(self._x_pin, non_blocking=True)
+        self._x_event = torch.cuda.Event()
+        self._x_event.record()
+
+    def _same_point(self, x, coords):
+        c = self._cache
+        if c["x"] is None or c["coords"] != coords:
+            return False
+        if is_torch(x):
+            import torch
+            if not is_torch(c["x"]):
+                return False
+            return c["x"].shape == x.reshape(-1).shape and bool(torch.equal(c["x"], x.reshape(-1)))
+        if is_torch(c["x"]):
+            return False
+        return np.array_equal(c["x"], np.asarray(x, dtype=np.float64).reshape(-1))
+
+    def evaluate(self, x, order, coords="free", force=False):
+        """Runs the fused evaluation of ``order`` (0 value, 1 +gradient, 2 +Hessian blocks) at
+        ``x`` unless the cached evaluation already covers it."""
+        if coords not in ("free", "vector"):
+            raise ValueError("coords must be 'free' or 'vector'")
+        if not force and self._cache["order"] >= order and self._same_point(x, coords):
+            return
+        if coords != self._coords:
+            nat.check(self._lib.lrvb_glmm_set_coords(self._h, 1 if coords == "vector" else 0))
+            self._coords = coords
+        self._stage_x(x)
+        nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(self._x_dev), int(order),
+                                           nat.ptr(self._out_global), nat.ptr(self._grad_local),
+                                           nat.stream_ptr()))
+        self._cache = dict(
+            x=(x.detach().reshape(-1).clone() if is_torch(x)
+               else np.array(x, dtype=np.float64).reshape(-1)),
+            order=int(order), coords=coords)
+
+    def invalidate(self):
+        self._cache = dict(x=None, order=-1, coords=None)
+
+    # raw device results of the last evaluation
+    def kl_tensor(self):
+        return self._out_global[0]
+
+    def grad_tensor(self):
+        import torch
+        return torch.cat([self._out_global[1:1 + self.Dg], self._grad_local])
+
+    def blocks(self):
+        """(A (Dg,Dg), B (G,2,Dg), L (G,3)) views of the cached Hessian (free or vector
+        coordinates, whichever was evaluated)."""
+        a, b, l = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        nat.check(self._lib.lrvb_glmm_blocks(self._h, ctypes.byref(a), ctypes.byref(b),
+                                             ctypes.byref(l)))
+        return (_view(a.value, (self.Dg, self.Dg), self), _view(b.value, (self.G, 2, self.Dg), self),
+                _view(l.value, (self.G, 3), self))
+
+    def obs_weights(self):
+        """(5, N) per-observation derivative weights of the last evaluation (sorted order)."""
+        w = ctypes.c_void_p()
+        nat.check(self._lib.lrvb_glmm_obs_weights(self._h, ctypes.byref(w)))
+        return _view(w.value, (5, self.N), self)
+
+    def set_global_block(self, A):
+        nat.check(self._lib.lrvb_glmm_set_global_block(self._h, nat.ptr(A), nat.stream_ptr()))
+
+    def hessian_csr(self):
+        """Device CSR of the cached Hessian."""
+        torch = nat.require_cuda()
+        nnz = ctypes.c_int64()
+        nat.check(self._lib.lrvb_glmm_hessian_csr_nnz(self._h, ctypes.byref(nnz), nat.stream_ptr()))
+        crow = torch.empty(self.D + 1, dtype=torch.int32, device=self.device)
+        col = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
+        val = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_hessian_csr_fill(self._h, nat.ptr(crow), nat.ptr(col),
+                                                       nat.ptr(val), nat.stream_ptr()))
+        return DeviceCSR(crow, col, val, (self.D, self.D))
+
+    def hvp_cached(self, v_dev, out=None, include_A=True):
+        """H v with the cached Hessian; v_dev a CUDA fp64 tensor (D,)."""
+        torch = nat.require_cuda()
+        if v_dev.numel() != self.D:
+            raise ValueError("Wrong size for HVP vector.  Expected {}, got {}".format(
+                self.D, v_dev.numel()))
+        if out is None:
+            out = torch.empty(self.D, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_hvp(self._h, nat.ptr(v_dev), nat.ptr(out),
+                                          1 if include_A else 0, nat.stream_ptr()))
+        return out
+
+    # names shared with distributed.ShardedLogisticGLMM (where they add the all-reduce)
+    def hvp(self, v_dev):
+        return self.hvp_cached(v_dev)
+
+    def cg(self, b_dev, x0_dev=None, precond=0, rtol=1e-8, maxiter=0):
+        return self.cg_cached(b_dev, x0_dev, precond, rtol, maxiter)
+
+    def global_covariance(self):
+        """(H^-1)_gg = S^-1: the linear-response covariance of the global free parameters."""
+        return self.spd_inverse_(self.schur_cached(include_A=True))
+
+    def solve(self, b_dev):
+        """x = H^-1 b (b (D,) or (nrhs, D)) by block elimination with the cached Hessian."""
+        Sinv = self.global_covariance()
+        rhs = self.solve_reduce_rhs(b_dev, include_bg=True)
+        return self.solve_finish(Sinv, rhs, b_dev)
+
+    def cg_cached(self, b_dev, x0_dev=None, precond=0, rtol=1e-8, maxiter=0):
+        """scipy-cg-compatible solve with the cached Hessian -> (x_dev, info, iters)."""
+        torch = nat.require_cuda()
+        x = torch.empty(self.D, dtype=torch.float64, device=self.device)
+        info, iters = ctypes.c_int32(), ctypes.c_int32()
+        nat.check(self._lib.lrvb_glmm_cg(self._h, nat.ptr(b_dev), nat.ptr(x0_dev), int(precond),
+                                         float(rtol), int(maxiter), nat.ptr(x), ctypes.byref(info),
+                                         ctypes.byref(iters), nat.stream_ptr()))
+        return x, info.value, iters.value
+
+    def schur_cached(self, include_A=True):
+        """S = [A] - sum_g B_g^T L_g^-1 B_g  (Dg,Dg)."""
+        torch = nat.require_cuda()
+        S = torch.empty(self.Dg, self.Dg, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_schur(self._h, nat.ptr(S), 1 if include_A else 0,
+                                            nat.stream_ptr()))
+        return S
+
+    @staticmethod
+    def spd_inverse_(S):
+        """In-place inverse of an SPD device matrix; raises if not positive definite."""
+        info = ctypes.c_int32()
+        nat.check(nat.load().lrvb_spd_inverse(nat.ptr(S), S.shape[0], ctypes.byref(info),
+                                              nat.stream_ptr()))
+        if info.value != 0:
+            raise np.linalg.LinAlgError(
+                "matrix not positive definite (pivot {})".format(info.value))
+        return S
+
+    def solve_reduce_rhs(self, b_dev, include_bg=True):
+        torch = nat.require_cuda()
+        b2 = b_dev.reshape(-1, self.D)
+        rhs = torch.empty(b2.shape[0], self.Dg, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_solve_reduce_rhs(self._h, nat.ptr(b2), b2.shape[0],
+                                                       nat.ptr(rhs), 1 if include_bg else 0,
+                                                       nat.stream_ptr()))
+        return rhs
+
+    def solve_finish(self, Sinv, rhs_g, b_dev):
+        torch = nat.require_cuda()
+        b2 = b_dev.reshape(-1, self.D)
+        x = torch.empty_like(b2)
+        nat.check(self._lib.lrvb_glmm_solve_finish(self._h, nat.ptr(Sinv), nat.ptr(rhs_g),
+                                                   nat.ptr(b2), b2.shape[0], nat.ptr(x),
+                                                   nat.stream_ptr()))
+        return x.reshape(b_dev.shape)
+
+    def local_cov(self, Sinv):
+        torch = nat.require_cuda()
+        cov = torch.empty(self.G, 3, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_local_cov(self._h, nat.ptr(Sinv), nat.ptr(cov),
+                                                nat.stream_ptr()))
+        return cov
+
+    # ---- moments (for LinearResponseCovariances) ------------------------------------------------
+    def moment_names(self):
+        return (["e_mu", "e_tau"] + ["e_beta_%d" % k for k in range(self.K)]
+                + ["e_u_%d" % g for g in range(self.G)])
+
+    def moment_jacobian(self, free):
+        """d [E mu, E tau, E beta (K), E u (G)] / d free as scipy CSR ((2+K+G), D).
+        E tau = shape/rate (GammaParams.py:9-10) with shape = exp(f)+lb (Parameters.py:55)."""
+        import scipy.sparse
+        free = np.asarray(free, dtype=np.float64).reshape(-1)
+        K, G, Dg = self.K, self.G, self.Dg
+        a = np.exp(free[2]) + self.lower_bounds["tau_shape"]
+        b = np.exp(free[3]) + self.lower_bounds["tau_rate"]
+        rows = [0, 1, 1] + list(range(2, 2 + K)) + list(range(2 + K, 2 + K + G))
+        cols = [0, 2, 3] + list(range(4, 4 + K)) + list(range(Dg, Dg + G))
+        vals = [1.0, np.exp(free[2]) / b, -a / (b * b) * np.exp(free[3])] + [1.0] * (K + G)
+        return scipy.sparse.csr_matrix((vals, (rows, cols)), (2 + K + G, self.D))

@@ -1,0 +1,121 @@
+"""Linear-response (LRVB) covariances of the GLMM posterior on the device.
+
+``north_star`` names ``ModelSensitivity.LinearResponseCovariances``; the reference's nearest
+code is ``ParametricSensitivityLinearApproximation`` (ModelSensitivity.py:555-612: Cholesky of
+the Hessian at the optimum, then ``-cho_solve(chol, cross_hessian)``) and ``Example.ipynb`` cell
+15 (``-solve(objective_hess, summary_jac.T)``); the class with this name lives in the successor
+library (README.md:14).  This module provides it over the CUDA path:
+
+    Cov(m) = J_m H^{-1} J_m^T,      J_m = d m / d free at the optimum,
+
+where ``H^{-1}`` is applied either by the direct arrowhead solve (Schur complement of the 2x2
+local blocks, csrc/solve.cu k_schur on the FP64 tensor cores + small SPD inverse) or by the
+device conjugate gradient -- the dense ``cho_factor`` of the reference is O(D^3) and is not used.
+"""
+import numpy as np
+import scipy.sparse
+
+from . import _native as nat
+from ._tensors import is_torch, to_device
+
+
+class LinearResponseCovariances(object):
+    def __init__(self, objective, opt_par_value, validate_optimum=False, grad_tol=1e-8,
+                 method="schur", cg_tol=1e-8, cg_preconditioner="block_jacobi"):
+        """objective: a device ``SparseObjectives.Objective``; opt_par_value: the free parameter
+        at the optimum (numpy or CUDA tensor).  method: 'schur' (direct) or 'cg'."""
+        if not getattr(getattr(objective, "model", None), "_lrvb_device_model", False):
+            raise TypeError("LinearResponseCovariances needs a device Objective")
+        if method not in ("schur", "cg"):
+            raise ValueError("method must be 'schur' or 'cg'")
+        self.objective = objective
+        self.model = objective.model
+        self.method = method
+        self.cg_tol = cg_tol
+        self.cg_preconditioner = cg_preconditioner
+        self.cg_infos = []
+        self.cg_iterations = []
+        self.set_base_values(opt_par_value, validate_optimum, grad_tol)
+
+    def set_base_values(self, opt_par_value, validate_optimum=False, grad_tol=1e-8):
+        self._opt0 = opt_par_value
+        if validate_optimum:
+            g = self.objective.fun_free_grad(opt_par_value)
+            gmax = float(abs(g).max())
+            if gmax > grad_tol:
+                raise ValueError("Gradient at the claimed optimum has max-abs {} > {}".format(
+                    gmax, grad_tol))
+        self.model.evaluate(opt_par_value, 2, "free")
+        self._sinv = None
+
+    def _ensure_point(self):
+        self.model.evaluate(self._opt0, 2, "free")
+
+    # ---- pieces ----
+    def get_hessian_at_opt(self):
+        """Sparse Hessian at the optimum (scipy CSR for numpy input, DeviceCSR for torch)."""
+        return self.objective.fun_free_hessian(self._opt0)
+
+    def get_global_covariance(self):
+        """(H^{-1})[:Dg,:Dg]: LRVB covariance of the global free parameters (Dg,Dg)."""
+        self._ensure_point()
+        if self._sinv is None:
+            self._sinv = self.model.global_covariance()
+        return self._sinv if is_torch(self._opt0) else self._sinv.cpu().numpy()
+
+    def get_local_covariances(self):
+        """Per-group LRVB covariance of (u.mean_g, u.info_g) free parameters, (G,3)=(mm,mi,ii)."""
+        self._ensure_point()
+        if self._sinv is None:
+            self._sinv = self.model.global_covariance()
+        cov = self.model.local_cov(self._sinv)
+        return cov if is_torch(self._opt0) else cov.cpu().numpy()
+
+    def hinv(self, rhs):
+        """H^{-1} rhs for rhs (D,) or (nrhs, D) -> same shape (device tensor)."""
+        self._ensure_point()
+        b = to_device(rhs)
+        if self.method == "schur":
+            return self.model.solve(b)
+        out = []
+        for row in b.reshape(-1, self.model.D):
+            x, info, iters = self.model.cg(
+                row.contiguous(), None,
+                precond=1 if self.cg_preconditioner == "block_jacobi" else 0, rtol=self.cg_tol)
+            self.cg_infos.append(info)
+            self.cg_iterations.append(iters)
+            out.append(x)
+        torch = nat.require_cuda()
+        return torch.stack(out).reshape(b.shape)
+
+    def get_moment_jacobian(self, calculate_moments=None):
+        """Jacobian of the moments w.r.t. the free parameters.  The model's analytic
+        [E mu, E tau, E beta, E u] Jacobian is used; an arbitrary ``calculate_moments`` callable
+        would need autodiff, which this library does not provide."""
+        if calculate_moments is not None:
+            raise TypeError("pass explicit Jacobians to get_lr_covariance_from_jacobians; "
+                            "arbitrary moment callables need autodiff")
+        x = self._opt0.detach().cpu().numpy() if is_torch(self._opt0) else self._opt0
+        return self.model.moment_jacobian(x)
+
+    def get_lr_covariance_from_jacobians(self, moment_jacobian1, moment_jacobian2=None):
+        """J1 H^{-1} J2^T for (m1, D) / (m2, D) Jacobians (dense, scipy-sparse or torch)."""
+        torch = nat.require_cuda()
+        if moment_jacobian2 is None:
+            moment_jacobian2 = moment_jacobian1
+
+        def dense_dev(j):
+            if scipy.sparse.issparse(j):
+                j = j.toarray()
+            return to_device(j).reshape(-1, self.model.D)
+
+        j2 = dense_dev(moment_jacobian2)
+        hinv_j2t = self.hinv(j2)                      # (m2, D): rows are H^{-1} J2[i]
+        j1 = dense_dev(moment_jacobian1)
+        cov = torch.matmul(j1, hinv_j2t.t())
+        return cov if (is_torch(moment_jacobian1) or is_torch(self._opt0)) else cov.cpu().numpy()
+
+    def get_lr_covariance(self, calculate_moments=None):
+        """LRVB covariance of the model's default moments [E mu, E tau, E beta, E u]."""
+        j = self.get_moment_jacobian(calculate_moments)
+        return self.get_lr_covariance_from_jacobians(j, j)

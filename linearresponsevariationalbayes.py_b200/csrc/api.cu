@@ -1,0 +1,268 @@
+// C-ABI entry points: handle life-cycle and evaluation (see include/lrvb_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include "common.cuh"
+
+namespace lrvb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Validate group ids (range, sortedness) and build gptr (G+1): first observation of each group.
+__global__ void k_gptr(const int32_t* __restrict__ g, int32_t* __restrict__ gptr, int* flags,
+                       int64_t N, int G) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > N) return;
+  int prev = (n == 0) ? -1 : g[n - 1];
+  int cur = (n == N) ? G : g[n];
+  if (n < N && (cur < 0 || cur >= G)) { atomicOr(flags, 1); return; }
+  if (n > 0 && (prev < 0 || prev >= G)) { atomicOr(flags, 1); return; }
+  if (n > 0 && n < N && cur < prev) { atomicOr(flags, 2); return; }
+  for (int gg = prev + 1; gg <= cur; ++gg) gptr[gg] = (int32_t)n;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  LRVB_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return LRVB_OK;
+}
+
+// kernels defined in glmm_eval.cu whose attributes must be raised for > 48 KB dynamic smem
+void configure_kernels(size_t obs_smem, size_t gram_smem);
+
+}  // namespace lrvb
+
+using namespace lrvb;
+
+extern "C" {
+
+const char* lrvb_last_error(void) { return g_err; }
+int lrvb_version(void) { return 100; }
+
+int lrvb_glmm_destroy(lrvb_glmm* h) {
+  if (!h) return LRVB_OK;
+  void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart,
+                  h->jobs, h->grampart, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk,
+                  h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
+                  h->schurpart};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete h;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q,
+                     const double* X_dev, const double* y_dev, const int32_t* g_dev,
+                     const double* w_dev, const double* gh_x_host, const double* gh_w_host,
+                     const lrvb_glmm_prior* prior, const lrvb_glmm_bounds* bounds,
+                     int32_t include_global_terms, void* stream) {
+  LRVB_REQUIRE(out != nullptr, "lrvb_glmm_create: out is NULL");
+  *out = nullptr;
+  LRVB_REQUIRE(N >= 0 && N < (int64_t)2147483000, "lrvb_glmm_create: N = %lld out of range",
+               (long long)N);
+  LRVB_REQUIRE(K >= 1 && K <= kMaxK, "lrvb_glmm_create: K = %d not in [1, %d]", K, kMaxK);
+  LRVB_REQUIRE(G >= 0, "lrvb_glmm_create: G = %d negative", G);
+  LRVB_REQUIRE(Q >= 1 && Q <= kMaxQ, "lrvb_glmm_create: Q = %d not in [1, %d]", Q, kMaxQ);
+  LRVB_REQUIRE(N == 0 || (X_dev && y_dev && g_dev), "lrvb_glmm_create: X, y, g must be non-NULL");
+  LRVB_REQUIRE(N == 0 || G >= 1, "lrvb_glmm_create: observations but no groups");
+  LRVB_REQUIRE(gh_x_host && gh_w_host && prior && bounds, "lrvb_glmm_create: NULL argument");
+  LRVB_REQUIRE((((uintptr_t)X_dev) & 7) == 0, "lrvb_glmm_create: X not 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  lrvb_glmm* h = new (std::nothrow) lrvb_glmm();
+  LRVB_REQUIRE(h != nullptr, "out of host memory");
+  h->N = N; h->K = K; h->G = G; h->Q = Q;
+  h->Dg = 4 + 2 * K;
+  h->D = h->Dg + 2 * (int64_t)G;
+  h->KT = (K + 7) / 8;
+  h->include_global = include_global_terms ? 1 : 0;
+  h->X = X_dev; h->y = y_dev; h->g = g_dev; h->w = w_dev;
+  h->prior = *prior;
+  h->bounds = *bounds;
+  const int Dg = h->Dg;
+
+#define CREATE_TRY(expr)                         \
+  do {                                           \
+    int rc__ = (expr);                           \
+    if (rc__ != LRVB_OK) { lrvb_glmm_destroy(h); return rc__; } \
+  } while (0)
+#define CREATE_CUDA(call)                                                      \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      set_error("%s failed: %s", #call, cudaGetErrorString(e__));              \
+      lrvb_glmm_destroy(h);                                                    \
+      return LRVB_ECUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+  // quadrature constants: c_q = sqrt(2) x_q, what_q = w_q / sqrt(pi)   (Modeling.py:41-48)
+  std::vector<double> ghh(2 * Q);
+  for (int q = 0; q < Q; ++q) {
+    ghh[q] = sqrt(2.0) * gh_x_host[q];
+    ghh[Q + q] = gh_w_host[q] / sqrt(M_PI);
+  }
+  CREATE_TRY(dev_alloc(&h->gh, 2 * Q));
+  CREATE_CUDA(cudaMemcpyAsync(h->gh, ghh.data(), sizeof(double) * 2 * Q, cudaMemcpyHostToDevice, st));
+  CREATE_CUDA(cudaStreamSynchronize(st));  // ghh goes out of scope
+
+  CREATE_TRY(dev_alloc(&h->flags, 8));
+  CREATE_CUDA(cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, st));
+  CREATE_TRY(dev_alloc(&h->gptr, (size_t)G + 1));
+  k_gptr<<<cdiv(N + 1, 256), 256, 0, st>>>(g_dev, h->gptr, h->flags, N, G);
+  CREATE_CUDA(cudaGetLastError());
+  int hflag = 0;
+  CREATE_CUDA(cudaMemcpyAsync(&hflag, h->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CREATE_CUDA(cudaStreamSynchronize(st));
+  if (hflag) {
+    set_error(hflag & 1 ? "lrvb_glmm_create: group id outside [0, G)"
+                        : "lrvb_glmm_create: group ids must be non-decreasing (group-sorted)");
+    lrvb_glmm_destroy(h);
+    return LRVB_EINVAL;
+  }
+
+  CREATE_TRY(dev_alloc(&h->vec, (size_t)h->D));
+  CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)N));
+
+  // observation pass geometry
+  h->obs_tn = (K <= 27) ? 256 : (K <= 54 ? 128 : 64);
+  h->obs_smem = sizeof(double) * ((size_t)h->obs_tn * K + 2 * K + 2 * Q + 2 * h->obs_tn + 32);
+  {
+    int per_sm = (int)(220 * 1024 / h->obs_smem);
+    if (per_sm > 2048 / h->obs_tn) per_sm = 2048 / h->obs_tn;
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    int64_t nt = (N + h->obs_tn - 1) / h->obs_tn;
+    int64_t gmax = (int64_t)kNumSMs * per_sm;
+    h->obs_grid = (int)(nt < gmax ? nt : gmax);
+    if (h->obs_grid < 1) h->obs_grid = 1;
+  }
+  CREATE_TRY(dev_alloc(&h->klpart, (size_t)h->obs_grid));
+  CREATE_TRY(dev_alloc(&h->gradpart, (size_t)h->obs_grid * 2 * K));
+
+  CREATE_TRY(dev_alloc(&h->gsc, (size_t)G * 5));
+  CREATE_TRY(dev_alloc(&h->BR, (size_t)G * 4 * K));
+  h->loc_grid = cdiv(G, 256);
+  if (h->loc_grid > 2 * kNumSMs) h->loc_grid = 2 * kNumSMs;
+  if (h->loc_grid < 1) h->loc_grid = 1;
+  CREATE_TRY(dev_alloc(&h->locpart, (size_t)h->loc_grid * 4));
+
+  // Gram geometry
+  {
+    const int KT = h->KT;
+    const int R = (KT + kRT - 1) / kRT;
+    std::vector<GramJob> jobs;
+    for (int fam = 0; fam < 3; ++fam)
+      for (int ri = 0; ri < R; ++ri)
+        for (int rj = 0; rj < R; ++rj) {
+          if (fam != 1 && rj < ri) continue;
+          jobs.push_back(GramJob{fam, kRT * ri, kRT * rj, 0});
+        }
+    h->gram_jobs = (int)jobs.size();
+    h->gram_grid_y = (h->gram_jobs + 7) / 8;
+    h->gram_jpc = (h->gram_jobs + h->gram_grid_y - 1) / h->gram_grid_y;
+    h->gram_split = 8 / h->gram_jpc;
+    if (h->gram_split < 1) h->gram_split = 1;
+    h->gram_tn = (K <= 24) ? 256 : (K <= 56 ? 128 : 64);
+    size_t tile = sizeof(double) * ((size_t)h->gram_tn * K + 3 * h->gram_tn);
+    size_t red = (h->gram_split > 1) ? sizeof(double) * (size_t)h->gram_jpc * kRT * kRT * 64 : 0;
+    h->gram_smem = tile > red ? tile : red;
+    int64_t nt = (N + h->gram_tn - 1) / h->gram_tn;
+    int64_t nchunk = (2 * kNumSMs) / h->gram_grid_y;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > nt) nchunk = nt;
+    if (nchunk < 1) nchunk = 1;
+    h->gram_grid_x = (int)nchunk * h->gram_grid_y;
+    CREATE_TRY(dev_alloc(&h->jobs, jobs.size()));
+    CREATE_CUDA(cudaMemcpyAsync(h->jobs, jobs.data(), sizeof(GramJob) * jobs.size(),
+                                cudaMemcpyHostToDevice, st));
+    CREATE_CUDA(cudaStreamSynchronize(st));
+    CREATE_TRY(dev_alloc(&h->grampart, (size_t)nchunk * h->gram_jobs * kRT * kRT * 64));
+    CREATE_CUDA(cudaMemsetAsync(h->grampart, 0,
+                                sizeof(double) * (size_t)nchunk * h->gram_jobs * kRT * kRT * 64, st));
+  }
+  configure_kernels(h->obs_smem, h->gram_smem);
+
+  CREATE_TRY(dev_alloc(&h->B, (size_t)G * 2 * Dg));
+  CREATE_TRY(dev_alloc(&h->L, (size_t)G * 3));
+  CREATE_TRY(dev_alloc(&h->gradl, 2 * (size_t)G));
+  CREATE_TRY(dev_alloc(&h->outg, 1 + (size_t)Dg + (size_t)Dg * Dg));
+  h->A = h->outg + 1 + Dg;
+  CREATE_TRY(dev_alloc(&h->scal, 32));
+  CREATE_CUDA(cudaStreamSynchronize(st));
+#undef CREATE_TRY
+#undef CREATE_CUDA
+  *out = h;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_set_coords(lrvb_glmm* h, int32_t vector_coords) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_set_coords: NULL handle");
+  if (h->vecmode != (vector_coords ? 1 : 0)) {
+    h->vecmode = vector_coords ? 1 : 0;
+    h->hess_valid = 0;
+    h->grad_valid = 0;
+  }
+  return LRVB_OK;
+}
+
+int lrvb_glmm_dims(const lrvb_glmm* h, int64_t* D, int32_t* Dg) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_dims: NULL handle");
+  if (D) *D = h->D;
+  if (Dg) *Dg = h->Dg;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_eval(lrvb_glmm* h, const double* free_dev, int32_t order, double* out_global_dev,
+                   double* grad_local_dev, void* stream) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_eval: NULL handle");
+  LRVB_REQUIRE(free_dev != nullptr, "lrvb_glmm_eval: free is NULL");
+  LRVB_REQUIRE(order >= 0 && order <= 2, "lrvb_glmm_eval: order = %d not in {0,1,2}", order);
+  return launch_eval(h, free_dev, order, out_global_dev, grad_local_dev, (cudaStream_t)stream);
+}
+
+int lrvb_glmm_blocks(lrvb_glmm* h, double** A_dev, double** B_dev, double** L_dev) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_blocks: NULL handle");
+  if (!h->hess_valid) {
+    set_error("lrvb_glmm_blocks: no Hessian cached (call lrvb_glmm_eval with order 2 first)");
+    return LRVB_ESTATE;
+  }
+  if (A_dev) *A_dev = h->A;
+  if (B_dev) *B_dev = h->B;
+  if (L_dev) *L_dev = h->L;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_set_global_block(lrvb_glmm* h, const double* A_dev, void* stream) {
+  LRVB_REQUIRE(h != nullptr && A_dev != nullptr, "lrvb_glmm_set_global_block: NULL argument");
+  if (!h->hess_valid) {
+    set_error("lrvb_glmm_set_global_block: no Hessian cached");
+    return LRVB_ESTATE;
+  }
+  if (A_dev != h->A)
+    LRVB_CUDA(cudaMemcpyAsync(h->A, A_dev, sizeof(double) * (size_t)h->Dg * h->Dg,
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return LRVB_OK;
+}
+
+int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev) {
+  LRVB_REQUIRE(h != nullptr && W_dev != nullptr, "lrvb_glmm_obs_weights: NULL argument");
+  if (!h->grad_valid) {
+    set_error("lrvb_glmm_obs_weights: no evaluation of order >= 1 cached");
+    return LRVB_ESTATE;
+  }
+  *W_dev = h->W;
+  return LRVB_OK;
+}
+
+}  // extern "C"

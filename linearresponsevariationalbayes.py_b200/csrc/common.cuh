@@ -1,0 +1,203 @@
+// Shared declarations of the lrvb_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/lrvb_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "lrvb_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace lrvb {
+
+void set_error(const char* fmt, ...);
+
+#define LRVB_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      lrvb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                      cudaGetErrorString(e__));                                      \
+      return LRVB_ECUDA;                                                             \
+    }                                                                                \
+  } while (0)
+
+#define LRVB_CHECK_LAUNCH() LRVB_CUDA(cudaGetLastError())
+
+#define LRVB_REQUIRE(cond, ...)                                                      \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      lrvb::set_error(__VA_ARGS__);                                                  \
+      return LRVB_EINVAL;                                                            \
+    }                                                                                \
+  } while (0)
+
+#define LRVB_TRY(expr)                                                               \
+  do {                                                                               \
+    int rc__ = (expr);                                                               \
+    if (rc__ != LRVB_OK) return rc__;                                                \
+  } while (0)
+
+constexpr int kMaxQ = 64;
+constexpr int kMaxK = 256;
+constexpr int kNumSMs = 148;  // B200
+constexpr int kRT = 4;        // Gram warp job = kRT x kRT output tiles of 8x8
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- fp64 special functions the CUDA math library lacks -------------------------------
+// digamma / trigamma / tetragamma for x > 0: upward recurrence to x >= 16, then the
+// asymptotic (Bernoulli) series; truncation < 1e-17 relative there.
+__host__ __device__ inline double digamma_pos(double x) {
+  double acc = 0.0;
+  while (x < 16.0) { acc -= 1.0 / x; x += 1.0; }
+  const double r = 1.0 / x, r2 = r * r;
+  double s = r2 * (1.0 / 12.0 - r2 * (1.0 / 120.0 - r2 * (1.0 / 252.0 - r2 * (1.0 / 240.0 -
+             r2 * (1.0 / 132.0 - r2 * (691.0 / 32760.0 - r2 * (1.0 / 12.0)))))));
+  return acc + log(x) - 0.5 * r - s;
+}
+__host__ __device__ inline double trigamma_pos(double x) {
+  double acc = 0.0;
+  while (x < 16.0) { acc += 1.0 / (x * x); x += 1.0; }
+  const double r = 1.0 / x, r2 = r * r;
+  double s = r * r2 * (1.0 / 6.0 - r2 * (1.0 / 30.0 - r2 * (1.0 / 42.0 - r2 * (1.0 / 30.0 -
+             r2 * (5.0 / 66.0 - r2 * (691.0 / 2730.0 - r2 * (7.0 / 6.0)))))));
+  return acc + r + 0.5 * r2 + s;
+}
+__host__ __device__ inline double tetragamma_pos(double x) {
+  double acc = 0.0;
+  while (x < 16.0) { acc -= 2.0 / (x * x * x); x += 1.0; }
+  const double r = 1.0 / x, r2 = r * r;
+  double s = r2 * r2 * (0.5 - r2 * (1.0 / 6.0 - r2 * (1.0 / 6.0 - r2 * (3.0 / 10.0 -
+             r2 * (5.0 / 6.0 - r2 * (691.0 / 210.0 - r2 * (35.0 / 2.0)))))));
+  return acc - r2 - r * r2 - s;
+}
+
+#ifdef __CUDACC__
+// ---- warp / block helpers ----------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum with a fixed (deterministic) tree; result valid in thread 0.
+// `red` is shared scratch of >= 32 doubles.  All threads must call.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
+//   a : A[lane>>2][lane&3]      b : B[lane&3][lane>>2]      c0,c1 : C[lane>>2][2*(lane&3)+{0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Copy `n` contiguous doubles global -> shared with cp.async (16 B chunks when both sides are
+// 16-B aligned, 8 B otherwise).  All threads of the CTA call; caller commits / waits / syncs.
+__device__ __forceinline__ void tile_load_async(double* dst, const double* src, int64_t n) {
+  const bool al16 = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+  if (al16) {
+    const int64_t n2 = n >> 1;
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) cp_async16(dst + 2 * i, src + 2 * i);
+    if ((n & 1) && threadIdx.x == 0) cp_async8(dst + n - 1, src + n - 1);
+  } else {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) cp_async8(dst + i, src + i);
+  }
+}
+#endif  // __CUDACC__
+
+// Gram warp-job: a kRT x kRT rectangle of 8x8 output tiles inside one of the three families
+// fam 0: X^T diag(a) X   fam 1: X^T diag(b) S   fam 2: S^T diag(c) S      (S = X*X elementwise)
+struct GramJob {
+  int fam, i0, j0, pad;
+};
+
+}  // namespace lrvb
+
+// ---- the model handle --------------------------------------------------------------------
+struct lrvb_glmm {
+  int64_t N = 0, D = 0;
+  int K = 0, G = 0, Q = 0, Dg = 0, KT = 0;  // KT = ceil(K/8) feature tiles
+  int include_global = 1;
+  int vecmode = 0;            // 1: evaluate in the constrained ("vector") parameterisation
+  const double *X = nullptr, *y = nullptr, *w = nullptr;
+  const int32_t* g = nullptr;
+  lrvb_glmm_prior prior;
+  lrvb_glmm_bounds bounds;
+  // ---- device-owned ----
+  double* gh = nullptr;       // [2][Q]: c_q = sqrt(2) x_q ; what_q = w_q / sqrt(pi)
+  int32_t* gptr = nullptr;    // (G+1) first observation of each group
+  double* vec = nullptr;      // (D) constrained values
+  double* W = nullptr;        // (5, N) per-observation derivative weights
+  // observation pass
+  int obs_tn = 0, obs_grid = 0;
+  size_t obs_smem = 0;
+  double* klpart = nullptr;   // (obs_grid) per-CTA partials of sum w*l
+  double* gradpart = nullptr; // (obs_grid, 2, K) per-CTA partials of X^T l_m , S^T l_v
+  // group pass
+  double* gsc = nullptr;      // (G, 5) per-group sums of l_m, l_v, a, b, c
+  double* BR = nullptr;       // (G, 4, K) raw borders: sum a x, sum b x, sum b s, sum c s
+  int loc_grid = 0;
+  double* locpart = nullptr;  // (loc_grid, 4) partials of sum dm, sum Sg, sum log u_info, -
+  // Gram
+  int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0, gram_jpc = 0, gram_split = 0;
+  size_t gram_smem = 0;
+  lrvb::GramJob* jobs = nullptr;   // device (gram_jobs)
+  double* grampart = nullptr;      // (gram_grid_x, gram_jobs, kRT*kRT, 64)
+  // results
+  double *A = nullptr, *B = nullptr, *L = nullptr;  // cached Hessian blocks (free coords)
+  double* gradl = nullptr;    // (2G) local gradient of the last eval
+  double* outg = nullptr;     // (1 + Dg + Dg*Dg) packed [KL, grad_g, A] of the last eval
+  int hess_valid = 0;
+  int grad_valid = 0;
+  // CSR
+  int32_t* rowcnt = nullptr;  // (D+1)
+  int32_t* scanblk = nullptr; // scan scratch
+  int64_t csr_nnz = -1;
+  // solver scratch
+  double* cgbuf = nullptr;    // 6*D
+  int hvp_grid = 0;
+  double* hvppart = nullptr;  // (hvp_grid, Dg)
+  int dot_grid = 0;
+  double* dotpart = nullptr;  // (dot_grid, 4)
+  double* scal = nullptr;     // device scalars (32)
+  int* flags = nullptr;       // device ints (8)
+  double* Linv = nullptr;     // (G,3) inverse local blocks (Schur / precond)
+  double* T = nullptr;        // (G,2,Dg) L^-1 B for the Schur path
+  int schur_grid = 0;
+  double* schurpart = nullptr;
+};
+
+namespace lrvb {
+// kernels.cu entry points used by api.cu (all enqueue on `st`)
+int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_global,
+                double* grad_local, cudaStream_t st);
+}  // namespace lrvb

@@ -1,0 +1,770 @@
+// ELBO (KL) value, gradient and arrowhead Hessian blocks of the logistic GLMM, fp64, sm_100a.
+//
+// Replaces, for the composed GLMM objective, what the reference obtains by
+// running autograd over Modeling.py:35-52 (get_e_logistic_term_guass_hermite),
+// ExponentialFamilies.py:23-35,111-112,186-195 and the constraining transforms of
+// Parameters.py:47-61, i.e. Objective.fun_free / fun_free_grad / fun_free_hessian
+// (SparseObjectives.py:120-158) plus convert_vector_to_free_hessian (Parameters.py:397-424).
+//
+// Pipeline of one evaluation (all on one stream, no atomics, fixed reduction orders so the
+// result is bitwise reproducible for a given launch geometry):
+//   k_prep         free -> constrained vector
+//   k_obs          per-observation pass: z_mean/z_var, Gauss-Hermite softplus / sigma / sigma',
+//                  analytic l, dl, d2l; per-CTA partials of KL and of X^T l_m, S^T l_v
+//   k_group        per-group segmented sums (observations are group-sorted): scalars + borders
+//   k_gram         X^T diag(a) X, X^T diag(b) S, S^T diag(c) S on the FP64 tensor cores (DMMA)
+//   k_local/k_border/k_gram_finish/k_global   chain rule to free coordinates, non-data terms
+#include "common.cuh"
+
+namespace lrvb {
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_prep(const double* __restrict__ free_v, double* __restrict__ vec, int K, int G,
+                       lrvb_glmm_bounds bd, int vecmode) {
+  const int64_t D = 4 + 2 * (int64_t)K + 2 * (int64_t)G;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  const double f = free_v[i];
+  double lb = 0.0;
+  bool con = true;
+  if (i == 0) con = false;
+  else if (i == 1) lb = bd.mu_info;
+  else if (i == 2) lb = bd.tau_shape;
+  else if (i == 3) lb = bd.tau_rate;
+  else if (i < 4 + K) con = false;
+  else if (i < 4 + 2 * K) lb = bd.beta_info;
+  else if (i < 4 + 2 * K + G) con = false;
+  else lb = bd.u_info;
+  vec[i] = (con && !vecmode) ? exp(f) + lb : f;   // Parameters.py:53-55
+}
+
+// ------------------------------------------------------------------------------------------
+// Gauss-Hermite node: softplus(t), sigma(t), sigma'(t) from ONE exp.
+// Modeling.py:48 evaluates log1p(exp(t)) unstabilised; this is the same function to <= 1 ulp
+// on the finite range and stays finite beyond it.
+struct GHSums {
+  double A, Am, As, Amm, Ams, Ass;
+};
+
+template <int ORDER>
+__device__ __forceinline__ void gh_node(double t, double c, double wq, GHSums& s) {
+  const double e = exp(-fabs(t));
+  const double sp = fmax(t, 0.0) + log1p(e);
+  s.A = fma(wq, sp, s.A);
+  if (ORDER >= 1) {
+    const double r = 1.0 / (1.0 + e);
+    const double sg = (t >= 0.0) ? r : e * r;
+    const double wsg = wq * sg;
+    s.Am += wsg;
+    s.As = fma(wsg, c, s.As);
+    if (ORDER >= 2) {
+      const double wd = wq * (e * r * r);
+      const double wdc = wd * c;
+      s.Amm += wd;
+      s.Ams += wdc;
+      s.Ass = fma(wdc, c, s.Ass);
+    }
+  }
+}
+
+// One thread per observation of a TN-row tile staged in shared memory (blockDim.x == TN).
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
+      const double* __restrict__ w, const double* __restrict__ vec, const double* __restrict__ gh,
+      double* __restrict__ W, double* __restrict__ klpart, double* __restrict__ gradpart,
+      int64_t N, int K, int G, int Q) {
+  extern __shared__ __align__(16) double sm[];
+  const int TN = blockDim.x;
+  const int tid = threadIdx.x;
+  double* xs = sm;                  // TN*K
+  double* bm = xs + (size_t)TN * K; // K   E[beta]
+  double* bv = bm + K;              // K   Var[beta] = 1/info
+  double* ghc = bv + K;             // Q   sqrt(2) x_q
+  double* ghw = ghc + Q;            // Q   w_q / sqrt(pi)
+  double* lms = ghw + Q;            // TN
+  double* lvs = lms + TN;           // TN
+  double* red = lvs + TN;           // 32
+
+  for (int k = tid; k < K; k += TN) {
+    bm[k] = vec[4 + k];
+    bv[k] = 1.0 / vec[4 + K + k];
+  }
+  for (int q = tid; q < Q; q += TN) {
+    ghc[q] = gh[q];
+    ghw[q] = gh[Q + q];
+  }
+  const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
+
+  // bank-conflict skew for the row-per-thread reads of the tile (row stride K doubles)
+  int gcd16 = 1;
+  while (gcd16 < 16 && (K % (gcd16 * 2)) == 0) gcd16 *= 2;
+  int skew = ((tid & 15) * gcd16) >> 4;
+  if (skew >= K) skew = 0;
+
+  // gradient column ownership
+  const bool caseA = (K <= TN);
+  const int P = caseA ? TN / K : 1;
+  const int ncol = caseA ? 1 : (K + TN - 1) / TN;
+  const int colA = caseA ? tid % K : tid;
+  const int partA = caseA ? tid / K : 0;
+  double gm[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};
+  double klacc = 0.0;
+
+  const int64_t ntiles = (N + TN - 1) / TN;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t n0 = tile * TN;
+    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
+    __syncthreads();  // previous tile fully consumed (also orders the bm/bv/gh fill)
+    tile_load_async(xs, X + n0 * K, (int64_t)rows * K);
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    double lm = 0.0, lv = 0.0;
+    if (tid < rows) {
+      const int64_t n = n0 + tid;
+      const int gi = g[n];
+      double zm = vec[um0 + gi];
+      double zv = 1.0 / vec[ui0 + gi];
+      const double* xr = xs + (size_t)tid * K;
+      for (int k = skew; k < K; ++k) {
+        const double x = xr[k];
+        zm = fma(x, bm[k], zm);
+        zv = fma(x * x, bv[k], zv);
+      }
+      for (int k = 0; k < skew; ++k) {
+        const double x = xr[k];
+        zm = fma(x, bm[k], zm);
+        zv = fma(x * x, bv[k], zv);
+      }
+      const double zs = sqrt(zv);
+      GHSums s = {0, 0, 0, 0, 0, 0};
+      for (int q = 0; q < Q; ++q) {
+        const double c = ghc[q];
+        gh_node<ORDER>(fma(zs, c, zm), c, ghw[q], s);
+      }
+      const double wn = w ? w[n] : 1.0;
+      const double yn = y[n];
+      klacc += wn * (yn * zm - s.A);
+      if (ORDER >= 1) {
+        const double h = 0.5 / zs;
+        lm = wn * (yn - s.Am);
+        lv = -wn * s.As * h;
+        W[n] = lm;
+        W[N + n] = lv;
+        if (ORDER >= 2) {
+          W[2 * N + n] = -wn * s.Amm;
+          W[3 * N + n] = -wn * s.Ams * h;
+          // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
+          W[4 * N + n] = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
+        }
+      }
+    }
+    if (ORDER >= 1) {
+      lms[tid] = lm;
+      lvs[tid] = lv;
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < ncol) {
+          const int k = colA + c * TN;
+          if (k < K && partA < P) {
+            double am = 0.0, av = 0.0;
+            for (int r = partA; r < rows; r += P) {
+              const double x = xs[(size_t)r * K + k];
+              am = fma(x, lms[r], am);
+              av = fma(x * x, lvs[r], av);
+            }
+            gm[c] += am;
+            gv[c] += av;
+          }
+        }
+      }
+    }
+  }
+
+  const double kl = block_sum(klacc, red);
+  if (tid == 0) klpart[blockIdx.x] = kl;
+  if (ORDER >= 1) {
+    double* gp = gradpart + (size_t)blockIdx.x * 2 * K;
+    if (caseA) {
+      __syncthreads();
+      double* buf = xs;  // P*K*2 <= TN*K*... needs 2*P*K <= TN*K  (K >= 2) or falls in lms
+      // stage [part][2][K]; for K == 1 use lms/lvs-sized scratch carefully
+      if (partA < P) {
+        buf[(size_t)partA * 2 * K + colA] = gm[0];
+        buf[(size_t)partA * 2 * K + K + colA] = gv[0];
+      }
+      __syncthreads();
+      if (tid < 2 * K) {
+        double s = 0.0;
+        for (int p = 0; p < P; ++p) s += buf[(size_t)p * 2 * K + tid];
+        gp[tid] = s;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = tid + c * TN;
+        if (c < ncol && k < K) {
+          gp[k] = gm[c];
+          gp[K + k] = gv[c];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-group segmented sums.  One warp per group (grid-stride); observations of a group are
+// the contiguous range [gptr[g], gptr[g+1]) so no atomics are needed and the summation order
+// is fixed.  gsc (G,5): sums of l_m, l_v, a, b, c.  BR (G,4,K): sum a x, sum b x, sum b s, sum c s.
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_group(const double* __restrict__ X, const double* __restrict__ W,
+        const int32_t* __restrict__ gptr, double* __restrict__ gsc, double* __restrict__ BR,
+        int64_t N, int K, int G) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nrow = (ORDER >= 2) ? 5 : 2;
+  for (int gi = blockIdx.x * wpb + (threadIdx.x >> 5); gi < G; gi += gridDim.x * wpb) {
+    const int64_t nb = gptr[gi], ne = gptr[gi + 1];
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int64_t n = nb + lane; n < ne; n += 32) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+        if (r < nrow) s[r] += W[r * N + n];
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+      if (r < nrow) s[r] = warp_sum(s[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) gsc[(size_t)gi * 5 + r] = (r < nrow) ? s[r] : 0.0;
+    }
+    if (ORDER >= 2) {
+      const double* Wa = W + 2 * N;
+      const double* Wb = W + 3 * N;
+      const double* Wc = W + 4 * N;
+      for (int k = lane; k < K; k += 32) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int64_t n = nb;
+        for (; n + 4 <= ne; n += 4) {
+          double x[4], a[4], b[4], c[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            x[u] = X[(n + u) * K + k];
+            a[u] = Wa[n + u];
+            b[u] = Wb[n + u];
+            c[u] = Wc[n + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double xx = x[u] * x[u];
+            s0 = fma(a[u], x[u], s0);
+            s1 = fma(b[u], x[u], s1);
+            s2 = fma(b[u], xx, s2);
+            s3 = fma(c[u], xx, s3);
+          }
+        }
+        for (; n < ne; ++n) {
+          const double x = X[n * K + k], xx = x * x;
+          s0 = fma(Wa[n], x, s0);
+          s1 = fma(Wb[n], x, s1);
+          s2 = fma(Wb[n], xx, s2);
+          s3 = fma(Wc[n], xx, s3);
+        }
+        double* br = BR + (size_t)gi * 4 * K;
+        br[k] = s0;
+        br[K + k] = s1;
+        br[2 * K + k] = s2;
+        br[3 * K + k] = s3;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weighted Grams on the FP64 tensor cores.  Each warp owns one GramJob (a kRT x kRT rectangle
+// of 8x8 output tiles of one family) for a subset of the 4-observation k-steps of every tile;
+// mma.m8n8k4: A[i][k] = F1[n0+k][8 it + i], B[k][j] = wgt[n0+k] * F2[n0+k][8 jt + j], so lane l
+// reads row n0 + (l&3), column 8 t + (l>>2) for both operands.
+__global__ void __launch_bounds__(256, 2)
+k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob* __restrict__ jobs,
+       double* __restrict__ grampart, int64_t N, int K, int KT, int TN, int n_jobs, int jpc,
+       int n_split, int ny, int n_chunk) {
+  extern __shared__ __align__(16) double sm[];
+  double* xs = sm;                       // TN*K
+  double* wgt = xs + (size_t)TN * K;     // 3*TN : a, b, c
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jg = blockIdx.x % ny;
+  const int chunk = blockIdx.x / ny;
+  const int jl = warp % jpc, split = warp / jpc;
+  const int job = jg * jpc + jl;
+  const bool active = (job < n_jobs) && (split < n_split);
+  GramJob jb = {0, 0, 0, 0};
+  if (active) jb = jobs[job];
+  const int fam = jb.fam;
+
+  double acc[kRT][kRT][2];
+#pragma unroll
+  for (int i = 0; i < kRT; ++i)
+#pragma unroll
+    for (int j = 0; j < kRT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // per-lane column of each tile and validity masks (warp-uniform parts hoisted)
+  const int lr = lane & 3, lc = lane >> 2;
+  int cola[kRT], colb[kRT];
+  unsigned tmask = 0;  // bit i*kRT+j : tile (i,j) computed
+#pragma unroll
+  for (int i = 0; i < kRT; ++i) {
+    cola[i] = 8 * (jb.i0 + i) + lc;
+    colb[i] = 8 * (jb.j0 + i) + lc;
+  }
+#pragma unroll
+  for (int i = 0; i < kRT; ++i)
+#pragma unroll
+    for (int j = 0; j < kRT; ++j) {
+      const int it = jb.i0 + i, jt = jb.j0 + j;
+      if (active && it < KT && jt < KT && (fam == 1 || it <= jt)) tmask |= 1u << (i * kRT + j);
+    }
+  const double* wsel = wgt + (size_t)fam * TN;
+
+  const int64_t ntiles = (N + TN - 1) / TN;
+  for (int64_t tile = chunk; tile < ntiles; tile += n_chunk) {
+    const int64_t n0 = tile * TN;
+    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
+    __syncthreads();
+    tile_load_async(xs, X + n0 * K, (int64_t)rows * K);
+    for (int r = tid; r < 3 * TN; r += blockDim.x) {
+      const int f = r / TN, n = r - f * TN;
+      wgt[r] = (n < rows) ? W[(int64_t)(2 + f) * N + n0 + n] : 0.0;
+    }
+    if (rows < TN)
+      for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) xs[e] = 0.0;
+    cp_async_commit_wait_all();
+    __syncthreads();
+    if (tmask) {
+      const int ksteps = (rows + 3) >> 2;
+      for (int ks = split; ks < ksteps; ks += n_split) {
+        const int n = 4 * ks + lr;
+        const double* xr = xs + (size_t)n * K;
+        const double wv = wsel[n];
+        double fa[kRT], fb[kRT];
+#pragma unroll
+        for (int i = 0; i < kRT; ++i) {
+          double xa = (cola[i] < K) ? xr[cola[i]] : 0.0;
+          double xb = (colb[i] < K) ? xr[colb[i]] : 0.0;
+          if (fam == 2) xa *= xa;
+          if (fam >= 1) xb *= xb;
+          fa[i] = xa;
+          fb[i] = xb * wv;
+        }
+#pragma unroll
+        for (int i = 0; i < kRT; ++i)
+#pragma unroll
+          for (int j = 0; j < kRT; ++j)
+            if (tmask & (1u << (i * kRT + j))) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    }
+  }
+
+  // in-CTA reduction over the k-step splits (fixed order), then one partial per (chunk, job)
+  __syncthreads();
+  double* red = sm;  // jpc * kRT*kRT*64 doubles when n_split > 1
+  const int crow = lane >> 2, ccol = 2 * (lane & 3);
+  if (n_split > 1) {
+    for (int s = 0; s < n_split; ++s) {
+      if (active && split == s) {
+#pragma unroll
+        for (int i = 0; i < kRT; ++i)
+#pragma unroll
+          for (int j = 0; j < kRT; ++j)
+            if (tmask & (1u << (i * kRT + j))) {
+              double* t = red + ((size_t)jl * kRT * kRT + i * kRT + j) * 64 + crow * 8 + ccol;
+              if (s == 0) { t[0] = acc[i][j][0]; t[1] = acc[i][j][1]; }
+              else { t[0] += acc[i][j][0]; t[1] += acc[i][j][1]; }
+            }
+      }
+      __syncthreads();
+    }
+    if (active && split == 0) {
+#pragma unroll
+      for (int i = 0; i < kRT; ++i)
+#pragma unroll
+        for (int j = 0; j < kRT; ++j)
+          if (tmask & (1u << (i * kRT + j))) {
+            const double* t = red + ((size_t)jl * kRT * kRT + i * kRT + j) * 64 + crow * 8 + ccol;
+            acc[i][j][0] = t[0];
+            acc[i][j][1] = t[1];
+          }
+    }
+  }
+  if (active && split == 0) {
+    double* out = grampart + ((size_t)chunk * n_jobs + job) * (kRT * kRT * 64);
+#pragma unroll
+    for (int i = 0; i < kRT; ++i)
+#pragma unroll
+      for (int j = 0; j < kRT; ++j)
+        if (tmask & (1u << (i * kRT + j))) {
+          double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+          *reinterpret_cast<double2*>(out + (i * kRT + j) * 64 + crow * 8 + ccol) = v;
+        }
+  }
+}
+
+// Sum the Gram partials over chunks (fixed order) and write the beta block of A in FREE
+// coordinates: A = -(d2F/dvec2) * j_i j_j  (the diagonal extras are added by k_global).
+// One CTA (256 threads) per (job, tile-in-rectangle).
+__global__ void __launch_bounds__(256)
+k_gram_finish(const double* __restrict__ grampart, const GramJob* __restrict__ jobs,
+              const double* __restrict__ vec, double* __restrict__ A, int K, int KT, int Dg,
+              int n_jobs, int n_chunk, lrvb_glmm_bounds bd, int vecmode) {
+  __shared__ double red[4][64];
+  const int job = blockIdx.x / (kRT * kRT);
+  const int t = blockIdx.x % (kRT * kRT);
+  const GramJob jb = jobs[job];
+  const int it = jb.i0 + t / kRT, jt = jb.j0 + t % kRT;
+  if (it >= KT || jt >= KT || (jb.fam != 1 && it > jt)) return;
+  const int e = threadIdx.x & 63, ps = threadIdx.x >> 6;
+  const double* src = grampart + ((size_t)job * kRT * kRT + t) * 64 + e;
+  const size_t stride = (size_t)n_jobs * kRT * kRT * 64;
+  double s = 0.0;
+#pragma unroll 8
+  for (int p = ps; p < n_chunk; p += 4) s += src[(size_t)p * stride];
+  red[ps][e] = s;
+  __syncthreads();
+  if (ps != 0) return;
+  s = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+  const int p = 8 * it + (e >> 3), q = 8 * jt + (e & 7);
+  if (p >= K || q >= K) return;
+  const int bm0 = 4, bi0 = 4 + K;
+  if (jb.fam == 0) {
+    if (it == jt && p > q) return;          // use the upper triangle of diagonal tiles
+    const double v = -s;                     // beta.mean is unconstrained: j = 1
+    A[(size_t)(bm0 + p) * Dg + bm0 + q] = v;
+    A[(size_t)(bm0 + q) * Dg + bm0 + p] = v;
+  } else if (jb.fam == 1) {
+    const double iq = vec[bi0 + q];
+    const double v = -s * (-1.0 / (iq * iq)) * (vecmode ? 1.0 : iq - bd.beta_info);
+    A[(size_t)(bm0 + p) * Dg + bi0 + q] = v;
+    A[(size_t)(bi0 + q) * Dg + bm0 + p] = v;
+  } else {
+    if (it == jt && p > q) return;
+    const double ip = vec[bi0 + p], iq = vec[bi0 + q];
+    const double v = -s * (1.0 / (ip * ip * iq * iq)) * (vecmode ? 1.0 : (ip - bd.beta_info) * (iq - bd.beta_info));
+    A[(size_t)(bi0 + p) * Dg + bi0 + q] = v;
+    A[(size_t)(bi0 + q) * Dg + bi0 + p] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Group-level chain rule: local gradient, local 2x2 blocks, and partial sums of the
+// random-effect term  sum_g [-1/2 E[tau]((E mu - E u_g)^2 + Var mu + Var u_g) + 1/2 E log tau]
+// (GammaParams.py:9-13, NormalParams.py:58-63).
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_local(const double* __restrict__ vec, const double* __restrict__ gsc,
+        double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ locpart,
+        int K, int G, lrvb_glmm_bounds bd, int vecmode) {
+  __shared__ double red[32];
+  const int Dg = 4 + 2 * K;
+  const double mu_m = vec[0], mu_i = vec[1], a = vec[2], b = vec[3];
+  const double E = a / b;
+  double dsum = 0.0, ssum = 0.0, lsum = 0.0;
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < G; gi += gridDim.x * blockDim.x) {
+    const double um = vec[Dg + gi], ui = vec[Dg + G + gi];
+    const double dm = mu_m - um;
+    const double r = 1.0 / ui;
+    dsum += dm;
+    ssum += dm * dm + 1.0 / mu_i + r;
+    lsum += log(ui);
+    if (ORDER >= 1) {
+      const double* s = gsc + (size_t)gi * 5;
+      const double r2 = r * r;
+      const double gF_um = s[0] + E * dm;
+      const double gF_ui = -s[1] * r2 + 0.5 * E * r2 - 0.5 * r;
+      // d info / d free = d2 info / d free2 = info - lb (Parameters.py:55); identity in vector mode
+      const double ji = vecmode ? 1.0 : ui - bd.u_info;
+      const double ji2 = vecmode ? 0.0 : ji;
+      const double gv_ui = -gF_ui;
+      gradl[gi] = -gF_um;
+      gradl[G + gi] = gv_ui * ji;
+      if (ORDER >= 2) {
+        const double dr = -r2;
+        const double L0 = s[2] - E;
+        const double L1 = s[3] * dr;
+        const double L2 = s[4] * dr * dr + s[1] * 2.0 * r2 * r - E * r2 * r + 0.5 * r2;
+        L[(size_t)gi * 3 + 0] = -L0;
+        L[(size_t)gi * 3 + 1] = -L1 * ji;
+        L[(size_t)gi * 3 + 2] = -L2 * ji * ji + gv_ui * ji2;
+      }
+    }
+  }
+  dsum = block_sum(dsum, red);
+  ssum = block_sum(ssum, red);
+  lsum = block_sum(lsum, red);
+  if (threadIdx.x == 0) {
+    locpart[blockIdx.x * 4 + 0] = dsum;
+    locpart[blockIdx.x * 4 + 1] = ssum;
+    locpart[blockIdx.x * 4 + 2] = lsum;
+    locpart[blockIdx.x * 4 + 3] = 0.0;
+  }
+}
+
+// Border rows B (G,2,Dg) in free coordinates: row 0 = (u.mean_g, globals), row 1 = (u.info_g, .)
+__global__ void __launch_bounds__(256)
+k_border(const double* __restrict__ vec, const double* __restrict__ BR, double* __restrict__ B,
+         int K, int G, lrvb_glmm_bounds bd, int vecmode) {
+  const int Dg = 4 + 2 * K;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * Dg) return;
+  const int gi = (int)(idx / Dg), col = (int)(idx - (int64_t)gi * Dg);
+  const double mu_m = vec[0], a = vec[2], b = vec[3];
+  const double um = vec[Dg + gi], ui = vec[Dg + G + gi];
+  const double r2 = 1.0 / (ui * ui);
+  const double dr = -r2;
+  const double ji = ui - bd.u_info;
+  double b0, b1, jg = 1.0;
+  if (col == 0) { b0 = a / b; b1 = 0.0; }
+  else if (col == 1) { b0 = 0.0; b1 = 0.0; jg = vec[1] - bd.mu_info; }
+  else if (col == 2) { b0 = (mu_m - um) / b; b1 = 0.5 * r2 / b; jg = a - bd.tau_shape; }
+  else if (col == 3) { b0 = -a * (mu_m - um) / (b * b); b1 = -0.5 * a * r2 / (b * b); jg = b - bd.tau_rate; }
+  else if (col < 4 + K) {
+    const int k = col - 4;
+    const double* br = BR + (size_t)gi * 4 * K;
+    b0 = br[k];
+    b1 = br[K + k] * dr;
+  } else {
+    const int k = col - 4 - K;
+    const double* br = BR + (size_t)gi * 4 * K;
+    const double ik = vec[4 + K + k];
+    const double dv = -1.0 / (ik * ik);
+    jg = ik - bd.beta_info;
+    b0 = br[2 * K + k] * dv;
+    b1 = br[3 * K + k] * dv * dr;
+  }
+  double* out = B + (size_t)gi * 2 * Dg;
+  if (vecmode) jg = 1.0;
+  out[col] = -b0 * jg;
+  out[Dg + col] = -b1 * jg * (vecmode ? 1.0 : ji);
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-CTA finish: fixed-order sums of the per-CTA partials, the non-data terms
+// (ExponentialFamilies.py:23-25 uvn entropy, :33-35 gamma entropy, :111-112 E log tau,
+// :191-195 priors), the global gradient and the 4x4 corner / diagonal extras of A,
+// then the vector->free chain rule (Parameters.py:397-424 for diagonal transforms).
+// out = [KL, grad_g (Dg), A (Dg*Dg)].
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int n_kl,
+         const double* __restrict__ gradpart, int n_gp, const double* __restrict__ locpart,
+         int n_lp, double* __restrict__ out, int K, int G, lrvb_glmm_prior pr,
+         lrvb_glmm_bounds bd, int include_global, int vecmode) {
+  __shared__ double red[32];
+  __shared__ double sh[8];
+  extern __shared__ double gsum[];  // 2K
+  const int tid = threadIdx.x;
+  const int Dg = 4 + 2 * K;
+  double v = 0.0;
+  for (int i = tid; i < n_kl; i += blockDim.x) v += klpart[i];
+  const double data_ll = block_sum(v, red);
+  double d0 = 0, d1 = 0, d2 = 0;
+  for (int i = tid; i < n_lp; i += blockDim.x) {
+    d0 += locpart[i * 4 + 0];
+    d1 += locpart[i * 4 + 1];
+    d2 += locpart[i * 4 + 2];
+  }
+  d0 = block_sum(d0, red);
+  d1 = block_sum(d1, red);
+  d2 = block_sum(d2, red);
+  if (tid == 0) { sh[0] = data_ll; sh[1] = d0; sh[2] = d1; sh[3] = d2; }
+  if (ORDER >= 1) {
+    for (int k = tid; k < 2 * K; k += blockDim.x) {
+      double s = 0.0;
+      for (int p = 0; p < n_gp; ++p) s += gradpart[(size_t)p * 2 * K + k];
+      gsum[k] = s;
+    }
+  }
+  __syncthreads();
+  const double ll = sh[0], dsum = sh[1], Ssum = sh[2], logsum = sh[3];
+  const double mu_m = vec[0], mu_i = vec[1], a = vec[2], b = vec[3];
+  const double Gl = (double)G;
+  const double E = a / b;
+  const double l2pi = 1.8378770664093454836;  // log(2 pi)
+  double* grad = out + 1;
+  double* A = out + 1 + Dg;
+
+  if (tid == 0) {
+    const double psi = digamma_pos(a), psi1 = trigamma_pos(a), psi2 = tetragamma_pos(a);
+    const double elt = psi - log(b);
+    double F = ll - 0.5 * E * Ssum + 0.5 * Gl * elt + 0.5 * (-logsum + Gl * (1.0 + l2pi));
+    double g0 = -E * dsum;
+    double g1 = 0.5 * E * Gl / (mu_i * mu_i);
+    double g2 = -0.5 * Ssum / b + 0.5 * Gl * psi1;
+    double g3 = 0.5 * a * Ssum / (b * b) - 0.5 * Gl / b;
+    double a00 = -E * Gl, a02 = -dsum / b, a03 = a * dsum / (b * b);
+    double a11 = -E * Gl / (mu_i * mu_i * mu_i);
+    double a12 = 0.5 * Gl / (b * mu_i * mu_i), a13 = -0.5 * a * Gl / (b * b * mu_i * mu_i);
+    double a22 = 0.5 * Gl * psi2, a23 = 0.5 * Ssum / (b * b);
+    double a33 = -a * Ssum / (b * b * b) + 0.5 * Gl / (b * b);
+    if (include_global) {
+      F += 0.5 * (-log(mu_i) + 1.0 + l2pi) + a - log(b) + lgamma(a) + (1.0 - a) * psi;
+      F += -0.5 * pr.mu_info * ((mu_m - pr.mu_mean) * (mu_m - pr.mu_mean) + 1.0 / mu_i);
+      F += (pr.tau_shape - 1.0) * elt - pr.tau_rate * E;
+      g0 += -pr.mu_info * (mu_m - pr.mu_mean);
+      g1 += -0.5 / mu_i + 0.5 * pr.mu_info / (mu_i * mu_i);
+      g2 += 1.0 + (1.0 - a) * psi1 + (pr.tau_shape - 1.0) * psi1 - pr.tau_rate / b;
+      g3 += -1.0 / b - (pr.tau_shape - 1.0) / b + pr.tau_rate * a / (b * b);
+      a00 += -pr.mu_info;
+      a11 += 0.5 / (mu_i * mu_i) - pr.mu_info / (mu_i * mu_i * mu_i);
+      a22 += -psi1 + (1.0 - a) * psi2 + (pr.tau_shape - 1.0) * psi2;
+      a23 += pr.tau_rate / (b * b);
+      a33 += 1.0 / (b * b) + (pr.tau_shape - 1.0) / (b * b) - 2.0 * pr.tau_rate * a / (b * b * b);
+    }
+    sh[4] = F;
+    if (ORDER >= 1) {
+      const double j1 = vecmode ? 1.0 : mu_i - bd.mu_info, j2 = vecmode ? 1.0 : a - bd.tau_shape,
+                   j3 = vecmode ? 1.0 : b - bd.tau_rate;
+      grad[0] = -g0;
+      grad[1] = -g1 * j1;
+      grad[2] = -g2 * j2;
+      grad[3] = -g3 * j3;
+      if (ORDER >= 2) {
+        const double jj[4] = {1.0, j1, j2, j3};
+        const double gvv[4] = {-g0, -g1, -g2, -g3};
+        const double m[4][4] = {{a00, 0.0, a02, a03}, {0.0, a11, a12, a13},
+                                {a02, a12, a22, a23}, {a03, a13, a23, a33}};
+        for (int r = 0; r < 4; ++r)
+          for (int c = 0; c < 4; ++c) {
+            double h = -m[r][c] * jj[r] * jj[c];
+            if (r == c && r > 0 && !vecmode) h += gvv[r] * jj[r];
+            A[(size_t)r * Dg + c] = h;
+          }
+      }
+    }
+  }
+  // beta entries: entropy + prior + data gradient, diagonal extras of A
+  double fpart = 0.0;
+  for (int k = tid; k < K; k += blockDim.x) {
+    const double bmk = vec[4 + k], bik = vec[4 + K + k];
+    const double rb = 1.0 / bik;
+    if (include_global) {
+      fpart += 0.5 * (-log(bik) + 1.0 + l2pi)
+             - 0.5 * pr.beta_info * ((bmk - pr.beta_mean) * (bmk - pr.beta_mean) + rb);
+    }
+    if (ORDER >= 1) {
+      double gbm = gsum[k];
+      double gbi = -gsum[K + k] * rb * rb;
+      if (include_global) {
+        gbm += -pr.beta_info * (bmk - pr.beta_mean);
+        gbi += -0.5 * rb + 0.5 * pr.beta_info * rb * rb;
+      }
+      const double jb = vecmode ? 1.0 : bik - bd.beta_info;
+      grad[4 + k] = -gbm;
+      grad[4 + K + k] = -gbi * jb;
+      if (ORDER >= 2) {
+        double emm = 0.0;
+        double eii = gsum[K + k] * 2.0 * rb * rb * rb;
+        if (include_global) {
+          emm += -pr.beta_info;
+          eii += 0.5 * rb * rb - pr.beta_info * rb * rb * rb;
+        }
+        A[(size_t)(4 + k) * Dg + 4 + k] += -emm;
+        A[(size_t)(4 + K + k) * Dg + 4 + K + k] += -eii * jb * jb + (vecmode ? 0.0 : (-gbi) * jb);
+      }
+    }
+  }
+  fpart = block_sum(fpart, red);
+  if (tid == 0) out[0] = -(sh[4] + fpart);
+}
+
+// ------------------------------------------------------------------------------------------
+int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_global,
+                double* grad_local, cudaStream_t st) {
+  const int K = h->K, G = h->G, Q = h->Q, Dg = h->Dg;
+  const int64_t N = h->N;
+  h->hess_valid = 0;
+  h->grad_valid = 0;
+  k_prep<<<cdiv(h->D, 256), 256, 0, st>>>(free_dev, h->vec, K, G, h->bounds, h->vecmode);
+  LRVB_CHECK_LAUNCH();
+
+  if (N > 0) {
+#define LRVB_OBS(O)                                                                          \
+  k_obs<O><<<h->obs_grid, h->obs_tn, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
+                                                         h->W, h->klpart, h->gradpart, N, K, G, Q)
+    if (order == 0) LRVB_OBS(0);
+    else if (order == 1) LRVB_OBS(1);
+    else LRVB_OBS(2);
+#undef LRVB_OBS
+    LRVB_CHECK_LAUNCH();
+  }
+  const int n_obs_cta = (N > 0) ? h->obs_grid : 0;
+
+  if (order >= 1 && G > 0) {
+    const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
+    if (order == 1) k_group<1><<<ggrid, 256, 0, st>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
+    else k_group<2><<<ggrid, 256, 0, st>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
+    LRVB_CHECK_LAUNCH();
+  }
+  double* gl = grad_local ? grad_local : h->gradl;
+  if (order == 0) k_local<0><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  else if (order == 1) k_local<1><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  else k_local<2><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  LRVB_CHECK_LAUNCH();
+
+  double* outp = out_global ? out_global : h->outg;
+  if (order >= 2) {
+    LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
+    if (N > 0) {
+      k_gram<<<h->gram_grid_x, 32 * h->gram_jpc * h->gram_split, h->gram_smem, st>>>(
+          h->X, h->W, h->jobs, h->grampart, N, K, h->KT, h->gram_tn, h->gram_jobs, h->gram_jpc,
+          h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
+      LRVB_CHECK_LAUNCH();
+      k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
+          h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
+          h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
+      LRVB_CHECK_LAUNCH();
+    }
+    if (G > 0) {
+      k_border<<<cdiv((int64_t)G * Dg, 256), 256, 0, st>>>(h->vec, h->BR, h->B, K, G, h->bounds, h->vecmode);
+      LRVB_CHECK_LAUNCH();
+    }
+  }
+  const size_t gsm = sizeof(double) * 2 * (size_t)K;
+#define LRVB_GLOB(O)                                                                          \
+  k_global<O><<<1, 256, gsm, st>>>(h->vec, h->klpart, n_obs_cta, h->gradpart, n_obs_cta,       \
+                                   h->locpart, h->loc_grid, outp, K, G, h->prior, h->bounds,   \
+                                   h->include_global, h->vecmode)
+  if (order == 0) LRVB_GLOB(0);
+  else if (order == 1) LRVB_GLOB(1);
+  else LRVB_GLOB(2);
+#undef LRVB_GLOB
+  LRVB_CHECK_LAUNCH();
+  if (outp != h->outg) {
+    const size_t nout = 1 + (order >= 1 ? Dg : 0) + (order >= 2 ? (size_t)Dg * Dg : 0);
+    LRVB_CUDA(cudaMemcpyAsync(h->outg, outp, sizeof(double) * nout, cudaMemcpyDeviceToDevice, st));
+  }
+  if (gl != h->gradl && order >= 1)
+    LRVB_CUDA(cudaMemcpyAsync(h->gradl, gl, sizeof(double) * 2 * (size_t)G, cudaMemcpyDeviceToDevice, st));
+  if (order >= 2) {
+    // the handle's own copy of the global block (A) lives inside outg
+    h->A = h->outg + 1 + Dg;
+    h->hess_valid = 1;
+  }
+  if (order >= 1) h->grad_valid = 1;
+  return LRVB_OK;
+}
+
+}  // namespace lrvb
+
+namespace lrvb {
+void configure_kernels(size_t obs_smem, size_t gram_smem) {
+  const int o = (int)obs_smem, gsm = (int)gram_smem;
+  cudaFuncSetAttribute(k_obs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
+  cudaFuncSetAttribute(k_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
+  cudaFuncSetAttribute(k_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
+  cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm);
+  cudaGetLastError();
+}
+}  // namespace lrvb

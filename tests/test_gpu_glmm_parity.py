@@ -1,0 +1,139 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Tolerance 1e-9 relative / 1e-12 absolute (BASELINE.json north_star); sparsity pattern
+(indptr / indices) bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, make_case, make_model, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # C1 of BASELINE.json: N=5000, K=5, G=100, Q=4
+    "c1": dict(N=5000, K=5, G=100, Q=4, seed=1001),
+    "c1_weights_bounds": dict(N=5000, K=5, G=100, Q=4, seed=1002, weights=True, bounds=0.05),
+    "ragged_shuffled": dict(N=3001, K=7, G=64, Q=8, seed=7, ragged=True, shuffle=True),
+    "empty_groups": dict(N=1203, K=3, G=50, Q=5, seed=8, ragged=True, empty_groups=9),
+    "k1": dict(N=777, K=1, G=10, Q=6, seed=9),
+    "k8_intercept": dict(N=2048, K=8, G=32, Q=8, seed=10, intercept=True),
+    "k20": dict(N=20000, K=20, G=200, Q=8, seed=2001),
+    "k33_multi_rect": dict(N=4100, K=33, G=41, Q=8, seed=11, weights=True),
+    "k50": dict(N=6000, K=50, G=60, Q=8, seed=3001),
+    "k70_job_groups": dict(N=1500, K=70, G=15, Q=8, seed=12),
+    "one_group": dict(N=900, K=4, G=1, Q=8, seed=13),
+    "tiny": dict(N=3, K=2, G=2, Q=3, seed=14),
+}
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def setup(request, vb):
+    case = make_case(**CASES[request.param])
+    oracle = make_oracle(case)
+    model = make_model(vb, case)
+    obj = vb.Objective(model.glmm_par, model)
+    return case, oracle, model, obj
+
+
+def test_value_and_gradient(setup):
+    case, oracle, model, obj = setup
+    x = case["free"]
+    kl = obj.fun_free(x)
+    assert isinstance(kl, float)
+    assert_close(kl, oracle.kl(x), what="KL")
+    g = obj.fun_free_grad(x)
+    ge = oracle.kl_grad(x)
+    assert_close(g, ge, scale=np.abs(ge).max() * 1e-3, what="grad")
+    # par holds plain numeric values equal to the evaluation point (SparseObjectives.py:142-150)
+    assert_close(model.glmm_par.get_free(), x, what="par.get_free")
+
+
+def test_hessian_csr_bit_exact_pattern_and_values(setup):
+    case, oracle, model, obj = setup
+    x = case["free"]
+    H = obj.fun_free_hessian(x)
+    He = oracle.kl_hessian_csr(x)
+    assert H.shape == He.shape
+    assert H.indptr.dtype == np.int32 and H.indices.dtype == np.int32
+    np.testing.assert_array_equal(H.indptr, He.indptr)
+    np.testing.assert_array_equal(H.indices, He.indices)
+    assert_close(H.data, He.data, scale=np.abs(He.data).max() * 1e-6, what="hessian data")
+    D = H.shape[0]
+    if D <= 600:
+        Hd = H.toarray()
+        assert np.array_equal(Hd, Hd.T), "device Hessian must be exactly symmetric"
+
+
+def test_structural_nnz_formula(setup):
+    case, oracle, model, obj = setup
+    # nnz = 4K^2 + 14 + G(8K + 14) when every group is non-empty and no X column
+    # is identically zero
+    counts = np.bincount(case["g"], minlength=case["G"])
+    if (counts > 0).all():
+        K, G = case["K"], case["G"]
+        H = obj.fun_free_hessian(case["free"])
+        assert H.nnz == 4 * K * K + 14 + G * (8 * K + 14)
+
+
+def test_hvp(setup):
+    case, oracle, model, obj = setup
+    x = case["free"]
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(x.size)
+    hv = obj.fun_free_hvp(x, v)
+    hve = oracle.kl_hvp(x, v)
+    assert_close(hv, hve, scale=np.abs(hve).max() * 1e-3, what="hvp")
+
+
+def test_vector_coordinates(setup):
+    case, oracle, model, obj = setup
+    vec = oracle.free_to_vector(case["free"])
+    kl, gv, blk = oracle.vector_derivs(vec, hessian=True)
+    assert_close(obj.fun_vector(vec), kl, what="KL(vector)")
+    g = obj.fun_vector_grad(vec)
+    assert_close(g, gv, scale=np.abs(gv).max() * 1e-3, what="grad(vector)")
+    if case["free"].size <= 600:
+        Hd = obj.fun_vector_hessian(vec).toarray()
+        He = oracle.blocks_to_dense(oracle.lay, blk)
+        assert_close(Hd, He, scale=np.abs(He).max() * 1e-6, what="hessian(vector)")
+    # back to free coordinates: the cache must not leak across coordinate systems
+    assert_close(obj.fun_free(case["free"]), oracle.kl(case["free"]), what="KL after vector")
+
+
+def test_cg_and_direct_solve(setup, vb):
+    case, oracle, model, obj = setup
+    x = case["free"]
+    D = x.size
+    if D > 1200:
+        pytest.skip("dense reference solve only for small D")
+    Hd = oracle.kl_hessian_dense(x)
+    if np.linalg.eigvalsh(Hd).min() <= 0:
+        pytest.skip("Hessian not PD at this (non-optimal) point")
+    rng = np.random.default_rng(6)
+    b = rng.standard_normal(D)
+    xe = np.linalg.solve(Hd, b)
+    solver = vb.ConjugateGradientSolver(obj.fun_free_hvp, x)
+    solver.tol = 1e-10
+    for pre in (None, "block_jacobi"):
+        solver.preconditioner = pre
+        xs, info = solver.get_hinv_vec(b)
+        assert info == 0
+        # contract of test_objectives.py:552-554: agreement with the direct solve to 1e-8
+        assert np.max(np.abs(xs - xe)) < 1e-8 * max(1.0, np.abs(xe).max())
+    lr = vb.LinearResponseCovariances(obj, x)
+    Hinv = np.linalg.inv(Hd)
+    Dg = model.Dg
+    cov_g = lr.get_global_covariance()
+    assert_close(cov_g, Hinv[:Dg, :Dg], rtol=1e-8, scale=np.abs(Hinv[:Dg, :Dg]).max() * 1e-3,
+                 what="global covariance")
+    xd = lr.hinv(b).cpu().numpy()
+    assert_close(xd, xe, rtol=1e-8, scale=np.abs(xe).max() * 1e-3, what="direct solve")
+    G = model.G
+    if G > 0:
+        um, ui = np.arange(Dg, Dg + G), np.arange(Dg + G, Dg + 2 * G)
+        loc = lr.get_local_covariances()
+        ref = np.stack([Hinv[um, um], Hinv[um, ui], Hinv[ui, ui]], axis=1)
+        assert_close(loc, ref, rtol=1e-8, scale=np.abs(ref).max() * 1e-3, what="local covariances")
+    J = model.moment_jacobian(x)
+    cov_m = lr.get_lr_covariance()
+    ref = J @ Hinv @ J.T
+    assert_close(cov_m, ref, rtol=1e-8, scale=np.abs(ref).max() * 1e-3, what="moment covariance")
