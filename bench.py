@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- logistic-GLMM observations/sec for one fused ELBO + gradient + sparse-Hessian
+evaluation (BASELINE.json metric) on N B200s, plus the end-to-end number through the public
+Objective API, the roofline of the dominant kernel and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic observations already resident in
+HBM: lrvb_glmm_eval(order 2) [+ NCCL all-reduce of the packed (KL, global gradient, global
+Hessian block) when N > 1] + device CSR assembly of the arrowhead Hessian.  N = 1 workload is
+BASELINE.json configs[1] (N=1M, K=20, G=10k, Q=8); with N > 1 every rank holds a shard of that
+size (weak scaling; groups are rank-private, globals all-reduced).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # per-GPU shard: observations, fixed effects, groups, Gauss-Hermite points
+    "c2": dict(N=1_000_000, K=20, G=10_000, Q=8,
+               name="logistic GLMM N=1M K=20 G=10k Q=8 per GPU (BASELINE configs[1])"),
+    "c3": dict(N=10_000_000, K=50, G=100_000, Q=8,
+               name="logistic GLMM N=10M K=50 G=100k Q=8 per GPU (BASELINE configs[2] shard)"),
+    "c1": dict(N=5_000, K=5, G=100, Q=4, name="logistic GLMM N=5k K=5 G=100 Q=4 (BASELINE configs[0])"),
+}
+METRIC = "GLMM obs/sec for ELBO+grad+sparse Hessian"
+UNIT = "obs/s"
+CPU_SAMPLE = dict(N=500_000, G=5_000)   # bounded sample of the workload for the CPU arm
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(max(mx)) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def synth_shard(torch, N, K, G, seed, device):
+    """Seeded synthetic shard on the device: X ~ N(0,1), balanced group-sorted ids,
+    y ~ Bernoulli(sigmoid(X beta + u_g))."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    X = torch.randn(N, K, dtype=torch.float64, device=device, generator=gen)
+    base, rem = divmod(N, G)
+    counts = torch.full((G,), base, dtype=torch.int64, device=device)
+    counts[:rem] += 1
+    g = torch.repeat_interleave(torch.arange(G, device=device), counts)
+    beta = 0.5 * torch.randn(K, dtype=torch.float64, device=device, generator=gen)
+    u = 0.3 + 0.5 * torch.randn(G, dtype=torch.float64, device=device, generator=gen)
+    p = torch.sigmoid(X @ beta + u[g])
+    y = (torch.rand(N, dtype=torch.float64, device=device, generator=gen) < p).double()
+    return X, y, g
+
+
+def measure_dgemm_tflops(torch, n=8192, reps=5):
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_oracle_step(sample, K, Q, seed=123):
+    """One CPU pass (oracle port) over a bounded sample: KL + gradient + arrowhead blocks + CSR."""
+    from oracle import glmm_oracle as go
+    Ns, Gs = sample["N"], sample["G"]
+    X, y, g = go.make_glmm_data(Ns, K, Gs, seed)
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+    o = go.GLMMOracle(X, y, g, gh_x, gh_w, G=Gs)
+    x = go.make_free(o.lay.D, seed)
+
+    def step():
+        t = time.perf_counter()
+        H = o.kl_hessian_csr(x)     # kl_blocks (value, gradient, Hessian blocks) + CSR emission
+        return time.perf_counter() - t, H.nnz
+    return step
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU path for this metric (oracle port -- the reference
+    itself needs autograd<1.4, not installable here), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step = cpu_oracle_step(CPU_SAMPLE, wl["K"], wl["Q"])
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    times = [step()[0] for _ in range(args.steps)]
+    ms = 1e3 * float(np.mean(times))
+    value = CPU_SAMPLE["N"] / (ms * 1e-3)
+    cores = blas_threads()
+    sample = "N=%d obs, K=%d, G=%d, Q=%d (1/%d of the per-GPU workload) per step" % (
+        CPU_SAMPLE["N"], wl["K"], CPU_SAMPLE["G"], wl["Q"], wl["N"] // CPU_SAMPLE["N"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "note": "numpy analytic restatement of the reference path (oracle/); "
+                                 "BLAS parts use %d threads, elementwise parts 1" % cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    import lrvb_b200 as vb
+    from lrvb_b200 import _native as nat
+    lib = nat.load()
+
+    N, K, G, Q = wl["N"], wl["K"], wl["G"], wl["Q"]
+    X, y, g = synth_shard(torch, N, K, G, seed=1000 * 2 + rank, device=device)
+    if world > 1:
+        from lrvb_b200 import distributed as vbd
+        model = vbd.ShardedLogisticGLMM.from_local_shard(X, y, g, num_local_groups=G,
+                                                         num_gh_points=Q)
+    else:
+        model = vb.LogisticGLMM(X, y, g, num_gh_points=Q, num_groups=G)
+    obj = vb.Objective(model.glmm_par, model)
+    D = model.D
+    gen = torch.Generator(device=device)
+    gen.manual_seed(7)
+    x_dev = 0.1 * torch.randn(D, dtype=torch.float64, device=device, generator=gen)
+    if world > 1:
+        dist.broadcast(x_dev, 0)
+    nsteps_total = args.warmup + args.steps
+    x_host = [x_dev.cpu().numpy() + 1e-3 * np.random.default_rng(s).standard_normal(D)
+              for s in range(min(nsteps_total, 8))]
+    if world > 1:   # every rank must evaluate at the same points
+        for xh in x_host:
+            t = torch.from_numpy(xh).to(device)
+            dist.broadcast(t, 0)
+            xh[:] = t.cpu().numpy()
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
+    local = model.local if world > 1 else model
+    nat.check(lib.lrvb_glmm_set_timing(local._h, 1))
+
+    def device_step():
+        model.evaluate(x_dev, 2, force=True)
+        return model.hessian_csr()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.lrvb_launch_count()
+    step_ms, gram_ms, obs_ms, eval_ms = [], [], [], []
+    import ctypes
+    ms3 = (ctypes.c_float * 3)()
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush (126 MB L2 < 256 MiB), outside the timing
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        csr = device_step()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        nat.check(lib.lrvb_glmm_last_timing(local._h, ms3))
+        eval_ms.append(ms3[0]); obs_ms.append(ms3[1]); gram_ms.append(ms3[2])
+    torch.cuda.synchronize()
+    launches = (lib.lrvb_launch_count() - launches0) // max(1, args.steps)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+    nnz = csr.nnz
+
+    # ---------------- end to end through the public API (host buffers) ----------------
+    nat.check(lib.lrvb_glmm_set_timing(local._h, 0))
+
+    def e2e_step(i):
+        xh = x_host[i % len(x_host)]
+        if world > 1:
+            # sharded: every rank brings ITS part of the distributed Hessian / gradient to its host
+            model.evaluate(xh, 2)
+            H = model.hessian_csr().to_scipy()
+            gr = model.grad_local_layout().cpu().numpy()
+            kl = float(model.kl_tensor().item())
+            return H, gr, kl
+        H = obj.fun_free_hessian(xh)     # scipy CSR on the host (order-2 evaluation, cached)
+        gr = obj.fun_free_grad(xh)       # numpy (D,)
+        kl = obj.fun_free(xh)            # float
+        return H, gr, kl
+    for i in range(args.warmup):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        H, gr, kl = e2e_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N / (float(e2e_s.item()) / args.steps)
+    h2d = 8 * D
+    d2h = 8 + 8 * D + 12 * int(H.nnz) + 4 * (D + 1)
+
+    if rank == 0:
+        # roofline of the dominant kernel (k_gram, FP64 tensor pipe)
+        peak = measure_dgemm_tflops(torch)
+        flops_per_obs = 4 * K * K + 2 * K       # three weighted Grams, symmetric
+        gms = float(np.mean(gram_ms))
+        achieved = N * flops_per_obs / (gms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get("k_gram_dram_bytes")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "tensor", "kernel": "lrvb::k_gram (DMMA.8x8x4)", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in "
+                                   "MEASURED_PEAKS.json); DMMA.8x8x4 microbenchmark: 37.1 TF",
+                    "kernel_ms": gms, "flops_per_obs": flops_per_obs,
+                    "k_obs_ms": float(np.mean(obs_ms)), "eval_ms": float(np.mean(eval_ms)),
+                    "hbm_bytes_per_obs": 8 * K + 12,
+                    "hbm_frac_of_step": (N * (8 * K + 12) / (ms_per_step * 1e-3) / 1e9)
+                    / _hbm_peak()}
+        cpu = None
+        if world == 1 or True:
+            stepf = cpu_oracle_step(CPU_SAMPLE, K, Q)
+            stepf()
+            ts = [stepf()[0] for _ in range(3)]
+            cores = blas_threads()
+            cpu = {"value": CPU_SAMPLE["N"] / float(np.median(ts)), "unit": UNIT, "cores": cores,
+                   "kind": "port",
+                   "sample": "N=%d obs, K=%d, G=%d, Q=%d (1/%d of the per-GPU workload), median of 3"
+                             % (CPU_SAMPLE["N"], K, CPU_SAMPLE["G"], Q, N // CPU_SAMPLE["N"])}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "obs_per_gpu": N, "K": K, "groups_per_gpu": G,
+                       "gh_points": Q, "free_dim": D, "hessian_nnz": int(nnz),
+                       "parallelism": "obs-sharded x%d, NCCL all-reduce of (KL, grad_g, H_gg)" % world
+                       if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write); X alone is %d MB"
+                             % (N * K * 8 // 10 ** 6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "api": "Objective.fun_free_hessian/fun_free_grad/fun_free with numpy x; "
+                           "scipy CSR + numpy gradient + float returned to the host"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rules: W >= 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,14 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
                      const lrvb_glmm_prior* prior, const lrvb_glmm_bounds* bounds,
                      int32_t include_global_terms, void* stream);
 int lrvb_glmm_destroy(lrvb_glmm* h);
+/* Number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
+long long lrvb_launch_count(void);
+/* Optional instrumentation for bench.py's roofline: when enabled, lrvb_glmm_eval records CUDA
+ * events on the launching stream around the whole evaluation, the per-observation kernel and the
+ * DMMA Gram kernel; lrvb_glmm_last_timing syncs on the last one and returns
+ * ms3 = {whole eval, k_obs, k_gram} (HOST floats). */
+int lrvb_glmm_set_timing(lrvb_glmm* h, int32_t enable);
+int lrvb_glmm_last_timing(lrvb_glmm* h, float* ms3_host);
 /* Coordinates of the evaluation point and of every derivative returned afterwards:
  * 0 (default) = free / unconstrained (Objective.fun_free*, SparseObjectives.py:120-158),
  * 1 = constrained "vector" coordinates (Objective.fun_vector*, :127-181).  Invalidates the

@@ -21,7 +21,7 @@ import scipy as sp
 import scipy.sparse.linalg
 from scipy.sparse.linalg import LinearOperator
 
-from ._tensors import is_torch, to_device
+from ._tensors import is_torch
 
 
 def split_vector(vec):
@@ -114,16 +114,14 @@ class ConjugateGradientSolver(object):
         else:
             raise ValueError("device CG supports preconditioner None or 'block_jacobi'")
         model.evaluate(self.x0, 2, self._coords)  # cached after the first solve
-        torch_in = is_torch(vec) and vec.is_cuda
-        b = to_device(vec).reshape(-1)
-        if b.numel() != self.dim:
+        n = vec.numel() if is_torch(vec) else np.asarray(vec).size
+        if n != self.dim:
             raise ValueError("Wrong size for CG right-hand side.  Expected {}, got {}".format(
-                self.dim, b.numel()))
-        x0d = None if x0 is None else to_device(x0).reshape(-1)
-        x, info, iters = model.cg(b, x0d, precond=precond, rtol=self.tol,
+                self.dim, n))
+        x, info, iters = model.cg(vec, x0, precond=precond, rtol=self.tol,
                                   maxiter=self.maxiter or 0)
         self.last_iterations = iters
-        return (x if torch_in else x.cpu().numpy()), info
+        return (x if is_torch(vec) else x.cpu().numpy()), info
 
     def get_hinv_vec_subsets(self, vec, masks, verbose=False, print_every=10):
         """One solve per boolean mask with the unmasked entries zeroed (:89-105)."""

@@ -317,11 +317,13 @@ class LogisticGLMM(object):
         return out
 
     # names shared with distributed.ShardedLogisticGLMM (where they add the all-reduce)
-    def hvp(self, v_dev):
-        return self.hvp_cached(v_dev)
+    def hvp(self, v):
+        return self.hvp_cached(to_device(v).reshape(-1))
 
-    def cg(self, b_dev, x0_dev=None, precond=0, rtol=1e-8, maxiter=0):
-        return self.cg_cached(b_dev, x0_dev, precond, rtol, maxiter)
+    def cg(self, b, x0=None, precond=0, rtol=1e-8, maxiter=0):
+        return self.cg_cached(to_device(b).reshape(-1),
+                              None if x0 is None else to_device(x0).reshape(-1),
+                              precond, rtol, maxiter)
 
     def global_covariance(self):
         """(H^-1)_gg = S^-1: the linear-response covariance of the global free parameters."""
@@ -329,6 +331,7 @@ class LogisticGLMM(object):
 
     def solve(self, b_dev):
         """x = H^-1 b (b (D,) or (nrhs, D)) by block elimination with the cached Hessian."""
+        b_dev = to_device(b_dev)
         Sinv = self.global_covariance()
         rhs = self.solve_reduce_rhs(b_dev, include_bg=True)
         return self.solve_finish(Sinv, rhs, b_dev)

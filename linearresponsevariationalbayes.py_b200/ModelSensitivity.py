@@ -15,8 +15,7 @@ device conjugate gradient -- the dense ``cho_factor`` of the reference is O(D^3)
 import numpy as np
 import scipy.sparse
 
-from . import _native as nat
-from ._tensors import is_torch, to_device
+from ._tensors import is_torch
 
 
 class LinearResponseCovariances(object):
@@ -73,20 +72,23 @@ class LinearResponseCovariances(object):
 
     def hinv(self, rhs):
         """H^{-1} rhs for rhs (D,) or (nrhs, D) -> same shape (device tensor)."""
+        import torch
         self._ensure_point()
-        b = to_device(rhs)
         if self.method == "schur":
-            return self.model.solve(b)
+            return self.model.solve(rhs)
+        if scipy.sparse.issparse(rhs):
+            rhs = rhs.toarray()
+        shape = tuple(rhs.shape)
+        rows = rhs.reshape(-1, self.model.D)
         out = []
-        for row in b.reshape(-1, self.model.D):
+        for row in rows:
             x, info, iters = self.model.cg(
-                row.contiguous(), None,
-                precond=1 if self.cg_preconditioner == "block_jacobi" else 0, rtol=self.cg_tol)
+                row, None, precond=1 if self.cg_preconditioner == "block_jacobi" else 0,
+                rtol=self.cg_tol)
             self.cg_infos.append(info)
             self.cg_iterations.append(iters)
             out.append(x)
-        torch = nat.require_cuda()
-        return torch.stack(out).reshape(b.shape)
+        return torch.stack(out).reshape(shape)
 
     def get_moment_jacobian(self, calculate_moments=None):
         """Jacobian of the moments w.r.t. the free parameters.  The model's analytic
@@ -100,19 +102,20 @@ class LinearResponseCovariances(object):
 
     def get_lr_covariance_from_jacobians(self, moment_jacobian1, moment_jacobian2=None):
         """J1 H^{-1} J2^T for (m1, D) / (m2, D) Jacobians (dense, scipy-sparse or torch)."""
-        torch = nat.require_cuda()
+        import torch
         if moment_jacobian2 is None:
             moment_jacobian2 = moment_jacobian1
 
-        def dense_dev(j):
+        def dense(j):
             if scipy.sparse.issparse(j):
                 j = j.toarray()
-            return to_device(j).reshape(-1, self.model.D)
+            return j.reshape(-1, self.model.D)
 
-        j2 = dense_dev(moment_jacobian2)
-        hinv_j2t = self.hinv(j2)                      # (m2, D): rows are H^{-1} J2[i]
-        j1 = dense_dev(moment_jacobian1)
-        cov = torch.matmul(j1, hinv_j2t.t())
+        hinv_j2t = self.hinv(dense(moment_jacobian2))   # (m2, D): rows are H^{-1} J2[i]
+        j1 = dense(moment_jacobian1)
+        if not is_torch(j1):
+            j1 = torch.from_numpy(np.ascontiguousarray(j1, dtype=np.float64))
+        cov = torch.matmul(j1.to(hinv_j2t.device), hinv_j2t.t())
         return cov if (is_torch(moment_jacobian1) or is_torch(self._opt0)) else cov.cpu().numpy()
 
     def get_lr_covariance(self, calculate_moments=None):

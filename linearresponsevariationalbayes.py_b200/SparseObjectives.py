@@ -135,16 +135,17 @@ class Objective(object):
     def _hessian(self, x, coords):
         self.model.evaluate(x, 2, coords)
         self._set_par(x, coords)
-        csr = self.model.hessian_csr()
-        return csr if is_torch(x) else csr.to_scipy()
+        if is_torch(x):
+            return self.model.hessian_csr()      # device CSR (a sharded model: this rank's part)
+        if hasattr(self.model, "hessian_csr_global"):
+            return self.model.hessian_csr_global()   # sharded model: gather the full matrix
+        return self.model.hessian_csr().to_scipy()
 
     def _hvp(self, x, vec, coords):
         self.model.evaluate(x, 2, coords)
         self._set_par(x, coords)
-        torch_in = is_torch(vec) and vec.is_cuda
-        from ._tensors import to_device
-        out = self.model.hvp(to_device(vec).reshape(-1))
-        return out if torch_in else out.cpu().numpy()
+        out = self.model.hvp(vec)
+        return out if is_torch(vec) else out.cpu().numpy()
 
     @staticmethod
     def _no_extra(argv, argk):

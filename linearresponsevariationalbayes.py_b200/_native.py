@@ -34,6 +34,9 @@ SIGNATURES = {
                                    _P, _P, POINTER(c_double), POINTER(c_double), POINTER(Prior),
                                    POINTER(Bounds), c_int32, _P]),
     "lrvb_glmm_destroy": (c_int32, [_P]),
+    "lrvb_launch_count": (ctypes.c_longlong, []),
+    "lrvb_glmm_set_timing": (c_int32, [_P, c_int32]),
+    "lrvb_glmm_last_timing": (c_int32, [_P, POINTER(ctypes.c_float)]),
     "lrvb_glmm_set_coords": (c_int32, [_P, c_int32]),
     "lrvb_glmm_dims": (c_int32, [_P, POINTER(c_int64), POINTER(c_int32)]),
     "lrvb_glmm_eval": (c_int32, [_P, _P, c_int32, _P, _P, _P]),

@@ -8,6 +8,7 @@
 namespace lrvb {
 
 static thread_local char g_err[1024] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -57,6 +58,8 @@ int lrvb_glmm_destroy(lrvb_glmm* h) {
                   h->schurpart};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->ev)
+    if (e) cudaEventDestroy(e);
   delete h;
   return LRVB_OK;
 }
@@ -203,6 +206,33 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
 #undef CREATE_TRY
 #undef CREATE_CUDA
   *out = h;
+  return LRVB_OK;
+}
+
+long long lrvb_launch_count(void) { return g_launches; }
+
+int lrvb_glmm_set_timing(lrvb_glmm* h, int32_t enable) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_set_timing: NULL handle");
+  if (enable && !h->ev[0])
+    for (int i = 0; i < 6; ++i) LRVB_CUDA(cudaEventCreate(&h->ev[i]));
+  h->timing = enable ? 1 : 0;
+  h->ev_order = -1;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_last_timing(lrvb_glmm* h, float* ms3) {
+  LRVB_REQUIRE(h != nullptr && ms3 != nullptr, "lrvb_glmm_last_timing: NULL argument");
+  if (!h->timing || h->ev_order < 0) {
+    set_error("lrvb_glmm_last_timing: timing not enabled or no evaluation since it was enabled");
+    return LRVB_ESTATE;
+  }
+  LRVB_CUDA(cudaEventSynchronize(h->ev[5]));
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  LRVB_CUDA(cudaEventElapsedTime(&ms3[0], h->ev[4], h->ev[5]));
+  if (h->N > 0) {
+    LRVB_CUDA(cudaEventElapsedTime(&ms3[1], h->ev[0], h->ev[1]));
+    if (h->ev_order >= 2) LRVB_CUDA(cudaEventElapsedTime(&ms3[2], h->ev[2], h->ev[3]));
+  }
   return LRVB_OK;
 }
 

@@ -24,7 +24,14 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define LRVB_CHECK_LAUNCH() LRVB_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by exactly one LRVB_CHECK_LAUNCH (or adds the
+// extra launches to g_launches by hand), so lrvb_launch_count() is the number of OUR kernels
+extern long long g_launches;
+#define LRVB_CHECK_LAUNCH()          \
+  do {                               \
+    ++lrvb::g_launches;              \
+    LRVB_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define LRVB_REQUIRE(cond, ...)                                                      \
   do {                                                                               \
@@ -178,6 +185,10 @@ struct lrvb_glmm {
   double* outg = nullptr;     // (1 + Dg + Dg*Dg) packed [KL, grad_g, A] of the last eval
   int hess_valid = 0;
   int grad_valid = 0;
+  // optional per-kernel timing (bench): events around the whole eval, k_obs and k_gram
+  int timing = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int ev_order = -1;
   // CSR
   int32_t* rowcnt = nullptr;  // (D+1)
   int32_t* scanblk = nullptr; // scan scratch

@@ -284,6 +284,77 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
 }
 
 // ------------------------------------------------------------------------------------------
+// k-step loop of one warp job, specialised at compile time on the number of valid tile rows /
+// columns of its rectangle and on whether it is a diagonal (upper-triangular) rectangle:
+// a predicated-off DMMA still occupies the FP64 pipe (measured: 2.3x slowdown), so the set of
+// issued DMMAs must be exact.
+template <int NI, int NJ, bool TRI>
+__device__ __forceinline__ void gram_ksteps(double (&acc)[kRT][kRT][2], const double* xs,
+                                            const double* wsel, int K, const int (&cola)[kRT],
+                                            const int (&colb)[kRT], int fam, int split,
+                                            int n_split, int ksteps, int lr) {
+  for (int ks = split; ks < ksteps; ks += n_split) {
+    const int n = 4 * ks + lr;
+    const double* xr = xs + (size_t)n * K;
+    const double wv = wsel[n];
+    double fa[kRT], fb[kRT];
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      if (i < NI) {
+        double xa = (cola[i] < K) ? xr[cola[i]] : 0.0;
+        if (fam == 2) xa *= xa;
+        fa[i] = xa;
+      }
+      if (i < NJ) {
+        double xb = (colb[i] < K) ? xr[colb[i]] : 0.0;
+        if (fam >= 1) xb *= xb;
+        fb[i] = xb * wv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kRT; ++i)
+#pragma unroll
+      for (int j = 0; j < kRT; ++j)
+        if (i < NI && j < NJ && (!TRI || i <= j)) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+  }
+}
+
+__device__ __forceinline__ void gram_dispatch(double (&acc)[kRT][kRT][2], int ni, int nj, bool tri,
+                                              const double* xs, const double* wsel, int K,
+                                              const int (&cola)[kRT], const int (&colb)[kRT],
+                                              int fam, int split, int n_split, int ksteps, int lr) {
+#define LRVB_G(NI, NJ, T)                                                                      \
+  gram_ksteps<NI, NJ, T>(acc, xs, wsel, K, cola, colb, fam, split, n_split, ksteps, lr)
+  if (tri) {
+    switch (ni) {
+      case 1: LRVB_G(1, 1, true); break;
+      case 2: LRVB_G(2, 2, true); break;
+      case 3: LRVB_G(3, 3, true); break;
+      default: LRVB_G(4, 4, true); break;
+    }
+  } else {
+    switch (ni * 4 + nj) {
+      case 5: LRVB_G(1, 1, false); break;
+      case 6: LRVB_G(1, 2, false); break;
+      case 7: LRVB_G(1, 3, false); break;
+      case 8: LRVB_G(1, 4, false); break;
+      case 9: LRVB_G(2, 1, false); break;
+      case 10: LRVB_G(2, 2, false); break;
+      case 11: LRVB_G(2, 3, false); break;
+      case 12: LRVB_G(2, 4, false); break;
+      case 13: LRVB_G(3, 1, false); break;
+      case 14: LRVB_G(3, 2, false); break;
+      case 15: LRVB_G(3, 3, false); break;
+      case 16: LRVB_G(3, 4, false); break;
+      case 17: LRVB_G(4, 1, false); break;
+      case 18: LRVB_G(4, 2, false); break;
+      case 19: LRVB_G(4, 3, false); break;
+      default: LRVB_G(4, 4, false); break;
+    }
+  }
+#undef LRVB_G
+}
+
 // Weighted Grams on the FP64 tensor cores.  Each warp owns one GramJob (a kRT x kRT rectangle
 // of 8x8 output tiles of one family) for a subset of the 4-observation k-steps of every tile;
 // mma.m8n8k4: A[i][k] = F1[n0+k][8 it + i], B[k][j] = wgt[n0+k] * F2[n0+k][8 jt + j], so lane l
@@ -328,6 +399,10 @@ k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob
       if (active && it < KT && jt < KT && (fam == 1 || it <= jt)) tmask |= 1u << (i * kRT + j);
     }
   const double* wsel = wgt + (size_t)fam * TN;
+  int ni = KT - jb.i0, nj = KT - jb.j0;
+  ni = ni > kRT ? kRT : ni;
+  nj = nj > kRT ? kRT : nj;
+  const bool tri = (fam != 1) && (jb.i0 == jb.j0);
 
   const int64_t ntiles = (N + TN - 1) / TN;
   for (int64_t tile = chunk; tile < ntiles; tile += n_chunk) {
@@ -343,29 +418,8 @@ k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob
       for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) xs[e] = 0.0;
     cp_async_commit_wait_all();
     __syncthreads();
-    if (tmask) {
-      const int ksteps = (rows + 3) >> 2;
-      for (int ks = split; ks < ksteps; ks += n_split) {
-        const int n = 4 * ks + lr;
-        const double* xr = xs + (size_t)n * K;
-        const double wv = wsel[n];
-        double fa[kRT], fb[kRT];
-#pragma unroll
-        for (int i = 0; i < kRT; ++i) {
-          double xa = (cola[i] < K) ? xr[cola[i]] : 0.0;
-          double xb = (colb[i] < K) ? xr[colb[i]] : 0.0;
-          if (fam == 2) xa *= xa;
-          if (fam >= 1) xb *= xb;
-          fa[i] = xa;
-          fb[i] = xb * wv;
-        }
-#pragma unroll
-        for (int i = 0; i < kRT; ++i)
-#pragma unroll
-          for (int j = 0; j < kRT; ++j)
-            if (tmask & (1u << (i * kRT + j))) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-      }
-    }
+    if (tmask) gram_dispatch(acc, ni, nj, tri, xs, wsel, K, cola, colb, fam, split, n_split,
+                             (rows + 3) >> 2, lr);
   }
 
   // in-CTA reduction over the k-step splits (fixed order), then one partial per (chunk, job)
@@ -636,10 +690,11 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
         const double m[4][4] = {{a00, 0.0, a02, a03}, {0.0, a11, a12, a13},
                                 {a02, a12, a22, a23}, {a03, a13, a23, a33}};
         for (int r = 0; r < 4; ++r)
-          for (int c = 0; c < 4; ++c) {
+          for (int c = r; c < 4; ++c) {   // upper triangle, mirrored: exactly symmetric
             double h = -m[r][c] * jj[r] * jj[c];
             if (r == c && r > 0 && !vecmode) h += gvv[r] * jj[r];
             A[(size_t)r * Dg + c] = h;
+            A[(size_t)c * Dg + r] = h;
           }
       }
     }
@@ -686,10 +741,12 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   const int64_t N = h->N;
   h->hess_valid = 0;
   h->grad_valid = 0;
+  if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[4], st));
   k_prep<<<cdiv(h->D, 256), 256, 0, st>>>(free_dev, h->vec, K, G, h->bounds, h->vecmode);
   LRVB_CHECK_LAUNCH();
 
   if (N > 0) {
+    if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
 #define LRVB_OBS(O)                                                                          \
   k_obs<O><<<h->obs_grid, h->obs_tn, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
                                                          h->W, h->klpart, h->gradpart, N, K, G, Q)
@@ -698,6 +755,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     else LRVB_OBS(2);
 #undef LRVB_OBS
     LRVB_CHECK_LAUNCH();
+    if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
   }
   const int n_obs_cta = (N > 0) ? h->obs_grid : 0;
 
@@ -717,10 +775,12 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   if (order >= 2) {
     LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
     if (N > 0) {
+      if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[2], st));
       k_gram<<<h->gram_grid_x, 32 * h->gram_jpc * h->gram_split, h->gram_smem, st>>>(
           h->X, h->W, h->jobs, h->grampart, N, K, h->KT, h->gram_tn, h->gram_jobs, h->gram_jpc,
           h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
       LRVB_CHECK_LAUNCH();
+      if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
       k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
           h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
           h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
@@ -753,6 +813,10 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     h->hess_valid = 1;
   }
   if (order >= 1) h->grad_valid = 1;
+  if (h->timing) {
+    LRVB_CUDA(cudaEventRecord(h->ev[5], st));
+    h->ev_order = order;
+  }
   return LRVB_OK;
 }
 

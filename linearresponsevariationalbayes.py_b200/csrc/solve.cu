@@ -607,6 +607,7 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
       LRVB_TRY(launch_hvp(h, p, q, 1, flags, st));
       k_dot<<<vgrid, 256, 0, st>>>(p, q, nullptr, nullptr, D, pqpart, flags);
       k_cg_update<<<vgrid, 256, 0, st>>>(x, r, p, q, pqpart, vgrid, rrpart, h->scal, flags, D, it);
+      g_launches += 4;  // precond, latch, dir, dot share the check below
       LRVB_CHECK_LAUNCH();
     }
     LRVB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));

@@ -358,7 +358,12 @@ class GLMMOracle:
         # borders (data): per-group sums
         def gsum_rows(wv, M):
             out = np.zeros((G, K))
-            np.add.at(out, self.g, wv[:, None] * M)
+            if self.N and np.all(self.g[1:] >= self.g[:-1]):
+                # group-sorted: segmented sums (same result as np.add.at, much faster)
+                starts = np.flatnonzero(np.r_[True, self.g[1:] != self.g[:-1]])
+                out[self.g[starts]] = np.add.reduceat(wv[:, None] * M, starts, axis=0)
+            else:
+                np.add.at(out, self.g, wv[:, None] * M)
             return out
         B[:, 0, bm0:bm0 + K] += gsum_rows(la, X)                       # (u_m, beta_m)
         B[:, 0, bi0:bi0 + K] += gsum_rows(lb_, S) * dv[None, :]        # (u_m, beta_i)

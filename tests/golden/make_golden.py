@@ -1,0 +1,197 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, imported
+under oracle/ref_shim.py) on seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+What is pinned
+  * forward values of Modeling.get_e_logistic_term_guass_hermite, ExponentialFamilies.* and the
+    Parameters / ModelParamsDict packing -- straight from the reference's code;
+  * the composed GLMM KL evaluated with the reference's own parameter bundles
+    (UVNParam, GammaParam, UVNParamVector .e()/.var()/.e_log()/.entropy()), Modeling and
+    ExponentialFamilies functions;
+  * its gradient by the complex-step method applied to that same reference code (exact to
+    rounding: the reference's forward code is complex-analytic once scipy's real-only gammaln
+    is continued by loggamma), and Hessian / Hessian-vector products by central differences of
+    the complex-step gradient with Richardson extrapolation (~1e-9 relative).
+The reference differentiates with autograd (not installable here); these derivative vectors are
+the strongest pin of "what autograd would return" available from the reference's own code.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.special
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_shim import import_reference  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def complex_safe_gammaln():
+    real_gammaln = scipy.special.gammaln
+
+    def gammaln(z):
+        if np.iscomplexobj(z):
+            return scipy.special.loggamma(z)
+        return real_gammaln(z)
+    scipy.special.gammaln = gammaln
+
+
+def build_par(vb, K, G, lb):
+    par = vb.ModelParamsDict("glmm_par")
+    par.push_param(vb.UVNParam("mu", min_info=lb))
+    par.push_param(vb.GammaParam("tau", min_shape=lb, min_rate=lb))
+    par.push_param(vb.UVNParamVector("beta", K, min_info=lb))
+    par.push_param(vb.UVNParamVector("u", G, min_info=lb))
+    return par
+
+
+def ref_kl(mods, par, data, prior, free):
+    vb, M, ef = mods
+    X, y, g, w, gh_x, gh_w = data
+    par.set_free(free)
+    mu, tau, beta, u = par["mu"], par["tau"], par["beta"], par["u"]
+    z_mean = u.e()[g] + np.matmul(X, beta.e())
+    z_var = u.var()[g] + np.matmul(X ** 2, beta.var())
+    z_sd = np.sqrt(z_var)
+    A = M.get_e_logistic_term_guass_hermite(z_mean, z_sd, gh_x, gh_w, aggregate_all=False)
+    loglik = np.sum(w * (y * z_mean - A))
+    e_tau, e_log_tau = tau.e(), tau.e_log()
+    loglik = loglik + np.sum(
+        -0.5 * e_tau * ((mu.e() - u.e()) ** 2 + mu.var() + u.var()) + 0.5 * e_log_tau)
+    entropy = mu.entropy() + beta.entropy() + u.entropy() + tau.entropy()
+    pm, pi, bm, bi, ps, pr = prior
+    log_prior = (ef.uvn_prior(pm, pi, mu.e(), mu.var())
+                 + np.sum(ef.uvn_prior(bm, bi, beta.e(), beta.var()))
+                 + ef.gamma_prior(ps, pr, e_tau, e_log_tau))
+    return np.squeeze(-(loglik + entropy + log_prior))
+
+
+def cs_grad(f, x, h=1e-30):
+    g = np.zeros(x.size)
+    for i in range(x.size):
+        xc = x.astype(complex)
+        xc[i] += 1j * h
+        g[i] = np.imag(f(xc)) / h
+    return g
+
+
+def fd_hvp(f, x, v, h=2e-3):
+    def d(hh):
+        return (cs_grad(f, x + hh * v) - cs_grad(f, x - hh * v)) / (2 * hh)
+    return (4 * d(h / 2) - d(h)) / 3   # Richardson: O(h^4)
+
+
+def glmm_case(mods, name, N, K, G, Q, seed, lb, weights, empty, full_hessian):
+    vb = mods[0]
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, K))
+    pool = np.setdiff1d(np.arange(G), empty)
+    g = np.sort(rng.choice(pool, size=N))
+    beta = rng.normal(0, 0.5, K)
+    uu = rng.normal(0.3, 0.5, G)
+    y = (rng.random(N) < scipy.special.expit(X @ beta + uu[g])).astype(np.float64)
+    w = rng.uniform(0.5, 1.5, N) if weights else np.ones(N)
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+    prior = (0.1, 0.01, -0.2, 0.02, 3.0, 2.5)
+    par = build_par(vb, K, G, lb)
+    D = par.free_size()
+    free = rng.normal(0, 0.3, D)
+    data = (X, y, g, w, gh_x, gh_w)
+
+    def f(x):
+        return ref_kl(mods, par, data, prior, x)
+    kl = float(np.real(f(free)))
+    grad = cs_grad(f, free)
+    par.set_free(free)
+    vec = par.get_vector()
+    dirs = rng.standard_normal((3, D))
+    hvps = np.stack([fd_hvp(f, free, v) for v in dirs])
+    out = dict(X=X, y=y, g=g, w=w, gh_x=gh_x, gh_w=gh_w, prior=np.array(prior), lb=lb, G=G,
+               free=free, vector=vec, kl=kl, grad=grad, dirs=dirs, hvps=hvps,
+               names=np.array([str(s) for s in par.names()]))
+    if full_hessian:
+        out["hessian"] = np.stack([fd_hvp(f, free, e) for e in np.eye(D)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "D =", D, "KL =", kl)
+
+
+def forward_cases(mods):
+    vb, M, ef = mods
+    rng = np.random.default_rng(20261018)
+    out = {}
+    for Q in (4, 8, 20):
+        gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+        zm = rng.normal(0, 3, 257)
+        zs = np.exp(rng.normal(0, 0.7, 257))
+        zm[:4] = [-40.0, 40.0, 0.0, 300.0]
+        out["gh%d_zm" % Q], out["gh%d_zs" % Q] = zm, zs
+        out["gh%d_each" % Q] = M.get_e_logistic_term_guass_hermite(zm, zs, gh_x, gh_w, False)
+        out["gh%d_all" % Q] = M.get_e_logistic_term_guass_hermite(zm, zs, gh_x, gh_w, True)
+    shape, rate = np.exp(rng.normal(0, 0.5, 101)), np.exp(rng.normal(0, 0.5, 101))
+    shape[:3] = [0.05, 3.0, 150.0]
+    out.update(gam_shape=shape, gam_rate=rate, gamma_entropy=ef.gamma_entropy(shape, rate),
+               e_log_gamma=ef.get_e_log_gamma(shape, rate))
+    info = np.exp(rng.normal(0, 1, 77))
+    out.update(uvn_info=info, uvn_entropy=ef.univariate_normal_entropy(info))
+    alpha = 10 * rng.random((5, 63)) + 0.1
+    out.update(dir_alpha=alpha, dirichlet_entropy=ef.dirichlet_entropy(alpha),
+               e_log_dirichlet=ef.get_e_log_dirichlet(alpha), e_dirichlet=ef.get_e_dirichlet(alpha))
+    alpha3 = 10 * rng.random((4, 6, 3)) + 0.1
+    out.update(dir_alpha3=alpha3, dirichlet_entropy3=ef.dirichlet_entropy(alpha3))
+    tau = 5 * rng.random((41, 2)) + 0.2
+    out.update(beta_tau=tau, beta_entropy=ef.beta_entropy(tau))
+    p = rng.random((19, 6))
+    p /= p.sum(1, keepdims=True)
+    out.update(mn_p=p, multinoulli_entropy=ef.multinoulli_entropy(p))
+    for k in (2, 3, 5):
+        Ms = 7
+        v = np.stack([(lambda a: a @ a.T + np.eye(k))(rng.standard_normal((k, k))) for _ in range(Ms)])
+        df = k + 1 + 5 * rng.random(Ms)
+        out["wis%d_v" % k], out["wis%d_df" % k] = v, df
+        out["wis%d_entropy" % k] = np.array([ef.wishart_entropy(df[i], v[i]) for i in range(Ms)])
+        out["wis%d_e_log_det" % k] = np.array([ef.e_log_det_wishart(df[i], v[i]) for i in range(Ms)])
+        out["wis%d_e_log_inv_diag" % k] = np.stack(
+            [ef.e_log_inv_wishart_diag(df[i], v[i]) for i in range(Ms)])
+        out["mvn%d_entropy" % k] = np.array([ef.multivariate_normal_entropy(v[i]) for i in range(Ms)])
+    out["mv_digamma"] = np.array([ef.multivariate_digamma(3.7, 4), ef.multivariate_digamma(2.2, 2)])
+    out["mv_gammaln"] = np.array([ef.multivariate_gammaln(3.7, 4), ef.multivariate_gammaln(2.2, 2)])
+    # packing: constrain / unconstrain over a bounds grid, ModelParamsDict layout
+    fv = rng.normal(0, 1, 11)
+    for i, (lb, ub) in enumerate([(-np.inf, np.inf), (0.0, np.inf), (-1.5, np.inf), (-np.inf, 2.0),
+                                  (-1.0, 3.0)]):
+        c = vb.Parameters.constrain(fv, lb, ub)
+        out["con%d" % i] = c
+        out["unc%d" % i] = vb.Parameters.unconstrain(c, lb, ub)
+    out["con_free"] = fv
+    par = build_par(vb, 3, 4, 0.25)
+    x = rng.normal(0, 0.4, par.free_size())
+    par.set_free(x)
+    out.update(pack_free=x, pack_vector=par.get_vector(), pack_free_back=par.get_free(),
+               pack_names=np.array([str(s) for s in par.names()]),
+               pack_free_index=np.array([[r.start, r.stop] for r in par.free_indices_dict.values()]),
+               pack_e_log_tau=par["tau"].e_log(), pack_tau_entropy=par["tau"].entropy(),
+               pack_u_entropy=par["u"].entropy(), pack_u_var=par["u"].var())
+    np.savez_compressed(os.path.join(OUT, "forward.npz"), **out)
+    print("forward.npz:", len(out), "arrays")
+
+
+def main():
+    vb = import_reference()
+    import LinearResponseVariationalBayes.Modeling as M
+    import LinearResponseVariationalBayes.ExponentialFamilies as ef
+    mods = (vb, M, ef)
+    forward_cases(mods)          # before gammaln is continued: pure reference behaviour
+    complex_safe_gammaln()
+    glmm_case(mods, "glmm_small", N=400, K=3, G=12, Q=4, seed=11, lb=0.0, weights=True,
+              empty=[5], full_hessian=True)
+    glmm_case(mods, "glmm_bounds", N=1500, K=5, G=30, Q=8, seed=12, lb=0.05, weights=False,
+              empty=[], full_hessian=False)
+    glmm_case(mods, "glmm_k9", N=900, K=9, G=20, Q=6, seed=13, lb=0.0, weights=True,
+              empty=[0, 19], full_hessian=False)
+
+
+if __name__ == "__main__":
+    main()
