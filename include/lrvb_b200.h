@@ -117,11 +117,13 @@ int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev);
 /* ---- sparse Hessian export ------------------------------------------------------------
  * Replaces get_sparse_sub_hessian + csr_matrix summation (SparseObjectives.py:591-619):
  * exact zeros dropped, columns sorted, int32 indices, one entry per coordinate.
- * _nnz counts (syncs; returns nnz of the cached Hessian), _fill writes
- * indptr (D+1,), indices (nnz,), data (nnz,) -- all dev. */
-int lrvb_glmm_hessian_csr_nnz(lrvb_glmm* h, int64_t* nnz, void* stream);
-int lrvb_glmm_hessian_csr_fill(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
-                               double* data_dev, void* stream);
+ * _capacity returns the structural upper bound Dg^2 + 4 Dg G + 4 G on nnz (no device work).
+ * lrvb_glmm_hessian_csr writes indptr (D+1,), indices and data (first nnz of `capacity` entries)
+ * and the actual nnz into the DEVICE scalar nnz_dev; it never synchronises, the caller reads
+ * nnz_dev when it needs the size.  capacity must be >= the structural bound. */
+int lrvb_glmm_hessian_csr_capacity(const lrvb_glmm* h, int64_t* capacity);
+int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
+                          double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream);
 
 /* ---- Hessian-vector product -------------------------------------------------------------
  * Replaces Objective.fun_free_hvp (SparseObjectives.py:183-187) at the point of the last

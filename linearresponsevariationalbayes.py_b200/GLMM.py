@@ -61,12 +61,27 @@ class DeviceCSR(object):
     int32 sorted within each row, ``values`` (nnz) float64 -- the canonical form scipy produces
     from get_sparse_sub_hessian triplets (SparseObjectives.py:591-619)."""
 
-    def __init__(self, crow, col, val, shape):
-        self.crow_indices, self.col_indices, self.values, self.shape = crow, col, val, tuple(shape)
+    def __init__(self, crow, col, val, shape, nnz_dev=None):
+        # col / val may be over-allocated to the structural capacity; the actual nnz sits in a
+        # device scalar and is read (one sync) only when a size is needed
+        self.crow_indices, self.shape = crow, tuple(shape)
+        self._col, self._val, self._nnz_dev, self._nnz = col, val, nnz_dev, None
+        if nnz_dev is None:
+            self._nnz = int(val.numel())
 
     @property
     def nnz(self):
-        return int(self.values.numel())
+        if self._nnz is None:
+            self._nnz = int(self._nnz_dev.item())
+        return self._nnz
+
+    @property
+    def col_indices(self):
+        return self._col[:self.nnz]
+
+    @property
+    def values(self):
+        return self._val[:self.nnz]
 
     def to_scipy(self):
         import scipy.sparse
@@ -295,14 +310,15 @@ class LogisticGLMM(object):
     def hessian_csr(self):
         """Device CSR of the cached Hessian."""
         torch = nat.require_cuda()
-        nnz = ctypes.c_int64()
-        nat.check(self._lib.lrvb_glmm_hessian_csr_nnz(self._h, ctypes.byref(nnz), nat.stream_ptr()))
+        cap = ctypes.c_int64()
+        nat.check(self._lib.lrvb_glmm_hessian_csr_capacity(self._h, ctypes.byref(cap)))
         crow = torch.empty(self.D + 1, dtype=torch.int32, device=self.device)
-        col = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
-        val = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
-        nat.check(self._lib.lrvb_glmm_hessian_csr_fill(self._h, nat.ptr(crow), nat.ptr(col),
-                                                       nat.ptr(val), nat.stream_ptr()))
-        return DeviceCSR(crow, col, val, (self.D, self.D))
+        col = torch.empty(cap.value, dtype=torch.int32, device=self.device)
+        val = torch.empty(cap.value, dtype=torch.float64, device=self.device)
+        nnz = torch.empty((), dtype=torch.int64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_hessian_csr(self._h, nat.ptr(crow), nat.ptr(col), nat.ptr(val),
+                                                  cap.value, nat.ptr(nnz), nat.stream_ptr()))
+        return DeviceCSR(crow, col, val, (self.D, self.D), nnz_dev=nnz)
 
     def hvp_cached(self, v_dev, out=None, include_A=True):
         """H v with the cached Hessian; v_dev a CUDA fp64 tensor (D,)."""

@@ -53,13 +53,16 @@ int lrvb_version(void) { return 100; }
 int lrvb_glmm_destroy(lrvb_glmm* h) {
   if (!h) return LRVB_OK;
   void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart,
-                  h->jobs, h->grampart, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk,
+                  h->jobs, h->grampart, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
                   h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
                   h->schurpart};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
   return LRVB_OK;
 }
@@ -142,8 +145,8 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   h->obs_smem = sizeof(double) * ((size_t)h->obs_tn * K + 2 * K + 2 * Q + 2 * h->obs_tn + 32);
   {
     int per_sm = (int)(220 * 1024 / h->obs_smem);
-    if (per_sm > 2048 / h->obs_tn) per_sm = 2048 / h->obs_tn;
-    if (per_sm > 6) per_sm = 6;
+    if (per_sm > 768 / h->obs_tn) per_sm = 768 / h->obs_tn;   // __launch_bounds__(256, 3)
+    if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     int64_t nt = (N + h->obs_tn - 1) / h->obs_tn;
     int64_t gmax = (int64_t)kNumSMs * per_sm;
@@ -176,8 +179,10 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     h->gram_jpc = (h->gram_jobs + h->gram_grid_y - 1) / h->gram_grid_y;
     h->gram_split = 8 / h->gram_jpc;
     if (h->gram_split < 1) h->gram_split = 1;
-    h->gram_tn = (K <= 24) ? 256 : (K <= 56 ? 128 : 64);
-    size_t tile = sizeof(double) * ((size_t)h->gram_tn * K + 3 * h->gram_tn);
+    // one pipeline stage <= ~54 KB so that two CTAs x two stages fit in an SM's shared memory
+    h->gram_tn = 256;
+    while (h->gram_tn > 16 && sizeof(double) * (size_t)h->gram_tn * (K + 3) > 54 * 1024) h->gram_tn >>= 1;
+    size_t tile = 2 * sizeof(double) * ((size_t)h->gram_tn * K + 3 * h->gram_tn);
     size_t red = (h->gram_split > 1) ? sizeof(double) * (size_t)h->gram_jpc * kRT * kRT * 64 : 0;
     h->gram_smem = tile > red ? tile : red;
     int64_t nt = (N + h->gram_tn - 1) / h->gram_tn;
@@ -202,6 +207,9 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   CREATE_TRY(dev_alloc(&h->outg, 1 + (size_t)Dg + (size_t)Dg * Dg));
   h->A = h->outg + 1 + Dg;
   CREATE_TRY(dev_alloc(&h->scal, 32));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CREATE_CUDA(cudaStreamSynchronize(st));
 #undef CREATE_TRY
 #undef CREATE_CUDA

@@ -186,12 +186,17 @@ struct lrvb_glmm {
   int hess_valid = 0;
   int grad_valid = 0;
   // optional per-kernel timing (bench): events around the whole eval, k_obs and k_gram
+  // side stream: the HBM-bound per-group pass runs beside the FP64-bound Gram kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int timing = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int ev_order = -1;
   // CSR
   int32_t* rowcnt = nullptr;  // (D+1)
   int32_t* scanblk = nullptr; // scan scratch
+  int32_t* csrwork = nullptr; // cntA | coltot | chunkcnt | chunkoff
+  int csr_cg = 0, csr_nchunk = 0;
   int64_t csr_nnz = -1;
   // solver scratch
   double* cgbuf = nullptr;    // 6*D

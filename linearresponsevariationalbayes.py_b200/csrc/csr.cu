@@ -7,66 +7,21 @@
 //   r <  Dg      : A[r,:] , B[g,0,r] for g = 0..G-1 , B[g,1,r] for g = 0..G-1
 //   r = Dg+g     : B[g,0,:] , L[g].mm , L[g].mi
 //   r = Dg+G+g   : B[g,1,:] , L[g].mi , L[g].ii
-// so the column order is already sorted and every kernel below only has to compact in order.
+// so the column order is already sorted and every kernel only compacts in order.
+//
+// The global rows are columns of B (group-major in memory), so they are produced by a
+// transposing pass: a CTA stages a chunk of kCG groups of B in shared memory (coalesced), then
+// each warp takes one (side, global row) column and ballot-compacts its kCG entries into a
+// contiguous, coalesced segment of that CSR row.  Per-(chunk, column) counts are scanned over
+// chunks to give each segment its offset.  Nothing synchronises with the host: nnz is left in a
+// device scalar.
 #include "common.cuh"
 
 namespace lrvb {
 
-__device__ __forceinline__ double global_row_elem(const double* __restrict__ A,
-                                                  const double* __restrict__ B, int r, int64_t j,
-                                                  int Dg, int G) {
-  if (j < Dg) return A[(size_t)r * Dg + j];
-  j -= Dg;
-  if (j < G) return B[(size_t)j * 2 * Dg + r];
-  j -= G;
-  return B[(size_t)j * 2 * Dg + Dg + r];
-}
+constexpr int kScanChunk = 2048;  // per CTA (256 threads x 8)
 
-// block-wide exclusive scan of a 0/1 flag, in thread order; returns offset, total in *total
-__device__ __forceinline__ int block_excl_scan_flag(bool f, int* wsum, int* total) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const unsigned m = __ballot_sync(0xffffffffu, f);
-  const int inw = __popc(m & ((1u << lane) - 1));
-  __syncthreads();
-  if (lane == 0) wsum[wid] = __popc(m);
-  __syncthreads();
-  int off = 0, tot = 0;
-  for (int w = 0; w < nw; ++w) {
-    const int c = wsum[w];
-    if (w < wid) off += c;
-    tot += c;
-  }
-  *total = tot;
-  return off + inw;
-}
-
-// FILL = false: count -> rowcnt[r].  FILL = true: write indices/data at indptr[r].
-template <bool FILL>
-__global__ void __launch_bounds__(256)
-k_csr_global_rows(const double* __restrict__ A, const double* __restrict__ B, int Dg, int G,
-                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ indptr,
-                  int32_t* __restrict__ indices, double* __restrict__ data) {
-  __shared__ int wsum[8];
-  const int r = blockIdx.x;
-  const int64_t len = Dg + 2 * (int64_t)G;
-  int64_t base = FILL ? indptr[r] : 0;
-  int count = 0;
-  for (int64_t j0 = 0; j0 < len; j0 += blockDim.x) {
-    const int64_t j = j0 + threadIdx.x;
-    const double v = (j < len) ? global_row_elem(A, B, r, j, Dg, G) : 0.0;
-    const bool nz = (v != 0.0);
-    int tot;
-    const int off = block_excl_scan_flag(nz, wsum, &tot);
-    if (FILL && nz) {
-      indices[base + off] = (int32_t)j;
-      data[base + off] = v;
-    }
-    base += tot;
-    count += tot;
-  }
-  if (!FILL && threadIdx.x == 0) rowcnt[r] = count;
-}
-
+// ---- local rows: one warp per row ------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_csr_local_rows(const double* __restrict__ B, const double* __restrict__ L, int Dg, int G,
@@ -110,9 +65,118 @@ k_csr_local_rows(const double* __restrict__ B, const double* __restrict__ L, int
   }
 }
 
-// ---- exclusive scan of rowcnt (n entries) into indptr (n+1 entries), 3 phases --------------------
-constexpr int kScanChunk = 2048;  // per CTA (256 threads x 8)
+// ---- global rows, part 1: the dense block A (one warp per row) -----------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_csr_A_rows(const double* __restrict__ A, int Dg, int32_t* __restrict__ cntA,
+             const int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
+             double* __restrict__ data) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= Dg) return;
+  const double* a = A + (size_t)r * Dg;
+  int64_t base = FILL ? indptr[r] : 0;
+  int count = 0;
+  for (int c0 = 0; c0 < Dg; c0 += 32) {
+    const int c = c0 + lane;
+    const double v = (c < Dg) ? a[c] : 0.0;
+    const bool nz = (v != 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if (FILL && nz) {
+      const int off = __popc(m & ((1u << lane) - 1));
+      indices[base + off] = c;
+      data[base + off] = v;
+    }
+    base += __popc(m);
+    count += __popc(m);
+  }
+  if (!FILL && lane == 0) cntA[r] = count;
+}
 
+// ---- global rows, part 2: columns of B, chunked over groups -----------------------------------
+// chunkcnt / chunkoff: (nchunk, 2*Dg) int32, column c = side*Dg + r.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_csr_B_cols(const double* __restrict__ B, int Dg, int G, int CG, int32_t* __restrict__ chunkcnt,
+             const int32_t* __restrict__ chunkoff, const int32_t* __restrict__ cntA,
+             const int32_t* __restrict__ coltot, const int32_t* __restrict__ indptr,
+             int32_t* __restrict__ indices, double* __restrict__ data) {
+  extern __shared__ double tile[];   // CG x (2*Dg + 1)  (+1: conflict-free column reads)
+  const int ncol = 2 * Dg, ld = ncol + 1;
+  const int chunk = blockIdx.x;
+  const int g0 = chunk * CG;
+  const int ng = (G - g0 < CG) ? (G - g0) : CG;
+  const double* src = B + (size_t)g0 * ncol;
+  for (int e = threadIdx.x; e < ng * ncol; e += blockDim.x) {
+    const int gl = e / ncol, c = e - gl * ncol;
+    tile[gl * ld + c] = src[e];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < ncol; c += 8) {
+    const int side = (c >= Dg) ? 1 : 0, r = c - side * Dg;
+    int64_t base = 0;
+    if (FILL)
+      base = (int64_t)indptr[r] + cntA[r] + (side ? coltot[r] : 0) + chunkoff[(size_t)chunk * ncol + c];
+    int count = 0;
+    for (int s0 = 0; s0 < ng; s0 += 32) {
+      const int gl = s0 + lane;
+      const double v = (gl < ng) ? tile[gl * ld + c] : 0.0;
+      const bool nz = (v != 0.0);
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (FILL && nz) {
+        const int off = __popc(m & ((1u << lane) - 1));
+        indices[base + off] = Dg + side * G + g0 + gl;
+        data[base + off] = v;
+      }
+      base += __popc(m);
+      count += __popc(m);
+    }
+    if (!FILL && lane == 0) chunkcnt[(size_t)chunk * ncol + c] = count;
+  }
+}
+
+// exclusive scan of chunkcnt over chunks, one CTA per column; coltot[c] = column total
+__global__ void __launch_bounds__(256)
+k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunkoff,
+              int32_t* __restrict__ coltot, int nchunk, int ncol) {
+  __shared__ int wsum[8];
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int carry = 0;
+  for (int s0 = 0; s0 < nchunk; s0 += 256) {
+    const int i = s0 + threadIdx.x;
+    const int cnt = (i < nchunk) ? chunkcnt[(size_t)i * ncol + c] : 0;
+    int v = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < wid) off += wsum[w];
+      tot += wsum[w];
+    }
+    if (i < nchunk) chunkoff[(size_t)i * ncol + c] = carry + off + v - cnt;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) coltot[c] = carry;
+}
+
+// rowcnt[r] for the global rows
+__global__ void k_csr_global_rowcnt(const int32_t* __restrict__ cntA,
+                                    const int32_t* __restrict__ coltot, int Dg,
+                                    int32_t* __restrict__ rowcnt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < Dg) rowcnt[r] = cntA[r] + coltot[r] + coltot[Dg + r];
+}
+
+// ---- exclusive scan of rowcnt (n entries) into indptr (n+1 entries), 3 phases --------------------
 __global__ void __launch_bounds__(256)
 k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk) {
   __shared__ double red[32];
@@ -125,7 +189,8 @@ k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk
   if (threadIdx.x == 0) blk[blockIdx.x] = (int64_t)t;
 }
 
-__global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restrict__ total) {
+__global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restrict__ total,
+                           int64_t* __restrict__ nnz_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int64_t run = 0;
   for (int i = 0; i < nblk; ++i) {
@@ -134,13 +199,13 @@ __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restr
     run += c;
   }
   *total = run;
+  if (nnz_out) *nnz_out = run;
 }
 
 __global__ void __launch_bounds__(256)
 k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restrict__ blk,
              const int64_t* __restrict__ total, int32_t* __restrict__ indptr) {
   __shared__ int wsum[8];
-  __shared__ int carry_s;
   const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t carry = blk[blockIdx.x];
@@ -165,8 +230,34 @@ k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restri
     if (i < n) indptr[i] = (int32_t)(carry + off + v - c);
     carry += tot;
   }
-  (void)carry_s;
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) indptr[n] = (int32_t)(*total);
+}
+
+static int csr_chunk_groups(int Dg) {
+  // stage CG x (2 Dg + 1) doubles in <= ~96 KB of shared memory
+  int cg = 32;
+  while (cg > 4 && sizeof(double) * (size_t)cg * (2 * Dg + 1) > 96 * 1024) cg >>= 1;
+  return cg;
+}
+
+static int ensure_csr_scratch(lrvb_glmm* h) {
+  if (h->rowcnt) return LRVB_OK;
+  const int Dg = h->Dg, G = h->G;
+  const int64_t D = h->D;
+  const int nblk = cdiv(D, kScanChunk);
+  const int CG = csr_chunk_groups(Dg);
+  const int nchunk = cdiv(G, CG) > 0 ? cdiv(G, CG) : 1;
+  h->csr_cg = CG;
+  h->csr_nchunk = nchunk;
+  LRVB_CUDA(cudaMalloc((void**)&h->rowcnt, sizeof(int32_t) * (size_t)(D + 1)));
+  LRVB_CUDA(cudaMalloc((void**)&h->scanblk, sizeof(int64_t) * ((size_t)nblk + 2)));
+  // cntA (Dg) | coltot (2Dg) | chunkcnt (nchunk*2Dg) | chunkoff (nchunk*2Dg)
+  LRVB_CUDA(cudaMalloc((void**)&h->csrwork,
+                       sizeof(int32_t) * ((size_t)3 * Dg + (size_t)4 * Dg * nchunk + 4)));
+  const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
+  cudaFuncSetAttribute(k_csr_B_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_B_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return LRVB_OK;
 }
 
 }  // namespace lrvb
@@ -175,61 +266,69 @@ using namespace lrvb;
 
 extern "C" {
 
-int lrvb_glmm_hessian_csr_nnz(lrvb_glmm* h, int64_t* nnz, void* stream) {
-  LRVB_REQUIRE(h != nullptr && nnz != nullptr, "lrvb_glmm_hessian_csr_nnz: NULL argument");
-  if (!h->hess_valid) {
-    set_error("lrvb_glmm_hessian_csr_nnz: no Hessian cached (call lrvb_glmm_eval with order 2)");
-    return LRVB_ESTATE;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int Dg = h->Dg, G = h->G;
-  const int64_t D = h->D;
-  const int nblk = cdiv(D, kScanChunk);
-  if (!h->rowcnt) {
-    LRVB_CUDA(cudaMalloc((void**)&h->rowcnt, sizeof(int32_t) * (size_t)(D + 1)));
-    LRVB_CUDA(cudaMalloc((void**)&h->scanblk, sizeof(int64_t) * ((size_t)nblk + 2)));
-  }
-  k_csr_global_rows<false><<<Dg, 256, 0, st>>>(h->A, h->B, Dg, G, h->rowcnt, nullptr, nullptr, nullptr);
-  LRVB_CHECK_LAUNCH();
-  if (G > 0) {
-    k_csr_local_rows<false><<<cdiv(2 * (int64_t)G, 8), 256, 0, st>>>(h->B, h->L, Dg, G, h->rowcnt,
-                                                                     nullptr, nullptr, nullptr);
-    LRVB_CHECK_LAUNCH();
-  }
-  int64_t* blk = (int64_t*)h->scanblk;
-  k_scan_sum<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk);
-  LRVB_CHECK_LAUNCH();
-  k_scan_top<<<1, 32, 0, st>>>(blk, nblk, blk + nblk);
-  LRVB_CHECK_LAUNCH();
-  int64_t total = 0;
-  LRVB_CUDA(cudaMemcpyAsync(&total, blk + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  LRVB_CUDA(cudaStreamSynchronize(st));
-  LRVB_REQUIRE(total < (int64_t)2147483647, "Hessian has %lld nonzeros: exceeds int32 CSR indices",
-               (long long)total);
-  h->csr_nnz = total;
-  *nnz = total;
+int lrvb_glmm_hessian_csr_capacity(const lrvb_glmm* h, int64_t* capacity) {
+  LRVB_REQUIRE(h != nullptr && capacity != nullptr, "lrvb_glmm_hessian_csr_capacity: NULL argument");
+  *capacity = (int64_t)h->Dg * h->Dg + 4 * (int64_t)h->Dg * h->G + 4 * (int64_t)h->G;
   return LRVB_OK;
 }
 
-int lrvb_glmm_hessian_csr_fill(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
-                               double* data_dev, void* stream) {
-  LRVB_REQUIRE(h != nullptr && indptr_dev && indices_dev && data_dev,
-               "lrvb_glmm_hessian_csr_fill: NULL argument");
-  if (!h->hess_valid || h->csr_nnz < 0) {
-    set_error("lrvb_glmm_hessian_csr_fill: call lrvb_glmm_hessian_csr_nnz first");
+int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
+                          double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream) {
+  LRVB_REQUIRE(h != nullptr && indptr_dev && indices_dev && data_dev && nnz_dev,
+               "lrvb_glmm_hessian_csr: NULL argument");
+  if (!h->hess_valid) {
+    set_error("lrvb_glmm_hessian_csr: no Hessian cached (call lrvb_glmm_eval with order 2)");
     return LRVB_ESTATE;
   }
+  int64_t cap = 0;
+  lrvb_glmm_hessian_csr_capacity(h, &cap);
+  LRVB_REQUIRE(capacity >= cap, "lrvb_glmm_hessian_csr: capacity %lld < structural bound %lld",
+               (long long)capacity, (long long)cap);
+  LRVB_REQUIRE(cap < (int64_t)2147483647, "Hessian may have %lld nonzeros: exceeds int32 CSR indices",
+               (long long)cap);
+  LRVB_TRY(ensure_csr_scratch(h));
   cudaStream_t st = (cudaStream_t)stream;
-  const int Dg = h->Dg, G = h->G;
+  const int Dg = h->Dg, G = h->G, CG = h->csr_cg, nchunk = h->csr_nchunk;
   const int64_t D = h->D;
   const int nblk = cdiv(D, kScanChunk);
+  int32_t* cntA = h->csrwork;
+  int32_t* coltot = cntA + Dg;
+  int32_t* chunkcnt = coltot + 2 * Dg;
+  int32_t* chunkoff = chunkcnt + (size_t)2 * Dg * nchunk;
   int64_t* blk = (int64_t*)h->scanblk;
-  k_scan_apply<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk, blk + nblk, indptr_dev);
-  LRVB_CHECK_LAUNCH();
-  k_csr_global_rows<true><<<Dg, 256, 0, st>>>(h->A, h->B, Dg, G, nullptr, indptr_dev, indices_dev,
-                                              data_dev);
+  const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
+
+  // ---- counts ----
+  k_csr_A_rows<false><<<cdiv(Dg, 8), 256, 0, st>>>(h->A, Dg, cntA, nullptr, nullptr, nullptr);
   LRVB_CHECK_LAUNCH();
   if (G > 0) {
+    k_csr_B_cols<false><<<nchunk, 256, smem, st>>>(h->B, Dg, G, CG, chunkcnt, nullptr, nullptr,
+                                                   nullptr, nullptr, nullptr, nullptr);
+    LRVB_CHECK_LAUNCH();
+    k_csr_colscan<<<2 * Dg, 256, 0, st>>>(chunkcnt, chunkoff, coltot, nchunk, 2 * Dg);
+    LRVB_CHECK_LAUNCH();
+    k_csr_local_rows<false><<<cdiv(2 * (int64_t)G, 8), 256, 0, st>>>(h->B, h->L, Dg, G, h->rowcnt,
+                                                                     nullptr, nullptr, nullptr);
+    LRVB_CHECK_LAUNCH();
+  } else {
+    LRVB_CUDA(cudaMemsetAsync(coltot, 0, sizeof(int32_t) * 2 * Dg, st));
+  }
+  k_csr_global_rowcnt<<<cdiv(Dg, 256), 256, 0, st>>>(cntA, coltot, Dg, h->rowcnt);
+  LRVB_CHECK_LAUNCH();
+  // ---- indptr ----
+  k_scan_sum<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk);
+  LRVB_CHECK_LAUNCH();
+  k_scan_top<<<1, 32, 0, st>>>(blk, nblk, blk + nblk, nnz_dev);
+  LRVB_CHECK_LAUNCH();
+  k_scan_apply<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk, blk + nblk, indptr_dev);
+  LRVB_CHECK_LAUNCH();
+  // ---- fill ----
+  k_csr_A_rows<true><<<cdiv(Dg, 8), 256, 0, st>>>(h->A, Dg, nullptr, indptr_dev, indices_dev, data_dev);
+  LRVB_CHECK_LAUNCH();
+  if (G > 0) {
+    k_csr_B_cols<true><<<nchunk, 256, smem, st>>>(h->B, Dg, G, CG, nullptr, chunkoff, cntA, coltot,
+                                                  indptr_dev, indices_dev, data_dev);
+    LRVB_CHECK_LAUNCH();
     k_csr_local_rows<true><<<cdiv(2 * (int64_t)G, 8), 256, 0, st>>>(h->B, h->L, Dg, G, nullptr,
                                                                     indptr_dev, indices_dev, data_dev);
     LRVB_CHECK_LAUNCH();

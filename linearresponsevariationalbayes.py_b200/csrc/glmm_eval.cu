@@ -69,7 +69,7 @@ __device__ __forceinline__ void gh_node(double t, double c, double wq, GHSums& s
 
 // One thread per observation of a TN-row tile staged in shared memory (blockDim.x == TN).
 template <int ORDER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
       const double* __restrict__ w, const double* __restrict__ vec, const double* __restrict__ gh,
       double* __restrict__ W, double* __restrict__ klpart, double* __restrict__ gradpart,
@@ -186,7 +186,9 @@ k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t*
   const double kl = block_sum(klacc, red);
   if (tid == 0) klpart[blockIdx.x] = kl;
   if (ORDER >= 1) {
-    double* gp = gradpart + (size_t)blockIdx.x * 2 * K;
+    // layout (2K, n_cta): column-major over CTAs so the finishing reduce reads contiguously
+    double* gp = gradpart + blockIdx.x;
+    const size_t gs = gridDim.x;
     if (caseA) {
       __syncthreads();
       double* buf = xs;  // P*K*2 <= TN*K*... needs 2*P*K <= TN*K  (K >= 2) or falls in lms
@@ -199,15 +201,15 @@ k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t*
       if (tid < 2 * K) {
         double s = 0.0;
         for (int p = 0; p < P; ++p) s += buf[(size_t)p * 2 * K + tid];
-        gp[tid] = s;
+        gp[(size_t)tid * gs] = s;
       }
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = tid + c * TN;
         if (c < ncol && k < K) {
-          gp[k] = gm[c];
-          gp[K + k] = gv[c];
+          gp[(size_t)k * gs] = gm[c];
+          gp[(size_t)(K + k) * gs] = gv[c];
         }
       }
     }
@@ -364,8 +366,7 @@ k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob
        double* __restrict__ grampart, int64_t N, int K, int KT, int TN, int n_jobs, int jpc,
        int n_split, int ny, int n_chunk) {
   extern __shared__ __align__(16) double sm[];
-  double* xs = sm;                       // TN*K
-  double* wgt = xs + (size_t)TN * K;     // 3*TN : a, b, c
+  // two stages of [X tile (TN*K) | weights a, b, c (3*TN)]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jg = blockIdx.x % ny;
   const int chunk = blockIdx.x / ny;
@@ -398,28 +399,49 @@ k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob
       const int it = jb.i0 + i, jt = jb.j0 + j;
       if (active && it < KT && jt < KT && (fam == 1 || it <= jt)) tmask |= 1u << (i * kRT + j);
     }
-  const double* wsel = wgt + (size_t)fam * TN;
   int ni = KT - jb.i0, nj = KT - jb.j0;
   ni = ni > kRT ? kRT : ni;
   nj = nj > kRT ? kRT : nj;
   const bool tri = (fam != 1) && (jb.i0 == jb.j0);
 
+  // 2-stage cp.async pipeline over this CTA's tiles: the loads of tile t+1 (X rows and the three
+  // weight rows) are in flight while the warps issue the DMMAs of tile t.
+  const size_t stage_elems = (size_t)TN * K + 3 * (size_t)TN;
   const int64_t ntiles = (N + TN - 1) / TN;
+  auto issue_tile = [&](int64_t tile, int stage) {
+    double* sx = sm + (size_t)stage * stage_elems;
+    double* sw = sx + (size_t)TN * K;
+    const int64_t n0 = tile * TN;
+    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
+    tile_load_async(sx, X + n0 * K, (int64_t)rows * K);
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      tile_load_async(sw + (size_t)f * TN, W + (int64_t)(2 + f) * N + n0, rows);
+    if (rows < TN) {   // tail rows: zero weights and finite (zero) data
+      for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) sx[e] = 0.0;
+      for (int r = tid; r < 3 * TN; r += blockDim.x)
+        if (r % TN >= rows) sw[r] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  int stage = 0;
+  if (chunk < ntiles) issue_tile(chunk, 0);
   for (int64_t tile = chunk; tile < ntiles; tile += n_chunk) {
     const int64_t n0 = tile * TN;
     const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
-    __syncthreads();
-    tile_load_async(xs, X + n0 * K, (int64_t)rows * K);
-    for (int r = tid; r < 3 * TN; r += blockDim.x) {
-      const int f = r / TN, n = r - f * TN;
-      wgt[r] = (n < rows) ? W[(int64_t)(2 + f) * N + n0 + n] : 0.0;
+    const bool more = tile + n_chunk < ntiles;
+    if (more) {
+      issue_tile(tile + n_chunk, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    if (rows < TN)
-      for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) xs[e] = 0.0;
-    cp_async_commit_wait_all();
     __syncthreads();
-    if (tmask) gram_dispatch(acc, ni, nj, tri, xs, wsel, K, cola, colb, fam, split, n_split,
-                             (rows + 3) >> 2, lr);
+    const double* sx = sm + (size_t)stage * stage_elems;
+    if (tmask) gram_dispatch(acc, ni, nj, tri, sx, sx + (size_t)TN * K + (size_t)fam * TN, K, cola,
+                             colb, fam, split, n_split, (rows + 3) >> 2, lr);
+    __syncthreads();   // every warp is done with this stage before it is refilled
+    stage ^= 1;
   }
 
   // in-CTA reduction over the k-step splits (fixed order), then one partial per (chunk, job)
@@ -634,10 +656,12 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
   d2 = block_sum(d2, red);
   if (tid == 0) { sh[0] = data_ll; sh[1] = d0; sh[2] = d1; sh[3] = d2; }
   if (ORDER >= 1) {
-    for (int k = tid; k < 2 * K; k += blockDim.x) {
+    // one warp per column, lanes over the per-CTA partials (fixed order: deterministic)
+    for (int k = tid >> 5; k < 2 * K; k += blockDim.x >> 5) {
       double s = 0.0;
-      for (int p = 0; p < n_gp; ++p) s += gradpart[(size_t)p * 2 * K + k];
-      gsum[k] = s;
+      for (int p = tid & 31; p < n_gp; p += 32) s += gradpart[(size_t)k * n_gp + p];
+      s = warp_sum(s);
+      if ((tid & 31) == 0) gsum[k] = s;
     }
   }
   __syncthreads();
@@ -759,19 +783,23 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   }
   const int n_obs_cta = (N > 0) ? h->obs_grid : 0;
 
+  // The per-group pass is HBM/latency bound, the Gram kernel FP64 bound: for order 2 they run
+  // side by side (fork after k_obs, join before the group-level chain rule).
+  const bool forked = (order >= 2 && G > 0 && N > 0);
+  double* outp = out_global ? out_global : h->outg;
   if (order >= 1 && G > 0) {
     const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
-    if (order == 1) k_group<1><<<ggrid, 256, 0, st>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
-    else k_group<2><<<ggrid, 256, 0, st>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
+    cudaStream_t gs = st;
+    if (forked) {
+      LRVB_CUDA(cudaEventRecord(h->ev_fork, st));
+      LRVB_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      gs = h->side;
+    }
+    if (order == 1) k_group<1><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
+    else k_group<2><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
     LRVB_CHECK_LAUNCH();
+    if (forked) LRVB_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
-  double* gl = grad_local ? grad_local : h->gradl;
-  if (order == 0) k_local<0><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  else if (order == 1) k_local<1><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  else k_local<2><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  LRVB_CHECK_LAUNCH();
-
-  double* outp = out_global ? out_global : h->outg;
   if (order >= 2) {
     LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
     if (N > 0) {
@@ -781,6 +809,17 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
           h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
       LRVB_CHECK_LAUNCH();
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
+    }
+  }
+  if (forked) LRVB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  double* gl = grad_local ? grad_local : h->gradl;
+  if (order == 0) k_local<0><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  else if (order == 1) k_local<1><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  else k_local<2><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
+  LRVB_CHECK_LAUNCH();
+
+  if (order >= 2) {
+    if (N > 0) {
       k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
           h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
           h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);

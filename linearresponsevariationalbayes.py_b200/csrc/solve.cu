@@ -266,6 +266,38 @@ __global__ void k_linv(const double* __restrict__ L, double* __restrict__ Linv, 
 // S = [A] - sum_g B_g^T L_g^-1 B_g  =  [A] - P^T Q  with P = B as a (2G, Dg) matrix and
 // Q = blockdiag(L_g^-1) P.  A warp owns a kRT x kRT rectangle (ri <= rj, the result is symmetric)
 // of 8x8 tiles for a chunk of groups; a k-step is 4 rows = 2 groups.
+template <int NI, int NJ, bool TRI>
+__device__ __forceinline__ void schur_ksteps(double (&acc)[kRT][kRT][2],
+                                             const double* __restrict__ B,
+                                             const double* __restrict__ Linv, int Dg, int G,
+                                             const int (&cola)[kRT], const int (&colb)[kRT],
+                                             int k0, int k1, int lr) {
+  const int which = lr & 1;
+  for (int ks = k0; ks < k1; ++ks) {
+    const int gi = 2 * ks + (lr >> 1);
+    const bool ok = gi < G;
+    const double* b0 = B + (size_t)(ok ? gi : 0) * 2 * Dg;
+    const double* b1 = b0 + Dg;
+    double w0 = 0.0, w1 = 0.0;
+    if (ok) {
+      const double* li = Linv + (size_t)gi * 3;
+      w0 = which ? li[1] : li[0];
+      w1 = which ? li[2] : li[1];
+    }
+    double fa[kRT], fb[kRT];
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      if (i < NI) fa[i] = (ok && cola[i] < Dg) ? (which ? b1[cola[i]] : b0[cola[i]]) : 0.0;
+      if (i < NJ) fb[i] = (ok && colb[i] < Dg) ? (w0 * b0[colb[i]] + w1 * b1[colb[i]]) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < kRT; ++i)
+#pragma unroll
+      for (int j = 0; j < kRT; ++j)
+        if (i < NI && j < NJ && (!TRI || i <= j)) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_schur(const double* __restrict__ B, const double* __restrict__ Linv, double* __restrict__ part,
         int Dg, int G, int R, int n_jobs, int n_chunk) {
@@ -299,30 +331,27 @@ k_schur(const double* __restrict__ B, const double* __restrict__ Linv, double* _
   const int ksteps = (G + 1) / 2;
   const int per = (ksteps + n_chunk - 1) / n_chunk;
   const int k0 = chunk * per, k1 = (k0 + per < ksteps) ? k0 + per : ksteps;
-  const int which = lr & 1;
-  for (int ks = k0; ks < k1; ++ks) {
-    const int gi = 2 * ks + (lr >> 1);
-    const bool ok = gi < G;
-    const double* b0 = B + (size_t)(ok ? gi : 0) * 2 * Dg;
-    const double* b1 = b0 + Dg;
-    double w0 = 0.0, w1 = 0.0;
-    if (ok) {
-      const double* li = Linv + (size_t)gi * 3;
-      w0 = which ? li[1] : li[0];
-      w1 = which ? li[2] : li[1];
+  int ni = DT - kRT * ri, nj = DT - kRT * rj;
+  ni = ni > kRT ? kRT : ni;
+  nj = nj > kRT ? kRT : nj;
+  // compile-time specialised on the live tiles: a predicated-off DMMA still occupies the pipe
+#define LRVB_S(NI, NJ, T) schur_ksteps<NI, NJ, T>(acc, B, Linv, Dg, G, cola, colb, k0, k1, lr)
+  if (ri == rj) {
+    switch (ni) {
+      case 1: LRVB_S(1, 1, true); break;
+      case 2: LRVB_S(2, 2, true); break;
+      case 3: LRVB_S(3, 3, true); break;
+      default: LRVB_S(4, 4, true); break;
     }
-    double fa[kRT], fb[kRT];
-#pragma unroll
-    for (int i = 0; i < kRT; ++i) {
-      fa[i] = (ok && cola[i] < Dg) ? (which ? b1[cola[i]] : b0[cola[i]]) : 0.0;
-      fb[i] = (ok && colb[i] < Dg) ? (w0 * b0[colb[i]] + w1 * b1[colb[i]]) : 0.0;
+  } else {
+    switch (nj) {   // ri < rj: the row rectangle is always full (ni == kRT)
+      case 1: LRVB_S(4, 1, false); break;
+      case 2: LRVB_S(4, 2, false); break;
+      case 3: LRVB_S(4, 3, false); break;
+      default: LRVB_S(4, 4, false); break;
     }
-#pragma unroll
-    for (int i = 0; i < kRT; ++i)
-#pragma unroll
-      for (int j = 0; j < kRT; ++j)
-        if (tmask & (1u << (i * kRT + j))) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
   }
+#undef LRVB_S
   double* out = part + ((size_t)chunk * n_jobs + job) * (kRT * kRT * 64);
   const int crow = lane >> 2, ccol = 2 * (lane & 3);
 #pragma unroll
