@@ -42,54 +42,69 @@ CPU_SAMPLE = dict(N=500_000, G=5_000)   # bounded sample of the workload for the
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML
+    (a thread polling every few ms; spawning nvidia-smi stalls the GPU for milliseconds and its
+    100 ms period misses a short timed region).  Falls back to one nvidia-smi query."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.power = [], set(), []
+        self.handle, self.nvml, self.max_mhz = None, None, None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception as exc:       # noqa: BLE001
+            self.error = "NVML unavailable: %s" % exc
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:          # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        if self.samples:
+            return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz,
+                        reasons=sorted(self.reasons), samples=len(self.samples),
+                        power_w_max=max(self.power) if self.power else None, source="nvml")
         try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None,
-                    sm_max_mhz=float(max(mx)) if mx else None, reasons=sorted(reasons),
-                    samples=len(sm))
+            out = subprocess.run(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                 "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            a, b2 = [float(v) for v in out.strip().split(",")[:2]]
+            return dict(sm_mhz=a, sm_max_mhz=b2, reasons=[], samples=1,
+                        source="nvidia-smi after the timed region (NVML polling failed)")
+        except Exception:              # noqa: BLE001
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampling unavailable"], samples=0)
 
 
 def synth_shard(torch, N, K, G, seed, device):
@@ -240,7 +255,7 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
     launches0 = lib.lrvb_launch_count()
@@ -268,6 +283,10 @@ def run_ours(args, wl):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
     value = world * N / (ms_per_step * 1e-3)
+    if rank == 0:
+        sm = np.sort(np.asarray(step_ms))
+        print("step ms: min %.3f median %.3f p90 %.3f max %.3f" % (
+            sm[0], sm[len(sm) // 2], sm[int(0.9 * (len(sm) - 1))], sm[-1]), file=sys.stderr)
     nnz = csr.nnz
 
     # ---------------- end to end through the public API (host buffers) ----------------
@@ -367,8 +386,8 @@ def _hbm_peak():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()

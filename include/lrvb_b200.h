@@ -109,10 +109,11 @@ int lrvb_glmm_eval(lrvb_glmm* h, const double* free_dev, int32_t order, double* 
 int lrvb_glmm_blocks(lrvb_glmm* h, double** A_dev, double** B_dev, double** L_dev);
 /* Overwrite the cached global block (after the all-reduce of out_global in a sharded job). */
 int lrvb_glmm_set_global_block(lrvb_glmm* h, const double* A_dev, void* stream);
-/* Per-observation derivative weights of the last eval: dev (5,N) rows
- * [dl/dz_mean, dl/dz_var, d2l/dz_mean2, d2l/dz_mean dz_var, d2l/dz_var2];
- * rows 2-4 only after order 2.  Borrowed pointer. */
-int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev);
+/* Per-observation derivative weights of the last eval: dev (5, *ld) rows
+ * [dl/dz_mean, dl/dz_var, d2l/dz_mean2, d2l/dz_mean dz_var, d2l/dz_var2], the
+ * first N entries of each row are the observations (row stride *ld >= N keeps rows 16-byte
+ * aligned); rows 2-4 only after order 2.  Borrowed pointer. */
+int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev, int64_t* ld);
 
 /* ---- sparse Hessian export ------------------------------------------------------------
  * Replaces get_sparse_sub_hessian + csr_matrix summation (SparseObjectives.py:591-619):

@@ -155,6 +155,8 @@ class LogisticGLMM(object):
             self.y = self.y.index_select(0, pd).contiguous()
             if self.w is not None:
                 self.w = self.w.index_select(0, pd).contiguous()
+        if self.X.numel() and self.X.data_ptr() % 16:
+            self.X = self.X.clone()   # a view into a larger buffer: the library needs 16-B alignment
         self.g = to_device(g_sorted, torch.int32).reshape(-1)
         if num_groups is None:
             num_groups = int(self.g.max().item()) + 1 if N > 0 else 0
@@ -300,9 +302,9 @@ class LogisticGLMM(object):
 
     def obs_weights(self):
         """(5, N) per-observation derivative weights of the last evaluation (sorted order)."""
-        w = ctypes.c_void_p()
-        nat.check(self._lib.lrvb_glmm_obs_weights(self._h, ctypes.byref(w)))
-        return _view(w.value, (5, self.N), self)
+        w, ld = ctypes.c_void_p(), ctypes.c_int64()
+        nat.check(self._lib.lrvb_glmm_obs_weights(self._h, ctypes.byref(w), ctypes.byref(ld)))
+        return _view(w.value, (5, ld.value), self)[:, :self.N]
 
     def set_global_block(self, A):
         nat.check(self._lib.lrvb_glmm_set_global_block(self._h, nat.ptr(A), nat.stream_ptr()))

@@ -4,6 +4,7 @@
 #include <new>
 #include <vector>
 #include "common.cuh"
+#include "gram_small.cuh"
 
 namespace lrvb {
 
@@ -82,7 +83,7 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   LRVB_REQUIRE(N == 0 || (X_dev && y_dev && g_dev), "lrvb_glmm_create: X, y, g must be non-NULL");
   LRVB_REQUIRE(N == 0 || G >= 1, "lrvb_glmm_create: observations but no groups");
   LRVB_REQUIRE(gh_x_host && gh_w_host && prior && bounds, "lrvb_glmm_create: NULL argument");
-  LRVB_REQUIRE((((uintptr_t)X_dev) & 7) == 0, "lrvb_glmm_create: X not 8-byte aligned");
+  LRVB_REQUIRE((((uintptr_t)X_dev) & 15) == 0, "lrvb_glmm_create: X not 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
 
   lrvb_glmm* h = new (std::nothrow) lrvb_glmm();
@@ -138,7 +139,8 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   }
 
   CREATE_TRY(dev_alloc(&h->vec, (size_t)h->D));
-  CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)N));
+  h->ldw = (N + 7) / 8 * 8;
+  CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)h->ldw));
 
   // observation pass geometry
   h->obs_tn = (K <= 27) ? 256 : (K <= 54 ? 128 : 64);
@@ -195,9 +197,16 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     CREATE_CUDA(cudaMemcpyAsync(h->jobs, jobs.data(), sizeof(GramJob) * jobs.size(),
                                 cudaMemcpyHostToDevice, st));
     CREATE_CUDA(cudaStreamSynchronize(st));
-    CREATE_TRY(dev_alloc(&h->grampart, (size_t)nchunk * h->gram_jobs * kRT * kRT * 64));
-    CREATE_CUDA(cudaMemsetAsync(h->grampart, 0,
-                                sizeof(double) * (size_t)nchunk * h->gram_jobs * kRT * kRT * 64, st));
+    size_t npart = (size_t)nchunk * h->gram_jobs * kRT * kRT * 64;
+    if (K <= 20) {
+      // small K: every warp owns the whole packed upper triangle (gram_small.cuh), one CTA per SM
+      h->gram_small = 1;
+      h->gram_grid_x = kNumSMs;
+      h->gram_grid_y = 1;
+      npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;
+    }
+    CREATE_TRY(dev_alloc(&h->grampart, npart));
+    CREATE_CUDA(cudaMemsetAsync(h->grampart, 0, sizeof(double) * npart, st));
   }
   configure_kernels(h->obs_smem, h->gram_smem);
 
@@ -293,13 +302,14 @@ int lrvb_glmm_set_global_block(lrvb_glmm* h, const double* A_dev, void* stream) 
   return LRVB_OK;
 }
 
-int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev) {
+int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev, int64_t* ld) {
   LRVB_REQUIRE(h != nullptr && W_dev != nullptr, "lrvb_glmm_obs_weights: NULL argument");
   if (!h->grad_valid) {
     set_error("lrvb_glmm_obs_weights: no evaluation of order >= 1 cached");
     return LRVB_ESTATE;
   }
   *W_dev = h->W;
+  if (ld) *ld = h->ldw;
   return LRVB_OK;
 }
 

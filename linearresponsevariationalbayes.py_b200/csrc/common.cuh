@@ -152,6 +152,7 @@ struct GramJob {
 // ---- the model handle --------------------------------------------------------------------
 struct lrvb_glmm {
   int64_t N = 0, D = 0;
+  int64_t ldw = 0;            // row stride of W (N rounded up to 8: 16-B aligned rows for TMA)
   int K = 0, G = 0, Q = 0, Dg = 0, KT = 0;  // KT = ceil(K/8) feature tiles
   int include_global = 1;
   int vecmode = 0;            // 1: evaluate in the constrained ("vector") parameterisation
@@ -163,7 +164,7 @@ struct lrvb_glmm {
   double* gh = nullptr;       // [2][Q]: c_q = sqrt(2) x_q ; what_q = w_q / sqrt(pi)
   int32_t* gptr = nullptr;    // (G+1) first observation of each group
   double* vec = nullptr;      // (D) constrained values
-  double* W = nullptr;        // (5, N) per-observation derivative weights
+  double* W = nullptr;        // (5, ldw) per-observation derivative weights
   // observation pass
   int obs_tn = 0, obs_grid = 0;
   size_t obs_smem = 0;
@@ -177,6 +178,7 @@ struct lrvb_glmm {
   // Gram
   int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0, gram_jpc = 0, gram_split = 0;
   size_t gram_smem = 0;
+  int gram_small = 0;         // K <= 20: packed whole-triangle-per-warp kernel (gram_small.cuh)
   lrvb::GramJob* jobs = nullptr;   // device (gram_jobs)
   double* grampart = nullptr;      // (gram_grid_x, gram_jobs, kRT*kRT, 64)
   // results

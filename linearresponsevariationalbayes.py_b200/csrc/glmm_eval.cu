@@ -15,6 +15,7 @@
 //   k_gram         X^T diag(a) X, X^T diag(b) S, S^T diag(c) S on the FP64 tensor cores (DMMA)
 //   k_local/k_border/k_gram_finish/k_global   chain rule to free coordinates, non-data terms
 #include "common.cuh"
+#include "gram_small.cuh"
 
 namespace lrvb {
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256, 3)
 k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
       const double* __restrict__ w, const double* __restrict__ vec, const double* __restrict__ gh,
       double* __restrict__ W, double* __restrict__ klpart, double* __restrict__ gradpart,
-      int64_t N, int K, int G, int Q) {
+      int64_t N, int64_t ldw, int K, int G, int Q) {
   extern __shared__ __align__(16) double sm[];
   const int TN = blockDim.x;
   const int tid = threadIdx.x;
@@ -151,12 +152,12 @@ k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t*
         lm = wn * (yn - s.Am);
         lv = -wn * s.As * h;
         W[n] = lm;
-        W[N + n] = lv;
+        W[ldw + n] = lv;
         if (ORDER >= 2) {
-          W[2 * N + n] = -wn * s.Amm;
-          W[3 * N + n] = -wn * s.Ams * h;
+          W[2 * ldw + n] = -wn * s.Amm;
+          W[3 * ldw + n] = -wn * s.Ams * h;
           // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
-          W[4 * N + n] = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
+          W[4 * ldw + n] = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
         }
       }
     }
@@ -224,7 +225,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(256)
 k_group(const double* __restrict__ X, const double* __restrict__ W,
         const int32_t* __restrict__ gptr, double* __restrict__ gsc, double* __restrict__ BR,
-        int64_t N, int K, int G) {
+        int64_t ldw, int K, int G) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nrow = (ORDER >= 2) ? 5 : 2;
@@ -234,7 +235,7 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
     for (int64_t n = nb + lane; n < ne; n += 32) {
 #pragma unroll
       for (int r = 0; r < 5; ++r)
-        if (r < nrow) s[r] += W[r * N + n];
+        if (r < nrow) s[r] += W[r * ldw + n];
     }
 #pragma unroll
     for (int r = 0; r < 5; ++r)
@@ -244,9 +245,9 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
       for (int r = 0; r < 5; ++r) gsc[(size_t)gi * 5 + r] = (r < nrow) ? s[r] : 0.0;
     }
     if (ORDER >= 2) {
-      const double* Wa = W + 2 * N;
-      const double* Wb = W + 3 * N;
-      const double* Wc = W + 4 * N;
+      const double* Wa = W + 2 * ldw;
+      const double* Wb = W + 3 * ldw;
+      const double* Wc = W + 4 * ldw;
       for (int k = lane; k < K; k += 32) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         int64_t n = nb;
@@ -363,8 +364,8 @@ __device__ __forceinline__ void gram_dispatch(double (&acc)[kRT][kRT][2], int ni
 // reads row n0 + (l&3), column 8 t + (l>>2) for both operands.
 __global__ void __launch_bounds__(256, 2)
 k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob* __restrict__ jobs,
-       double* __restrict__ grampart, int64_t N, int K, int KT, int TN, int n_jobs, int jpc,
-       int n_split, int ny, int n_chunk) {
+       double* __restrict__ grampart, int64_t N, int64_t ldw, int K, int KT, int TN, int n_jobs,
+       int jpc, int n_split, int ny, int n_chunk) {
   extern __shared__ __align__(16) double sm[];
   // two stages of [X tile (TN*K) | weights a, b, c (3*TN)]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -416,7 +417,7 @@ k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob
     tile_load_async(sx, X + n0 * K, (int64_t)rows * K);
 #pragma unroll
     for (int f = 0; f < 3; ++f)
-      tile_load_async(sw + (size_t)f * TN, W + (int64_t)(2 + f) * N + n0, rows);
+      tile_load_async(sw + (size_t)f * TN, W + (int64_t)(2 + f) * ldw + n0, rows);
     if (rows < TN) {   // tail rows: zero weights and finite (zero) data
       for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) sx[e] = 0.0;
       for (int r = tid; r < 3 * TN; r += blockDim.x)
@@ -530,6 +531,51 @@ k_gram_finish(const double* __restrict__ grampart, const GramJob* __restrict__ j
     const double v = -s * (1.0 / (ip * ip * iq * iq)) * (vecmode ? 1.0 : (ip - bd.beta_info) * (iq - bd.beta_info));
     A[(size_t)(bi0 + p) * Dg + bi0 + q] = v;
     A[(size_t)(bi0 + q) * Dg + bi0 + p] = v;
+  }
+}
+
+// Finish of the small-K packed Gram (gram_small.cuh): fixed-order sum of the per-CTA partials of
+// one packed tile, then the same chain rule as k_gram_finish.  Packed column p < K is x_p,
+// p >= K is s_{p-K}; only the upper triangle of the packed matrix was computed.
+__global__ void __launch_bounds__(256)
+k_gram_small_finish(const double* __restrict__ part, const double* __restrict__ vec,
+                    double* __restrict__ A, int K, int Dg, int NT, int n_cta, lrvb_glmm_bounds bd,
+                    int vecmode) {
+  __shared__ double red[4][64];
+  const int t = blockIdx.x;
+  int jt = 0;
+  while ((jt + 1) * (jt + 2) / 2 <= t) ++jt;
+  const int it = t - jt * (jt + 1) / 2;
+  const int e = threadIdx.x & 63, ps = threadIdx.x >> 6;
+  const double* src = part + (size_t)t * 64 + e;
+  const size_t stride = (size_t)NT * 64;
+  double s = 0.0;
+#pragma unroll 8
+  for (int c = ps; c < n_cta; c += 4) s += src[(size_t)c * stride];
+  red[ps][e] = s;
+  __syncthreads();
+  if (ps != 0) return;
+  s = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+  const int p = 8 * it + (e >> 3), q = 8 * jt + (e & 7);
+  if (p > q || q >= 2 * K) return;
+  const int bm0 = 4, bi0 = 4 + K;
+  if (q < K) {                       // (x, x): beta.mean is unconstrained, j = 1
+    const double v = -s;
+    A[(size_t)(bm0 + p) * Dg + bm0 + q] = v;
+    A[(size_t)(bm0 + q) * Dg + bm0 + p] = v;
+  } else if (p < K) {                // (x, s)
+    const int k2 = q - K;
+    const double iq = vec[bi0 + k2];
+    const double v = -s * (-1.0 / (iq * iq)) * (vecmode ? 1.0 : iq - bd.beta_info);
+    A[(size_t)(bm0 + p) * Dg + bi0 + k2] = v;
+    A[(size_t)(bi0 + k2) * Dg + bm0 + p] = v;
+  } else {                           // (s, s)
+    const int k1 = p - K, k2 = q - K;
+    const double ip = vec[bi0 + k1], iq = vec[bi0 + k2];
+    const double v = -s * (1.0 / (ip * ip * iq * iq)) *
+                     (vecmode ? 1.0 : (ip - bd.beta_info) * (iq - bd.beta_info));
+    A[(size_t)(bi0 + k1) * Dg + bi0 + k2] = v;
+    A[(size_t)(bi0 + k2) * Dg + bi0 + k1] = v;
   }
 }
 
@@ -773,7 +819,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
 #define LRVB_OBS(O)                                                                          \
   k_obs<O><<<h->obs_grid, h->obs_tn, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
-                                                         h->W, h->klpart, h->gradpart, N, K, G, Q)
+                                                         h->W, h->klpart, h->gradpart, N, h->ldw, K, G, Q)
     if (order == 0) LRVB_OBS(0);
     else if (order == 1) LRVB_OBS(1);
     else LRVB_OBS(2);
@@ -795,8 +841,8 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
       LRVB_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
       gs = h->side;
     }
-    if (order == 1) k_group<1><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
-    else k_group<2><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, N, K, G);
+    if (order == 1) k_group<1><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
+    else k_group<2><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
     LRVB_CHECK_LAUNCH();
     if (forked) LRVB_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
@@ -804,9 +850,16 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
     if (N > 0) {
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[2], st));
-      k_gram<<<h->gram_grid_x, 32 * h->gram_jpc * h->gram_split, h->gram_smem, st>>>(
-          h->X, h->W, h->jobs, h->grampart, N, K, h->KT, h->gram_tn, h->gram_jobs, h->gram_jpc,
-          h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
+      if (h->gram_small) {
+        if (!launch_gram_small(h->X, h->W + 2 * h->ldw, h->grampart, N, h->ldw, K, h->gram_grid_x, st)) {
+          set_error("launch_eval: small-K Gram kernel rejected K = %d / alignment", K);
+          return LRVB_ESTATE;
+        }
+      } else {
+        k_gram<<<h->gram_grid_x, 32 * h->gram_jpc * h->gram_split, h->gram_smem, st>>>(
+            h->X, h->W, h->jobs, h->grampart, N, h->ldw, K, h->KT, h->gram_tn, h->gram_jobs,
+            h->gram_jpc, h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
+      }
       LRVB_CHECK_LAUNCH();
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
     }
@@ -820,9 +873,15 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
 
   if (order >= 2) {
     if (N > 0) {
-      k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
-          h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
-          h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
+      if (h->gram_small) {
+        const GramSmallShape sh = gram_small_shape(K);
+        k_gram_small_finish<<<sh.NT, 256, 0, st>>>(h->grampart, h->vec, outp + 1 + Dg, K, Dg, sh.NT,
+                                                   h->gram_grid_x, h->bounds, h->vecmode);
+      } else {
+        k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
+            h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
+            h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
+      }
       LRVB_CHECK_LAUNCH();
     }
     if (G > 0) {
