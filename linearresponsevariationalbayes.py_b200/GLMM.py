@@ -155,9 +155,11 @@ class LogisticGLMM(object):
             self.y = self.y.index_select(0, pd).contiguous()
             if self.w is not None:
                 self.w = self.w.index_select(0, pd).contiguous()
-        if self.X.numel() and self.X.data_ptr() % 16:
-            self.X = self.X.clone()   # a view into a larger buffer: the library needs 16-B alignment
         self.g = to_device(g_sorted, torch.int32).reshape(-1)
+        for nm in ("X", "y", "w", "g"):   # views into larger buffers: the library needs 16-B alignment
+            t = getattr(self, nm)
+            if t is not None and t.numel() and t.data_ptr() % 16:
+                setattr(self, nm, t.clone())
         if num_groups is None:
             num_groups = int(self.g.max().item()) + 1 if N > 0 else 0
         self.N, self.K, self.G = N, K, int(num_groups)

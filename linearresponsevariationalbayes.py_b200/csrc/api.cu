@@ -5,6 +5,7 @@
 #include <vector>
 #include "common.cuh"
 #include "gram_small.cuh"
+#include "obs_fused.cuh"
 
 namespace lrvb {
 
@@ -41,6 +42,7 @@ static int dev_alloc(T** p, size_t n) {
 
 // kernels defined in glmm_eval.cu whose attributes must be raised for > 48 KB dynamic smem
 void configure_kernels(size_t obs_smem, size_t gram_smem);
+void configure_obs_fused(size_t smem);
 
 }  // namespace lrvb
 
@@ -54,7 +56,7 @@ int lrvb_version(void) { return 100; }
 int lrvb_glmm_destroy(lrvb_glmm* h) {
   if (!h) return LRVB_OK;
   void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart,
-                  h->jobs, h->grampart, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
+                  h->jobs, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
                   h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
                   h->schurpart};
   for (void* p : ptrs)
@@ -84,6 +86,8 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   LRVB_REQUIRE(N == 0 || G >= 1, "lrvb_glmm_create: observations but no groups");
   LRVB_REQUIRE(gh_x_host && gh_w_host && prior && bounds, "lrvb_glmm_create: NULL argument");
   LRVB_REQUIRE((((uintptr_t)X_dev) & 15) == 0, "lrvb_glmm_create: X not 16-byte aligned");
+  LRVB_REQUIRE(N == 0 || (((((uintptr_t)y_dev) | ((uintptr_t)g_dev) | ((uintptr_t)w_dev)) & 15) == 0),
+               "lrvb_glmm_create: y, g, w must be 16-byte aligned (bulk async copies)");
   cudaStream_t st = (cudaStream_t)stream;
 
   lrvb_glmm* h = new (std::nothrow) lrvb_glmm();
@@ -154,6 +158,22 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     int64_t gmax = (int64_t)kNumSMs * per_sm;
     h->obs_grid = (int)(nt < gmax ? nt : gmax);
     if (h->obs_grid < 1) h->obs_grid = 1;
+  }
+  if (K <= kOfMaxK) {
+    // fused observation + group pass: every warp owns a contiguous multiple-of-32 range of rows
+    h->obs_fused = 1;
+    h->of_warps = obs_fused_warps(K);
+    const int64_t nst = (N + kOfRows - 1) / kOfRows;
+    int64_t grid = (nst + h->of_warps - 1) / h->of_warps;
+    if (grid > kNumSMs) grid = kNumSMs;
+    if (grid < 1) grid = 1;
+    h->of_grid = (int)grid;
+    const int64_t tw = grid * h->of_warps;
+    h->of_rows_per_warp = ((nst + tw - 1) / tw) * kOfRows;
+    h->of_smem = obs_fused_smem(K, Q, h->of_warps);
+    CREATE_TRY(dev_alloc(&h->bval, (size_t)tw * 2 * (5 + 4 * (size_t)K)));
+    configure_obs_fused(h->of_smem);
+    if (h->obs_grid < h->of_grid) h->obs_grid = h->of_grid;
   }
   CREATE_TRY(dev_alloc(&h->klpart, (size_t)h->obs_grid));
   CREATE_TRY(dev_alloc(&h->gradpart, (size_t)h->obs_grid * 2 * K));

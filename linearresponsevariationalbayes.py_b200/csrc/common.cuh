@@ -170,6 +170,11 @@ struct lrvb_glmm {
   size_t obs_smem = 0;
   double* klpart = nullptr;   // (obs_grid) per-CTA partials of sum w*l
   double* gradpart = nullptr; // (obs_grid, 2, K) per-CTA partials of X^T l_m , S^T l_v
+  // fused observation + group pass (K <= 62, obs_fused.cuh)
+  int obs_fused = 0, of_grid = 0, of_warps = 0;
+  size_t of_smem = 0;
+  int64_t of_rows_per_warp = 0;
+  double* bval = nullptr;     // (of_grid * of_warps, 2, 5 + 4K) head / tail pieces of straddling groups
   // group pass
   double* gsc = nullptr;      // (G, 5) per-group sums of l_m, l_v, a, b, c
   double* BR = nullptr;       // (G, 4, K) raw borders: sum a x, sum b x, sum b s, sum c s

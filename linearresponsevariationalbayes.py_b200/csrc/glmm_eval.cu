@@ -16,6 +16,7 @@
 //   k_local/k_border/k_gram_finish/k_global   chain rule to free coordinates, non-data terms
 #include "common.cuh"
 #include "gram_small.cuh"
+#include "obs_fused.cuh"
 
 namespace lrvb {
 
@@ -199,10 +200,10 @@ k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t*
         buf[(size_t)partA * 2 * K + K + colA] = gv[0];
       }
       __syncthreads();
-      if (tid < 2 * K) {
+      for (int k = tid; k < 2 * K; k += TN) {   // 2K may exceed the CTA size (K in 33..64, TN = 64)
         double s = 0.0;
-        for (int p = 0; p < P; ++p) s += buf[(size_t)p * 2 * K + tid];
-        gp[(size_t)tid * gs] = s;
+        for (int p = 0; p < P; ++p) s += buf[(size_t)p * 2 * K + k];
+        gp[(size_t)k * gs] = s;
       }
     } else {
 #pragma unroll
@@ -815,6 +816,39 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   k_prep<<<cdiv(h->D, 256), 256, 0, st>>>(free_dev, h->vec, K, G, h->bounds, h->vecmode);
   LRVB_CHECK_LAUNCH();
 
+  double* outp = out_global ? out_global : h->outg;
+  bool forked = false;
+  int n_obs_cta = 0;
+  if (h->obs_fused) {
+    // K <= 62: observation pass and per-group sums in one kernel (obs_fused.cuh)
+    if (N > 0) {
+      if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
+      const int nch = (K + 1 + 31) / 32;
+#define LRVB_OF(O, C)                                                                          \
+  k_obs_fused<O, C><<<h->of_grid, 32 * h->of_warps, h->of_smem, st>>>(                          \
+      h->X, h->y, h->g, h->w, h->vec, h->gh, h->gptr, h->W, h->ldw, h->klpart, h->gradpart,    \
+      h->gsc, h->BR, h->bval, N, K, G, Q, h->of_rows_per_warp)
+      if (nch == 1) {
+        if (order == 0) LRVB_OF(0, 1);
+        else if (order == 1) LRVB_OF(1, 1);
+        else LRVB_OF(2, 1);
+      } else {
+        if (order == 0) LRVB_OF(0, 2);
+        else if (order == 1) LRVB_OF(1, 2);
+        else LRVB_OF(2, 2);
+      }
+#undef LRVB_OF
+      LRVB_CHECK_LAUNCH();
+      if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
+      n_obs_cta = h->of_grid;
+    }
+    if (order >= 1 && G > 0) {
+      const int64_t rpw = h->of_rows_per_warp > 0 ? h->of_rows_per_warp : 32;
+      if (order == 1) k_obs_fixup<1><<<cdiv(G, 8), 256, 0, st>>>(h->gptr, h->bval, h->gsc, h->BR, K, G, rpw);
+      else k_obs_fixup<2><<<cdiv(G, 8), 256, 0, st>>>(h->gptr, h->bval, h->gsc, h->BR, K, G, rpw);
+      LRVB_CHECK_LAUNCH();
+    }
+  } else {
   if (N > 0) {
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
 #define LRVB_OBS(O)                                                                          \
@@ -827,12 +861,11 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     LRVB_CHECK_LAUNCH();
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
   }
-  const int n_obs_cta = (N > 0) ? h->obs_grid : 0;
+  n_obs_cta = (N > 0) ? h->obs_grid : 0;
 
   // The per-group pass is HBM/latency bound, the Gram kernel FP64 bound: for order 2 they run
   // side by side (fork after k_obs, join before the group-level chain rule).
-  const bool forked = (order >= 2 && G > 0 && N > 0);
-  double* outp = out_global ? out_global : h->outg;
+  forked = (order >= 2 && G > 0 && N > 0);
   if (order >= 1 && G > 0) {
     const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
     cudaStream_t gs = st;
@@ -845,6 +878,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     else k_group<2><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
     LRVB_CHECK_LAUNCH();
     if (forked) LRVB_CUDA(cudaEventRecord(h->ev_join, h->side));
+  }
   }
   if (order >= 2) {
     LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
@@ -921,6 +955,16 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
 }  // namespace lrvb
 
 namespace lrvb {
+void configure_obs_fused(size_t smem) {
+  const int v = (int)smem;
+  cudaFuncSetAttribute(k_obs_fused<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaGetLastError();
+}
 void configure_kernels(size_t obs_smem, size_t gram_smem) {
   const int o = (int)obs_smem, gsm = (int)gram_smem;
   cudaFuncSetAttribute(k_obs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);

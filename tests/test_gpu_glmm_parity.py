@@ -22,6 +22,20 @@ CASES = {
     "k70_job_groups": dict(N=1500, K=70, G=15, Q=8, seed=12),
     "one_group": dict(N=900, K=4, G=1, Q=8, seed=13),
     "tiny": dict(N=3, K=2, G=2, Q=3, seed=14),
+    # fused observation+group kernel: groups that straddle many warps' row ranges, several
+    # stages per warp, ragged last stage, weights
+    "big_groups_multistage": dict(N=200003, K=12, G=37, Q=6, seed=15, ragged=True, weights=True),
+    # (almost) one observation per group, many empty groups: a flush per row
+    "many_tiny_groups": dict(N=40000, K=6, G=30000, Q=4, seed=16, ragged=True),
+    # column-chunk boundaries of the fused kernel (K + 1 columns in 32-lane chunks) and the
+    # hand-over to the separate observation / group kernels above K = 62
+    "k31": dict(N=2500, K=31, G=25, Q=8, seed=17),
+    "k32": dict(N=2500, K=32, G=25, Q=8, seed=18, weights=True),
+    "k62": dict(N=2500, K=62, G=25, Q=8, seed=19),
+    "k63": dict(N=2500, K=63, G=25, Q=8, seed=20),
+    # packed-Gram tile shapes: no straddle tile (K = 16), straddle in tile 0 (K = 3)
+    "k16": dict(N=3000, K=16, G=30, Q=8, seed=21),
+    "k3": dict(N=3000, K=3, G=30, Q=8, seed=22, intercept=True),
 }
 
 
