@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gram_small.cuh"
 #include "obs_fused.cuh"
+#include "gram_big.cuh"
 
 namespace lrvb {
 
@@ -56,7 +57,7 @@ int lrvb_version(void) { return 100; }
 int lrvb_glmm_destroy(lrvb_glmm* h) {
   if (!h) return LRVB_OK;
   void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart,
-                  h->jobs, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
+                  h->jobs, h->gslots, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
                   h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
                   h->schurpart};
   for (void* p : ptrs)
@@ -187,43 +188,33 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
 
   // Gram geometry
   {
-    const int KT = h->KT;
-    const int R = (KT + kRT - 1) / kRT;
-    std::vector<GramJob> jobs;
-    for (int fam = 0; fam < 3; ++fam)
-      for (int ri = 0; ri < R; ++ri)
-        for (int rj = 0; rj < R; ++rj) {
-          if (fam != 1 && rj < ri) continue;
-          jobs.push_back(GramJob{fam, kRT * ri, kRT * rj, 0});
-        }
-    h->gram_jobs = (int)jobs.size();
-    h->gram_grid_y = (h->gram_jobs + 7) / 8;
-    h->gram_jpc = (h->gram_jobs + h->gram_grid_y - 1) / h->gram_grid_y;
-    h->gram_split = 8 / h->gram_jpc;
-    if (h->gram_split < 1) h->gram_split = 1;
-    // one pipeline stage <= ~54 KB so that two CTAs x two stages fit in an SM's shared memory
-    h->gram_tn = 256;
-    while (h->gram_tn > 16 && sizeof(double) * (size_t)h->gram_tn * (K + 3) > 54 * 1024) h->gram_tn >>= 1;
-    size_t tile = 2 * sizeof(double) * ((size_t)h->gram_tn * K + 3 * h->gram_tn);
-    size_t red = (h->gram_split > 1) ? sizeof(double) * (size_t)h->gram_jpc * kRT * kRT * 64 : 0;
-    h->gram_smem = tile > red ? tile : red;
-    int64_t nt = (N + h->gram_tn - 1) / h->gram_tn;
-    int64_t nchunk = (2 * kNumSMs) / h->gram_grid_y;
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > nt) nchunk = nt;
-    if (nchunk < 1) nchunk = 1;
-    h->gram_grid_x = (int)nchunk * h->gram_grid_y;
-    CREATE_TRY(dev_alloc(&h->jobs, jobs.size()));
-    CREATE_CUDA(cudaMemcpyAsync(h->jobs, jobs.data(), sizeof(GramJob) * jobs.size(),
-                                cudaMemcpyHostToDevice, st));
-    CREATE_CUDA(cudaStreamSynchronize(st));
-    size_t npart = (size_t)nchunk * h->gram_jobs * kRT * kRT * 64;
+    size_t npart;
     if (K <= 20) {
       // small K: every warp owns the whole packed upper triangle (gram_small.cuh), one CTA per SM
       h->gram_small = 1;
       h->gram_grid_x = kNumSMs;
       h->gram_grid_y = 1;
       npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;
+    } else {
+      // rectangles of the packed triangle dealt to 16-warp CTAs (gram_big.cuh)
+      const GbPlan pl = gram_big_plan(K);
+      h->gram_jobs = (int)pl.jobs.size();
+      h->gram_grid_y = pl.n_groups;
+      h->gram_tn = pl.TN;
+      h->gram_smem = pl.smem;
+      int64_t nst = (N + pl.TN - 1) / pl.TN;
+      int64_t nchunk = (kNumSMs * kGbCtasPerSM) / pl.n_groups;
+      if (nchunk > nst) nchunk = nst;
+      if (nchunk < 1) nchunk = 1;
+      h->gram_grid_x = (int)nchunk * pl.n_groups;
+      CREATE_TRY(dev_alloc((char**)&h->jobs, sizeof(GbJob) * pl.jobs.size()));
+      CREATE_TRY(dev_alloc((char**)&h->gslots, sizeof(GbSlot) * pl.slots.size()));
+      CREATE_CUDA(cudaMemcpyAsync(h->jobs, pl.jobs.data(), sizeof(GbJob) * pl.jobs.size(),
+                                  cudaMemcpyHostToDevice, st));
+      CREATE_CUDA(cudaMemcpyAsync(h->gslots, pl.slots.data(), sizeof(GbSlot) * pl.slots.size(),
+                                  cudaMemcpyHostToDevice, st));
+      CREATE_CUDA(cudaStreamSynchronize(st));   // pl goes out of scope
+      npart = (size_t)nchunk * pl.n_groups * kGbWarps * 16 * 64;
     }
     CREATE_TRY(dev_alloc(&h->grampart, npart));
     CREATE_CUDA(cudaMemsetAsync(h->grampart, 0, sizeof(double) * npart, st));

@@ -50,7 +50,7 @@ extern long long g_launches;
 constexpr int kMaxQ = 64;
 constexpr int kMaxK = 256;
 constexpr int kNumSMs = 148;  // B200
-constexpr int kRT = 4;        // Gram warp job = kRT x kRT output tiles of 8x8
+constexpr int kRT = 4;        // Schur warp job = kRT x kRT output tiles of 8x8 (solve.cu)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -141,12 +141,6 @@ __device__ __forceinline__ void tile_load_async(double* dst, const double* src, 
 }
 #endif  // __CUDACC__
 
-// Gram warp-job: a kRT x kRT rectangle of 8x8 output tiles inside one of the three families
-// fam 0: X^T diag(a) X   fam 1: X^T diag(b) S   fam 2: S^T diag(c) S      (S = X*X elementwise)
-struct GramJob {
-  int fam, i0, j0, pad;
-};
-
 }  // namespace lrvb
 
 // ---- the model handle --------------------------------------------------------------------
@@ -181,11 +175,12 @@ struct lrvb_glmm {
   int loc_grid = 0;
   double* locpart = nullptr;  // (loc_grid, 4) partials of sum dm, sum Sg, sum log u_info, -
   // Gram
-  int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0, gram_jpc = 0, gram_split = 0;
+  int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0;   // grid_y = job groups
   size_t gram_smem = 0;
   int gram_small = 0;         // K <= 20: packed whole-triangle-per-warp kernel (gram_small.cuh)
-  lrvb::GramJob* jobs = nullptr;   // device (gram_jobs)
-  double* grampart = nullptr;      // (gram_grid_x, gram_jobs, kRT*kRT, 64)
+  void* jobs = nullptr;            // device GbJob[gram_jobs]   (gram_big.cuh, K > 20)
+  void* gslots = nullptr;          // device GbSlot[gram_grid_y * 16]
+  double* grampart = nullptr;      // per-CTA partial tiles of the Gram kernel
   // results
   double *A = nullptr, *B = nullptr, *L = nullptr;  // cached Hessian blocks (free coords)
   double* gradl = nullptr;    // (2G) local gradient of the last eval

@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "gram_small.cuh"
 #include "obs_fused.cuh"
+#define LRVB_GRAM_BIG_KERNELS
+#include "gram_big.cuh"
 
 namespace lrvb {
 
@@ -284,254 +286,6 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
         br[3 * K + k] = s3;
       }
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k-step loop of one warp job, specialised at compile time on the number of valid tile rows /
-// columns of its rectangle and on whether it is a diagonal (upper-triangular) rectangle:
-// a predicated-off DMMA still occupies the FP64 pipe (measured: 2.3x slowdown), so the set of
-// issued DMMAs must be exact.
-template <int NI, int NJ, bool TRI>
-__device__ __forceinline__ void gram_ksteps(double (&acc)[kRT][kRT][2], const double* xs,
-                                            const double* wsel, int K, const int (&cola)[kRT],
-                                            const int (&colb)[kRT], int fam, int split,
-                                            int n_split, int ksteps, int lr) {
-  for (int ks = split; ks < ksteps; ks += n_split) {
-    const int n = 4 * ks + lr;
-    const double* xr = xs + (size_t)n * K;
-    const double wv = wsel[n];
-    double fa[kRT], fb[kRT];
-#pragma unroll
-    for (int i = 0; i < kRT; ++i) {
-      if (i < NI) {
-        double xa = (cola[i] < K) ? xr[cola[i]] : 0.0;
-        if (fam == 2) xa *= xa;
-        fa[i] = xa;
-      }
-      if (i < NJ) {
-        double xb = (colb[i] < K) ? xr[colb[i]] : 0.0;
-        if (fam >= 1) xb *= xb;
-        fb[i] = xb * wv;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kRT; ++i)
-#pragma unroll
-      for (int j = 0; j < kRT; ++j)
-        if (i < NI && j < NJ && (!TRI || i <= j)) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-  }
-}
-
-__device__ __forceinline__ void gram_dispatch(double (&acc)[kRT][kRT][2], int ni, int nj, bool tri,
-                                              const double* xs, const double* wsel, int K,
-                                              const int (&cola)[kRT], const int (&colb)[kRT],
-                                              int fam, int split, int n_split, int ksteps, int lr) {
-#define LRVB_G(NI, NJ, T)                                                                      \
-  gram_ksteps<NI, NJ, T>(acc, xs, wsel, K, cola, colb, fam, split, n_split, ksteps, lr)
-  if (tri) {
-    switch (ni) {
-      case 1: LRVB_G(1, 1, true); break;
-      case 2: LRVB_G(2, 2, true); break;
-      case 3: LRVB_G(3, 3, true); break;
-      default: LRVB_G(4, 4, true); break;
-    }
-  } else {
-    switch (ni * 4 + nj) {
-      case 5: LRVB_G(1, 1, false); break;
-      case 6: LRVB_G(1, 2, false); break;
-      case 7: LRVB_G(1, 3, false); break;
-      case 8: LRVB_G(1, 4, false); break;
-      case 9: LRVB_G(2, 1, false); break;
-      case 10: LRVB_G(2, 2, false); break;
-      case 11: LRVB_G(2, 3, false); break;
-      case 12: LRVB_G(2, 4, false); break;
-      case 13: LRVB_G(3, 1, false); break;
-      case 14: LRVB_G(3, 2, false); break;
-      case 15: LRVB_G(3, 3, false); break;
-      case 16: LRVB_G(3, 4, false); break;
-      case 17: LRVB_G(4, 1, false); break;
-      case 18: LRVB_G(4, 2, false); break;
-      case 19: LRVB_G(4, 3, false); break;
-      default: LRVB_G(4, 4, false); break;
-    }
-  }
-#undef LRVB_G
-}
-
-// Weighted Grams on the FP64 tensor cores.  Each warp owns one GramJob (a kRT x kRT rectangle
-// of 8x8 output tiles of one family) for a subset of the 4-observation k-steps of every tile;
-// mma.m8n8k4: A[i][k] = F1[n0+k][8 it + i], B[k][j] = wgt[n0+k] * F2[n0+k][8 jt + j], so lane l
-// reads row n0 + (l&3), column 8 t + (l>>2) for both operands.
-__global__ void __launch_bounds__(256, 2)
-k_gram(const double* __restrict__ X, const double* __restrict__ W, const GramJob* __restrict__ jobs,
-       double* __restrict__ grampart, int64_t N, int64_t ldw, int K, int KT, int TN, int n_jobs,
-       int jpc, int n_split, int ny, int n_chunk) {
-  extern __shared__ __align__(16) double sm[];
-  // two stages of [X tile (TN*K) | weights a, b, c (3*TN)]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int jg = blockIdx.x % ny;
-  const int chunk = blockIdx.x / ny;
-  const int jl = warp % jpc, split = warp / jpc;
-  const int job = jg * jpc + jl;
-  const bool active = (job < n_jobs) && (split < n_split);
-  GramJob jb = {0, 0, 0, 0};
-  if (active) jb = jobs[job];
-  const int fam = jb.fam;
-
-  double acc[kRT][kRT][2];
-#pragma unroll
-  for (int i = 0; i < kRT; ++i)
-#pragma unroll
-    for (int j = 0; j < kRT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  // per-lane column of each tile and validity masks (warp-uniform parts hoisted)
-  const int lr = lane & 3, lc = lane >> 2;
-  int cola[kRT], colb[kRT];
-  unsigned tmask = 0;  // bit i*kRT+j : tile (i,j) computed
-#pragma unroll
-  for (int i = 0; i < kRT; ++i) {
-    cola[i] = 8 * (jb.i0 + i) + lc;
-    colb[i] = 8 * (jb.j0 + i) + lc;
-  }
-#pragma unroll
-  for (int i = 0; i < kRT; ++i)
-#pragma unroll
-    for (int j = 0; j < kRT; ++j) {
-      const int it = jb.i0 + i, jt = jb.j0 + j;
-      if (active && it < KT && jt < KT && (fam == 1 || it <= jt)) tmask |= 1u << (i * kRT + j);
-    }
-  int ni = KT - jb.i0, nj = KT - jb.j0;
-  ni = ni > kRT ? kRT : ni;
-  nj = nj > kRT ? kRT : nj;
-  const bool tri = (fam != 1) && (jb.i0 == jb.j0);
-
-  // 2-stage cp.async pipeline over this CTA's tiles: the loads of tile t+1 (X rows and the three
-  // weight rows) are in flight while the warps issue the DMMAs of tile t.
-  const size_t stage_elems = (size_t)TN * K + 3 * (size_t)TN;
-  const int64_t ntiles = (N + TN - 1) / TN;
-  auto issue_tile = [&](int64_t tile, int stage) {
-    double* sx = sm + (size_t)stage * stage_elems;
-    double* sw = sx + (size_t)TN * K;
-    const int64_t n0 = tile * TN;
-    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
-    tile_load_async(sx, X + n0 * K, (int64_t)rows * K);
-#pragma unroll
-    for (int f = 0; f < 3; ++f)
-      tile_load_async(sw + (size_t)f * TN, W + (int64_t)(2 + f) * ldw + n0, rows);
-    if (rows < TN) {   // tail rows: zero weights and finite (zero) data
-      for (int64_t e = (int64_t)rows * K + tid; e < (int64_t)TN * K; e += blockDim.x) sx[e] = 0.0;
-      for (int r = tid; r < 3 * TN; r += blockDim.x)
-        if (r % TN >= rows) sw[r] = 0.0;
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-  int stage = 0;
-  if (chunk < ntiles) issue_tile(chunk, 0);
-  for (int64_t tile = chunk; tile < ntiles; tile += n_chunk) {
-    const int64_t n0 = tile * TN;
-    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
-    const bool more = tile + n_chunk < ntiles;
-    if (more) {
-      issue_tile(tile + n_chunk, stage ^ 1);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();
-    const double* sx = sm + (size_t)stage * stage_elems;
-    if (tmask) gram_dispatch(acc, ni, nj, tri, sx, sx + (size_t)TN * K + (size_t)fam * TN, K, cola,
-                             colb, fam, split, n_split, (rows + 3) >> 2, lr);
-    __syncthreads();   // every warp is done with this stage before it is refilled
-    stage ^= 1;
-  }
-
-  // in-CTA reduction over the k-step splits (fixed order), then one partial per (chunk, job)
-  __syncthreads();
-  double* red = sm;  // jpc * kRT*kRT*64 doubles when n_split > 1
-  const int crow = lane >> 2, ccol = 2 * (lane & 3);
-  if (n_split > 1) {
-    for (int s = 0; s < n_split; ++s) {
-      if (active && split == s) {
-#pragma unroll
-        for (int i = 0; i < kRT; ++i)
-#pragma unroll
-          for (int j = 0; j < kRT; ++j)
-            if (tmask & (1u << (i * kRT + j))) {
-              double* t = red + ((size_t)jl * kRT * kRT + i * kRT + j) * 64 + crow * 8 + ccol;
-              if (s == 0) { t[0] = acc[i][j][0]; t[1] = acc[i][j][1]; }
-              else { t[0] += acc[i][j][0]; t[1] += acc[i][j][1]; }
-            }
-      }
-      __syncthreads();
-    }
-    if (active && split == 0) {
-#pragma unroll
-      for (int i = 0; i < kRT; ++i)
-#pragma unroll
-        for (int j = 0; j < kRT; ++j)
-          if (tmask & (1u << (i * kRT + j))) {
-            const double* t = red + ((size_t)jl * kRT * kRT + i * kRT + j) * 64 + crow * 8 + ccol;
-            acc[i][j][0] = t[0];
-            acc[i][j][1] = t[1];
-          }
-    }
-  }
-  if (active && split == 0) {
-    double* out = grampart + ((size_t)chunk * n_jobs + job) * (kRT * kRT * 64);
-#pragma unroll
-    for (int i = 0; i < kRT; ++i)
-#pragma unroll
-      for (int j = 0; j < kRT; ++j)
-        if (tmask & (1u << (i * kRT + j))) {
-          double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-          *reinterpret_cast<double2*>(out + (i * kRT + j) * 64 + crow * 8 + ccol) = v;
-        }
-  }
-}
-
-// Sum the Gram partials over chunks (fixed order) and write the beta block of A in FREE
-// coordinates: A = -(d2F/dvec2) * j_i j_j  (the diagonal extras are added by k_global).
-// One CTA (256 threads) per (job, tile-in-rectangle).
-__global__ void __launch_bounds__(256)
-k_gram_finish(const double* __restrict__ grampart, const GramJob* __restrict__ jobs,
-              const double* __restrict__ vec, double* __restrict__ A, int K, int KT, int Dg,
-              int n_jobs, int n_chunk, lrvb_glmm_bounds bd, int vecmode) {
-  __shared__ double red[4][64];
-  const int job = blockIdx.x / (kRT * kRT);
-  const int t = blockIdx.x % (kRT * kRT);
-  const GramJob jb = jobs[job];
-  const int it = jb.i0 + t / kRT, jt = jb.j0 + t % kRT;
-  if (it >= KT || jt >= KT || (jb.fam != 1 && it > jt)) return;
-  const int e = threadIdx.x & 63, ps = threadIdx.x >> 6;
-  const double* src = grampart + ((size_t)job * kRT * kRT + t) * 64 + e;
-  const size_t stride = (size_t)n_jobs * kRT * kRT * 64;
-  double s = 0.0;
-#pragma unroll 8
-  for (int p = ps; p < n_chunk; p += 4) s += src[(size_t)p * stride];
-  red[ps][e] = s;
-  __syncthreads();
-  if (ps != 0) return;
-  s = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
-  const int p = 8 * it + (e >> 3), q = 8 * jt + (e & 7);
-  if (p >= K || q >= K) return;
-  const int bm0 = 4, bi0 = 4 + K;
-  if (jb.fam == 0) {
-    if (it == jt && p > q) return;          // use the upper triangle of diagonal tiles
-    const double v = -s;                     // beta.mean is unconstrained: j = 1
-    A[(size_t)(bm0 + p) * Dg + bm0 + q] = v;
-    A[(size_t)(bm0 + q) * Dg + bm0 + p] = v;
-  } else if (jb.fam == 1) {
-    const double iq = vec[bi0 + q];
-    const double v = -s * (-1.0 / (iq * iq)) * (vecmode ? 1.0 : iq - bd.beta_info);
-    A[(size_t)(bm0 + p) * Dg + bi0 + q] = v;
-    A[(size_t)(bi0 + q) * Dg + bm0 + p] = v;
-  } else {
-    if (it == jt && p > q) return;
-    const double ip = vec[bi0 + p], iq = vec[bi0 + q];
-    const double v = -s * (1.0 / (ip * ip * iq * iq)) * (vecmode ? 1.0 : (ip - bd.beta_info) * (iq - bd.beta_info));
-    A[(size_t)(bi0 + p) * Dg + bi0 + q] = v;
-    A[(size_t)(bi0 + q) * Dg + bi0 + p] = v;
   }
 }
 
@@ -817,7 +571,6 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   LRVB_CHECK_LAUNCH();
 
   double* outp = out_global ? out_global : h->outg;
-  bool forked = false;
   int n_obs_cta = 0;
   if (h->obs_fused) {
     // K <= 62: observation pass and per-group sums in one kernel (obs_fused.cuh)
@@ -863,21 +616,13 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   }
   n_obs_cta = (N > 0) ? h->obs_grid : 0;
 
-  // The per-group pass is HBM/latency bound, the Gram kernel FP64 bound: for order 2 they run
-  // side by side (fork after k_obs, join before the group-level chain rule).
-  forked = (order >= 2 && G > 0 && N > 0);
+  // (the Gram kernel fills every SM, so the per-group pass runs before it on the same stream)
   if (order >= 1 && G > 0) {
     const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
     cudaStream_t gs = st;
-    if (forked) {
-      LRVB_CUDA(cudaEventRecord(h->ev_fork, st));
-      LRVB_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-      gs = h->side;
-    }
     if (order == 1) k_group<1><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
     else k_group<2><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
     LRVB_CHECK_LAUNCH();
-    if (forked) LRVB_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
   }
   if (order >= 2) {
@@ -890,15 +635,14 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
           return LRVB_ESTATE;
         }
       } else {
-        k_gram<<<h->gram_grid_x, 32 * h->gram_jpc * h->gram_split, h->gram_smem, st>>>(
-            h->X, h->W, h->jobs, h->grampart, N, h->ldw, K, h->KT, h->gram_tn, h->gram_jobs,
-            h->gram_jpc, h->gram_split, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
+        k_gram_big<<<h->gram_grid_x, 32 * kGbWarps, h->gram_smem, st>>>(
+            h->X, h->W + 2 * h->ldw, h->ldw, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,
+            h->grampart, N, K, h->gram_tn, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
       }
       LRVB_CHECK_LAUNCH();
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
     }
   }
-  if (forked) LRVB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   double* gl = grad_local ? grad_local : h->gradl;
   if (order == 0) k_local<0><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
   else if (order == 1) k_local<1><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
@@ -912,9 +656,9 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
         k_gram_small_finish<<<sh.NT, 256, 0, st>>>(h->grampart, h->vec, outp + 1 + Dg, K, Dg, sh.NT,
                                                    h->gram_grid_x, h->bounds, h->vecmode);
       } else {
-        k_gram_finish<<<h->gram_jobs * kRT * kRT, 256, 0, st>>>(
-            h->grampart, h->jobs, h->vec, outp + 1 + Dg, K, h->KT, Dg, h->gram_jobs,
-            h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
+        k_gram_big_finish<<<h->gram_jobs * 16, 256, 0, st>>>(
+            h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots, h->vec, outp + 1 + Dg, K,
+            Dg, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
       }
       LRVB_CHECK_LAUNCH();
     }
@@ -970,7 +714,8 @@ void configure_kernels(size_t obs_smem, size_t gram_smem) {
   cudaFuncSetAttribute(k_obs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
   cudaFuncSetAttribute(k_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
   cudaFuncSetAttribute(k_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
-  cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm);
+  if (gsm > 0) cudaFuncSetAttribute(k_gram_big, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm);
   cudaGetLastError();
 }
 }  // namespace lrvb
+
