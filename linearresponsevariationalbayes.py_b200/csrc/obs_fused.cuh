@@ -19,6 +19,7 @@
 // order, so there are no atomics and the summation order is fixed.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 #include "gram_small.cuh"   // mbarrier / bulk-copy helpers
 
 namespace lrvb {
@@ -37,9 +38,9 @@ constexpr int kOfMaxK = 62;      // K + 1 columns in at most two 32-lane chunks
 
 // doubles per stage: X rows | y | w | g (int32, 16 doubles)
 __host__ __device__ inline int obs_fused_stage_elems(int K) { return kOfRows * K + 2 * kOfRows + kOfRows / 2; }
-// per-warp shared memory (doubles): ring + weights of the current stage (5 x 32)
+// per-warp shared memory (doubles): ring + weights of the current stage (32 rows x 6: l_m, l_v, a, b, c, -)
 __host__ __device__ inline int obs_fused_warp_elems(int K) {
-  return kOfStages * obs_fused_stage_elems(K) + 5 * kOfRows;
+  return kOfStages * obs_fused_stage_elems(K) + 6 * kOfRows;
 }
 inline int obs_fused_warps(int K) {
   int w = (int)((200 * 1024) / (sizeof(double) * obs_fused_warp_elems(K)));
@@ -154,7 +155,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
   const int stage_elems = obs_fused_stage_elems(K);
   const int warp_elems = obs_fused_warp_elems(K);
   double* ring = sm + (size_t)warp * warp_elems;
-  double* wsm = ring + kOfStages * stage_elems;            // 5 x 32 weights of the current stage
+  double* wsm = ring + kOfStages * stage_elems;            // 32 x 6 weights of the current stage
   double* bm = sm + (size_t)nwarp * warp_elems;            // K   E[beta]
   double* bv = bm + K;                                     // K   Var[beta]
   double* ghc = bv + K;                                    // Q   sqrt(2) x_q
@@ -287,10 +288,15 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
     const int rows = (int)((re - n0 < kOfRows) ? (re - n0) : kOfRows);
 
     // ---- phase A: lane = observation ----
+    unsigned segmask;   // bit r: row r starts a new group segment
     {
       const int64_t n = n0 + lane;
       const bool valid = lane < rows;
       const int gi = valid ? gs[lane] : 0;
+      {
+        const int gprev = __shfl_up_sync(0xffffffffu, gi, 1);
+        segmask = __ballot_sync(0xffffffffu, valid && (lane == 0 ? gi != cur_g : gi != gprev));
+      }
       double zm = vec[um0 + gi];
       double zv = 1.0 / vec[ui0 + gi];
       const double* xr = xs + (size_t)lane * K;
@@ -329,8 +335,8 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
         const double h = 0.5 / zs;
         const double lm = wn * (yn - s.Am);
         const double lv = -wn * s.As * h;
-        wsm[lane] = lm;
-        wsm[kOfRows + lane] = lv;
+        double2* wrow = reinterpret_cast<double2*>(wsm + 6 * lane);
+        wrow[0] = make_double2(lm, lv);
         if (valid) {
           W[n] = lm;
           W[ldw + n] = lv;
@@ -340,9 +346,8 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
           const double b = -wn * s.Ams * h;
           // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
           const double c = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
-          wsm[2 * kOfRows + lane] = a;
-          wsm[3 * kOfRows + lane] = b;
-          wsm[4 * kOfRows + lane] = c;
+          wrow[1] = make_double2(a, b);
+          wrow[2] = make_double2(c, 0.0);
           if (valid) {
             W[2 * ldw + n] = a;
             W[3 * ldw + n] = b;
@@ -352,84 +357,64 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
       }
     }
 
-    // ---- phase C: lane = column; segmented running sums over the rows of the stage ----
+    // ---- phase C: lane = column; running sums of the current group over the rows of the stage,
+    // one tight loop per group segment (segment starts come from the ballot above) ----
     if (ORDER >= 1) {
       __syncwarp();
-      auto row_acc = [&](int r) {
-        const double lm = wsm[r], lv = wsm[kOfRows + r];
-        double a = 0.0, b = 0.0, cc = 0.0;
-        if (ORDER >= 2) {
-          a = wsm[2 * kOfRows + r];
-          b = wsm[3 * kOfRows + r];
-          cc = wsm[4 * kOfRows + r];
+      const double2* w2 = reinterpret_cast<const double2*>(wsm);
+      int koff[NCH];
+      bool isone[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int k = lane + 32 * c;
+        koff[c] = (k < K) ? k : 0;        // lanes beyond the ones column compute garbage nobody stores
+        isone[c] = (k == K);
+      }
+      auto rows_acc = [&](int r, auto nrow) {   // nrow consecutive rows of the current group
+        constexpr int NR = decltype(nrow)::value;
+        double2 wl[NR], wab[NR], wc[NR];
+        double x[NR][NCH];
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+          wl[u] = w2[3 * (r + u)];
+          if (ORDER >= 2) { wab[u] = w2[3 * (r + u) + 1]; wc[u] = w2[3 * (r + u) + 2]; }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const double v = xs[(size_t)(r + u) * K + koff[c]];
+            x[u][c] = isone[c] ? 1.0 : v;
+          }
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int k = lane + 32 * c;
-          if (k <= K) {
-            const double x = (k < K) ? xs[(size_t)r * K + k] : 1.0;
-            const double xx = x * x;
-            q0[c] = fma(lm, x, q0[c]);
-            q1[c] = fma(lv, xx, q1[c]);
+          double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
+#pragma unroll
+          for (int u = 0; u < NR; ++u) {
+            const double xv = x[u][c], xx = xv * xv;
+            t0 = fma(wl[u].x, xv, t0);
+            t1 = fma(wl[u].y, xx, t1);
             if (ORDER >= 2) {
-              q2[c] = fma(a, x, q2[c]);
-              q3[c] = fma(b, x, q3[c]);
-              q4[c] = fma(b, xx, q4[c]);
-              q5[c] = fma(cc, xx, q5[c]);
+              t2 = fma(wab[u].x, xv, t2);
+              t3 = fma(wab[u].y, xv, t3);
+              t4 = fma(wab[u].y, xx, t4);
+              t5 = fma(wc[u].x, xx, t5);
             }
           }
+          q0[c] += t0; q1[c] += t1;
+          if (ORDER >= 2) { q2[c] += t2; q3[c] += t3; q4[c] += t4; q5[c] += t5; }
         }
       };
       int r = 0;
+      unsigned m = segmask;
       while (r < rows) {
-        if (r + 4 <= rows && gs[r] == cur_g && gs[r + 3] == cur_g) {
-          // four rows of the current group (ids are sorted): no flush inside, loads batched
-          double lm[4], lv[4], a[4], b[4], cc[4], x[4][NCH];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            lm[u] = wsm[r + u];
-            lv[u] = wsm[kOfRows + r + u];
-            if (ORDER >= 2) {
-              a[u] = wsm[2 * kOfRows + r + u];
-              b[u] = wsm[3 * kOfRows + r + u];
-              cc[u] = wsm[4 * kOfRows + r + u];
-            }
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              const int k = lane + 32 * c;
-              x[u][c] = (k < K) ? xs[(size_t)(r + u) * K + k] : 1.0;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (lane + 32 * c <= K) {
-              double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const double xv = x[u][c], xx = xv * xv;
-                t0 = fma(lm[u], xv, t0);
-                t1 = fma(lv[u], xx, t1);
-                if (ORDER >= 2) {
-                  t2 = fma(a[u], xv, t2);
-                  t3 = fma(b[u], xv, t3);
-                  t4 = fma(b[u], xx, t4);
-                  t5 = fma(cc[u], xx, t5);
-                }
-              }
-              q0[c] += t0; q1[c] += t1;
-              if (ORDER >= 2) { q2[c] += t2; q3[c] += t3; q4[c] += t4; q5[c] += t5; }
-            }
-          }
-          r += 4;
-        } else {
-          const int gi = gs[r];
-          if (gi != cur_g) {
-            flush();
-            cur_g = gi;
-          }
-          row_acc(r);
-          ++r;
+        if ((m >> r) & 1u) {            // row r opens a new group
+          flush();
+          cur_g = gs[r];
         }
+        const unsigned rest = (r + 1 < 32) ? (m >> (r + 1)) : 0u;
+        const int nxt = rest ? (r + 1 + __ffs((int)rest) - 1) : rows;   // next segment start
+        const int r1 = nxt < rows ? nxt : rows;
+        for (; r + 4 <= r1; r += 4) rows_acc(r, std::integral_constant<int, 4>());
+        for (; r < r1; ++r) rows_acc(r, std::integral_constant<int, 1>());
       }
     }
     __syncwarp();   // every lane is done with this slot (and with wsm) before the refill
