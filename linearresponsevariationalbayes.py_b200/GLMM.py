@@ -84,10 +84,18 @@ class DeviceCSR(object):
         return self._val[:self.nnz]
 
     def to_scipy(self):
+        """Host copy as ``scipy.sparse.csr_matrix``.  The three arrays land in pinned host blocks
+        from torch's caching host allocator by asynchronous copies on the current stream (one
+        synchronisation); the scipy matrix keeps those blocks alive, no second host copy."""
         import scipy.sparse
-        m = scipy.sparse.csr_matrix(
-            (self.values.cpu().numpy(), self.col_indices.cpu().numpy(),
-             self.crow_indices.cpu().numpy()), shape=self.shape)
+        torch = nat.require_cuda()
+        host = []
+        for t in (self.values, self.col_indices, self.crow_indices):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            host.append(h)
+        torch.cuda.current_stream().synchronize()
+        m = scipy.sparse.csr_matrix(tuple(h.numpy() for h in host), shape=self.shape, copy=False)
         m.has_sorted_indices = True
         return m
 

@@ -174,8 +174,15 @@ class ShardedLogisticGLMM(object):
         c = self._cache
         if c["x"] is None or c["coords"] != coords:
             return False
-        xh = x.detach().cpu().numpy().reshape(-1) if is_torch(x) else np.asarray(x).reshape(-1)
-        return np.array_equal(c["x"], xh)
+        if is_torch(x):
+            import torch
+            if not is_torch(c["x"]):
+                return False
+            xf = x.detach().reshape(-1).to(c["x"].device)
+            return c["x"].shape == xf.shape and bool(torch.equal(c["x"], xf))
+        if is_torch(c["x"]):
+            return False
+        return np.array_equal(c["x"], np.asarray(x, dtype=np.float64).reshape(-1))
 
     # ---- the model interface used by Objective / ConjugateGradientSolver / LRVB --------------
     def evaluate(self, x, order, coords="free", force=False):
@@ -193,8 +200,9 @@ class ShardedLogisticGLMM(object):
         if order >= 2:
             self.local.set_global_block(buf[1 + Dg:])
         self._sinv = None
+        # the cache key stays where the point lives: a device clone for tensors (no host sync)
         self._cache = dict(
-            x=(x.detach().cpu().numpy().reshape(-1).copy() if is_torch(x)
+            x=(x.detach().reshape(-1).clone() if is_torch(x)
                else np.array(x, dtype=np.float64).reshape(-1)), order=int(order), coords=coords)
 
     def kl_tensor(self):
