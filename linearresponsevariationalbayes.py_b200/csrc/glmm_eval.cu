@@ -292,12 +292,11 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
 // Finish of the small-K packed Gram (gram_small.cuh): fixed-order sum of the per-CTA partials of
 // one packed tile, then the same chain rule as k_gram_finish.  Packed column p < K is x_p,
 // p >= K is s_{p-K}; only the upper triangle of the packed matrix was computed.
-__global__ void __launch_bounds__(256)
-k_gram_small_finish(const double* __restrict__ part, const double* __restrict__ vec,
+__device__ __forceinline__ void gram_small_finish_body(int bid, const double* __restrict__ part, const double* __restrict__ vec,
                     double* __restrict__ A, int K, int Dg, int NT, int n_cta, lrvb_glmm_bounds bd,
                     int vecmode) {
   __shared__ double red[4][64];
-  const int t = blockIdx.x;
+  const int t = bid;
   int jt = 0;
   while ((jt + 1) * (jt + 2) / 2 <= t) ++jt;
   const int it = t - jt * (jt + 1) / 2;
@@ -339,8 +338,7 @@ k_gram_small_finish(const double* __restrict__ part, const double* __restrict__ 
 // random-effect term  sum_g [-1/2 E[tau]((E mu - E u_g)^2 + Var mu + Var u_g) + 1/2 E log tau]
 // (GammaParams.py:9-13, NormalParams.py:58-63).
 template <int ORDER>
-__global__ void __launch_bounds__(256)
-k_local(const double* __restrict__ vec, const double* __restrict__ gsc,
+__device__ __forceinline__ void local_body(int bid, int nblk, const double* __restrict__ vec, const double* __restrict__ gsc,
         double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ locpart,
         int K, int G, lrvb_glmm_bounds bd, int vecmode) {
   __shared__ double red[32];
@@ -348,7 +346,7 @@ k_local(const double* __restrict__ vec, const double* __restrict__ gsc,
   const double mu_m = vec[0], mu_i = vec[1], a = vec[2], b = vec[3];
   const double E = a / b;
   double dsum = 0.0, ssum = 0.0, lsum = 0.0;
-  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < G; gi += gridDim.x * blockDim.x) {
+  for (int gi = bid * blockDim.x + threadIdx.x; gi < G; gi += nblk * blockDim.x) {
     const double um = vec[Dg + gi], ui = vec[Dg + G + gi];
     const double dm = mu_m - um;
     const double r = 1.0 / ui;
@@ -381,19 +379,18 @@ k_local(const double* __restrict__ vec, const double* __restrict__ gsc,
   ssum = block_sum(ssum, red);
   lsum = block_sum(lsum, red);
   if (threadIdx.x == 0) {
-    locpart[blockIdx.x * 4 + 0] = dsum;
-    locpart[blockIdx.x * 4 + 1] = ssum;
-    locpart[blockIdx.x * 4 + 2] = lsum;
-    locpart[blockIdx.x * 4 + 3] = 0.0;
+    locpart[bid * 4 + 0] = dsum;
+    locpart[bid * 4 + 1] = ssum;
+    locpart[bid * 4 + 2] = lsum;
+    locpart[bid * 4 + 3] = 0.0;
   }
 }
 
 // Border rows B (G,2,Dg) in free coordinates: row 0 = (u.mean_g, globals), row 1 = (u.info_g, .)
-__global__ void __launch_bounds__(256)
-k_border(const double* __restrict__ vec, const double* __restrict__ BR, double* __restrict__ B,
+__device__ __forceinline__ void border_body(int bid, const double* __restrict__ vec, const double* __restrict__ BR, double* __restrict__ B,
          int K, int G, lrvb_glmm_bounds bd, int vecmode) {
   const int Dg = 4 + 2 * K;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = (int64_t)bid * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)G * Dg) return;
   const int gi = (int)(idx / Dg), col = (int)(idx - (int64_t)gi * Dg);
   const double mu_m = vec[0], a = vec[2], b = vec[3];
@@ -424,6 +421,30 @@ k_border(const double* __restrict__ vec, const double* __restrict__ BR, double* 
   if (vecmode) jg = 1.0;
   out[col] = -b0 * jg;
   out[Dg + col] = -b1 * jg * (vecmode ? 1.0 : ji);
+}
+
+// ------------------------------------------------------------------------------------------
+// One launch for the three independent finishing passes: blocks [0, n_loc) run the group-level
+// chain rule, the next n_bor blocks the border rows, the rest the Gram finish (block-uniform roles).
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const double* __restrict__ BR,
+         double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ B,
+         double* __restrict__ locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
+         const GbSlot* __restrict__ slots, double* __restrict__ A, int K, int G, int n_loc, int n_bor,
+         int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode) {
+  const int bid = blockIdx.x;
+  const int Dg = 4 + 2 * K;
+  if (bid < n_loc) {
+    local_body<ORDER>(bid, n_loc, vec, gsc, gradl, L, locpart, K, G, bd, vecmode);
+  } else if (bid < n_loc + n_bor) {
+    border_body(bid - n_loc, vec, BR, B, K, G, bd, vecmode);
+  } else if (gram_small) {
+    gram_small_finish_body(bid - n_loc - n_bor, grampart, vec, A, K, Dg, NT, gram_chunks, bd, vecmode);
+  } else {
+    gram_big_finish_body(bid - n_loc - n_bor, grampart, jobs, slots, vec, A, K, Dg, gram_groups, gram_chunks,
+                         bd, vecmode);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -644,28 +665,28 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     }
   }
   double* gl = grad_local ? grad_local : h->gradl;
-  if (order == 0) k_local<0><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  else if (order == 1) k_local<1><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  else k_local<2><<<h->loc_grid, 256, 0, st>>>(h->vec, h->gsc, gl, h->L, h->locpart, K, G, h->bounds, h->vecmode);
-  LRVB_CHECK_LAUNCH();
-
-  if (order >= 2) {
-    if (N > 0) {
-      if (h->gram_small) {
-        const GramSmallShape sh = gram_small_shape(K);
-        k_gram_small_finish<<<sh.NT, 256, 0, st>>>(h->grampart, h->vec, outp + 1 + Dg, K, Dg, sh.NT,
-                                                   h->gram_grid_x, h->bounds, h->vecmode);
-      } else {
-        k_gram_big_finish<<<h->gram_jobs * 16, 256, 0, st>>>(
-            h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots, h->vec, outp + 1 + Dg, K,
-            Dg, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y, h->bounds, h->vecmode);
+  {
+    const int n_loc = h->loc_grid;
+    int n_bor = 0, n_gf = 0, NT = 0;
+    if (order >= 2) {
+      if (G > 0) n_bor = cdiv((int64_t)G * Dg, 256);
+      if (N > 0) {
+        if (h->gram_small) { NT = gram_small_shape(K).NT; n_gf = NT; }
+        else n_gf = h->gram_jobs * 16;
       }
-      LRVB_CHECK_LAUNCH();
     }
-    if (G > 0) {
-      k_border<<<cdiv((int64_t)G * Dg, 256), 256, 0, st>>>(h->vec, h->BR, h->B, K, G, h->bounds, h->vecmode);
-      LRVB_CHECK_LAUNCH();
-    }
+    const int grid = n_loc + n_bor + n_gf;
+#define LRVB_FIN(O)                                                                              \
+  k_finish<O><<<grid, 256, 0, st>>>(h->vec, h->gsc, h->BR, gl, h->L, h->B, h->locpart, h->grampart, \
+                                    (const GbJob*)h->jobs, (const GbSlot*)h->gslots, outp + 1 + Dg, K, \
+                                    G, n_loc, n_bor, h->gram_small, NT, h->gram_grid_y,           \
+                                    h->gram_small ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
+                                    h->bounds, h->vecmode)
+    if (order == 0) LRVB_FIN(0);
+    else if (order == 1) LRVB_FIN(1);
+    else LRVB_FIN(2);
+#undef LRVB_FIN
+    LRVB_CHECK_LAUNCH();
   }
   const size_t gsm = sizeof(double) * 2 * (size_t)K;
 #define LRVB_GLOB(O)                                                                          \

@@ -333,6 +333,7 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
     }
   };
 
+#ifndef LRVB_GB_NOPACK
   if (tid == 0) { arm(0); arm(1); }
   __syncthreads();
   issue(0);
@@ -341,6 +342,7 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
   if (tid == 0) arm(2);
   __syncthreads();
   issue(2);
+#endif
   for (int64_t j = 0; j < nmine; ++j) {
     const int64_t s = chunk + j * n_chunk;
     const double* zb = zbase + (j & 1) * z_elems;
@@ -363,10 +365,16 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
         }
       }
     }
+#ifndef LRVB_GB_NOPACK
     if (j + 1 < nmine) pack(j + 1);      // Z buffer (j+1) % 2 was last read in stage j - 1
     if (tid == 0) arm(j + 3);            // raw slot (j+1) % 2: its current phase completed above
+#endif
+#ifndef LRVB_GB_NOBAR
     __syncthreads();                     // Z(j+1) complete; stage j's DMMAs and raw slot (j+1) % 2 done
+#endif
+#ifndef LRVB_GB_NOPACK
     issue(j + 3);
+#endif
   }
 
   if (active) {
@@ -384,13 +392,12 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
 
 // Sum the partials of one (job, tile) over the row chunks and the k-splits in a fixed order and
 // write the beta block of A in free coordinates (same chain rule as k_gram_small_finish).
-__global__ void __launch_bounds__(256)
-k_gram_big_finish(const double* __restrict__ part, const GbJob* __restrict__ jobs,
+__device__ __forceinline__ void gram_big_finish_body(int bid, const double* __restrict__ part, const GbJob* __restrict__ jobs,
                   const GbSlot* __restrict__ slots, const double* __restrict__ vec,
                   double* __restrict__ A, int K, int Dg, int n_groups, int n_chunk,
                   lrvb_glmm_bounds bd, int vecmode) {
   __shared__ double red[4][64];
-  const int job = blockIdx.x / 16, t = blockIdx.x % 16;
+  const int job = bid / 16, t = bid % 16;
   const GbJob jb = jobs[job];
   const int ti = t / 4, tj = t % 4;
   if (ti >= jb.ni || tj >= jb.nj || (jb.stair && ti > tj)) return;
