@@ -54,14 +54,14 @@ struct GbPlan {
   size_t smem = 0;
 };
 
-// shared memory: two raw slots [X rows | a b c] filled by TMA and two packed buffers
-// [Z rows | a b c], Z row = [x | s | 0] with stride ZS = 8 T2 + 4 (== 4 mod 8), which spreads the
-// four rows a DMMA operand load touches over distinct bank groups; columns 2K .. ZS stay zero
-inline size_t gram_big_raw_elems(int K, int TN) { return (size_t)TN * (K + 3); }
+// shared memory: a ring of three stage buffers [Z rows | a b c], Z row = [x | s | 0] with stride
+// ZS = 8 T2 + 4 (== 4 mod 8), which spreads the four rows a DMMA operand load touches over distinct
+// bank groups; the x part of every row and the weights arrive by TMA, columns 2K .. ZS stay zero
+constexpr int kGbBuffers = 3;
 inline int gram_big_zs(int K) { return 8 * ((2 * K + 7) / 8) + 4; }
 inline size_t gram_big_z_elems(int K, int TN) { return (size_t)TN * (gram_big_zs(K) + 3); }
 inline size_t gram_big_smem(int K, int TN) {
-  return sizeof(double) * 2 * (gram_big_raw_elems(K, TN) + gram_big_z_elems(K, TN)) + 64;
+  return sizeof(double) * kGbBuffers * gram_big_z_elems(K, TN) + 64;
 }
 
 inline GbPlan gram_big_plan(int K) {
@@ -161,16 +161,29 @@ template <int NI, int NJ, bool STAIR>
 __device__ __forceinline__ void gb_ksteps(double (&acc)[4][4][2], const double* st, const double* sw,
                                           const GbLane& L, int w0off, int w1off, int ZS, int split,
                                           int nsplit, int ksteps, int lr) {
+  // byte addresses of this lane's fragments in k-step 0; a k-step advances every one by 32 ZS
+  const unsigned zu = smem_u32(st) + 8u * (unsigned)(lr * ZS), wu = smem_u32(sw) + 8u * (unsigned)lr;
+  unsigned aA[4], aB[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    aA[f] = zu + 8u * (unsigned)L.offA[f];
+    aB[f] = zu + 8u * (unsigned)L.offB[f];
+  }
+  const unsigned aw0 = wu + 8u * (unsigned)w0off, aw1 = wu + 8u * (unsigned)w1off;
+  const unsigned zstep = 32u * (unsigned)ZS;
   for (int ks = split; ks < ksteps; ks += nsplit) {
-    const int n = 4 * ks + lr;
-    const double* zr = st + (size_t)n * ZS;
-    const double w0 = sw[w0off + n], w1 = sw[w1off + n];
+    const unsigned zo = zstep * (unsigned)ks, wo = 32u * (unsigned)ks;
     double fa[4], fb[4];
+    // all loads first (volatile asm keeps them ahead of the DMMAs), then the weights, then the MMAs
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      if (f < NI) fa[f] = zr[L.offA[f]];
-      if (f < NJ) fb[f] = zr[L.offB[f]] * (((L.selB >> f) & 1u) ? w1 : w0);
+      if (f < NI) fa[f] = lds_f64(aA[f] + zo);
+      if (f < NJ) fb[f] = lds_f64(aB[f] + zo);
     }
+    const double w0 = lds_f64(aw0 + wo), w1 = lds_f64(aw1 + wo);
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      if (f < NJ) fb[f] *= ((L.selB >> f) & 1u) ? w1 : w0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -229,18 +242,17 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane & 3, lc = lane >> 2;
   const int grp = blockIdx.x % n_groups, chunk = blockIdx.x / n_groups;
-  const size_t raw_elems = (size_t)TN * (K + 3);
   const int ZS = 8 * ((2 * K + 7) / 8) + 4;
   const size_t z_elems = (size_t)TN * (ZS + 3);
-  double* zbase = sm + 2 * raw_elems;                      // two buffers [TN x ZS packed rows | a b c]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(zbase + 2 * z_elems);
+  double* zbase = sm;                                      // kGbBuffers x [TN x ZS packed rows | a b c]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(zbase + kGbBuffers * z_elems);
   const unsigned sm_u = smem_u32(sm), bars_u = smem_u32(bars);
   if (tid == 0) {
-    mbar_init(bars_u, 1);
-    mbar_init(bars_u + 8, 1);
+#pragma unroll
+    for (int b2 = 0; b2 < kGbBuffers; ++b2) mbar_init(bars_u + 8 * b2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  for (int b2 = 0; b2 < 2; ++b2)                           // the zero tail of every Z row, once
+  for (int b2 = 0; b2 < kGbBuffers; ++b2)                  // the zero tail of every Z row, once
     for (int r = warp; r < TN; r += kGbWarps)
       for (int c = 2 * K + lane; c < ZS; c += 32) zbase[b2 * z_elems + (size_t)r * ZS + c] = 0.0;
 
@@ -269,55 +281,54 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   __syncthreads();
 
-  // Stage j of this CTA is global stage chunk + j n_chunk.  Its rows arrive in raw slot j % 2 by
-  // bulk async copies, one piece per warp (a single big copy is served too slowly to keep up), are
-  // packed into Z buffer j % 2 while the slower warps still run the DMMAs of stage j - 1, and are
-  // consumed after ONE block barrier per stage.
+  // Stage j of this CTA is global stage chunk + j n_chunk and lives in buffer j % 3.  The x part
+  // of its rows and its weights arrive by bulk async copies (TMA), one per row, straight into the
+  // packed layout (K even; odd K rows are not 16-B aligned and are loaded by the warps instead);
+  // the s part is squared in place by the warps that finish stage j - 1 early; ONE block barrier
+  // per stage.  A buffer is refilled two stages ahead.
   const int64_t nstage = (N + TN - 1) / TN;
   const int64_t nfull = N / TN;
   const int64_t nmine = (chunk < nstage) ? (nstage - chunk + n_chunk - 1) / n_chunk : 0;
-  int prow = 2;                                                     // rows per piece, even: 16-B sizes
-  while (TN / prow > kGbWarps || TN % prow) prow += 2;              // TN is a multiple of 16
-  const int npiece = TN / prow;
-  const unsigned xbytes = (unsigned)((size_t)TN * K * sizeof(double));
+  const bool tma_x = (K & 1) == 0;
+  const unsigned rbytes = (unsigned)(K * sizeof(double));
   const unsigned wbytes = (unsigned)(TN * sizeof(double));
   auto arm = [&](int64_t j) {      // thread 0, BEFORE the barrier that precedes issue(j)
-    if (j < nmine && chunk + j * n_chunk < nfull) mbar_arrive_expect_tx(bars_u + 8 * (unsigned)(j & 1), xbytes + 3 * wbytes);
+    if (j < nmine && chunk + j * n_chunk < nfull)
+      mbar_arrive_expect_tx(bars_u + 8 * (unsigned)(j % kGbBuffers), (tma_x ? TN * rbytes : 0u) + 3 * wbytes);
   };
-  auto issue = [&](int64_t j) {    // lane 0 of every warp
+  auto issue = [&](int64_t j) {    // threads 0 .. TN-1: one row each; threads TN .. TN+2: the weights
     const int64_t s = chunk + j * n_chunk;
-    if (j < nmine && s < nfull && lane == 0) {
-      const unsigned bar = bars_u + 8 * (unsigned)(j & 1);
-      const unsigned dst = sm_u + (unsigned)((j & 1) * raw_elems * sizeof(double));
-      if (warp < npiece) {
-        const unsigned pb = (unsigned)((size_t)prow * K * sizeof(double));
-        bulk_g2s(dst + warp * pb, X + (s * TN + (int64_t)warp * prow) * K, pb, bar);
-      }
-      if (warp >= kGbWarps - 3) {
-        const int f = warp - (kGbWarps - 3);
-        bulk_g2s(dst + xbytes + f * wbytes, Wabc + (int64_t)f * ldw + s * TN, wbytes, bar);
+    if (j < nmine && s < nfull && tid < TN + 3) {
+      const unsigned b2 = (unsigned)(j % kGbBuffers);
+      const unsigned bar = bars_u + 8 * b2;
+      const unsigned dst = sm_u + (unsigned)(b2 * z_elems * sizeof(double));
+      if (tid < TN) {
+        if (tma_x) bulk_g2s(dst + (unsigned)tid * (unsigned)(ZS * sizeof(double)), X + (s * TN + tid) * K, rbytes, bar);
+      } else {
+        const int f = tid - TN;
+        bulk_g2s(dst + (unsigned)((size_t)TN * ZS * sizeof(double)) + f * wbytes,
+                 Wabc + (int64_t)f * ldw + s * TN, wbytes, bar);
       }
     }
   };
-  auto pack = [&](int64_t j) {     // all warps: stage j -> Z buffer j % 2
+  auto square = [&](int64_t j) {   // all warps: finish stage j in its buffer (s = x * x)
     const int64_t s = chunk + j * n_chunk;
-    double* zb = zbase + (j & 1) * z_elems;
+    double* zb = zbase + (j % kGbBuffers) * z_elems;
     double* zw = zb + (size_t)TN * ZS;
     if (s < nfull) {
-      const double* xs = sm + (j & 1) * raw_elems;
-      mbar_wait(bars_u + 8 * (unsigned)(j & 1), (unsigned)(j >> 1) & 1u);
+      mbar_wait(bars_u + 8 * (unsigned)(j % kGbBuffers), (unsigned)(j / kGbBuffers) & 1u);
       for (int r0 = 4 * warp; r0 < TN; r0 += 4 * kGbWarps)
         for (int k = lane; k < K; k += 32) {
           double v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = xs[(size_t)(r0 + u) * K + k];
+          for (int u = 0; u < 4; ++u)
+            v[u] = tma_x ? zb[(size_t)(r0 + u) * ZS + k] : X[(s * TN + r0 + u) * K + k];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            zb[(size_t)(r0 + u) * ZS + k] = v[u];
+            if (!tma_x) zb[(size_t)(r0 + u) * ZS + k] = v[u];
             zb[(size_t)(r0 + u) * ZS + K + k] = v[u] * v[u];
           }
         }
-      for (int e = tid; e < 3 * TN; e += blockDim.x) zw[e] = xs[(size_t)TN * K + e];
     } else {   // ragged last stage of the data: straight from global memory, zero fill
       const int rows = (int)(N - s * TN);
       for (int r = warp; r < TN; r += kGbWarps)
@@ -333,19 +344,17 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
     }
   };
 
-#ifndef LRVB_GB_NOPACK
   if (tid == 0) { arm(0); arm(1); }
   __syncthreads();
   issue(0);
   issue(1);
-  if (nmine > 0) pack(0);
+  if (nmine > 0) square(0);
   if (tid == 0) arm(2);
   __syncthreads();
   issue(2);
-#endif
   for (int64_t j = 0; j < nmine; ++j) {
     const int64_t s = chunk + j * n_chunk;
-    const double* zb = zbase + (j & 1) * z_elems;
+    const double* zb = zbase + (j % kGbBuffers) * z_elems;
     const double* sw = zb + (size_t)TN * ZS;
     const int rows = (s < nfull) ? TN : (int)(N - s * TN);
     const int ksteps = (rows + 3) >> 2;
@@ -365,16 +374,10 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_
         }
       }
     }
-#ifndef LRVB_GB_NOPACK
-    if (j + 1 < nmine) pack(j + 1);      // Z buffer (j+1) % 2 was last read in stage j - 1
-    if (tid == 0) arm(j + 3);            // raw slot (j+1) % 2: its current phase completed above
-#endif
-#ifndef LRVB_GB_NOBAR
-    __syncthreads();                     // Z(j+1) complete; stage j's DMMAs and raw slot (j+1) % 2 done
-#endif
-#ifndef LRVB_GB_NOPACK
+    if (j + 1 < nmine) square(j + 1);    // its TMA was issued two barriers ago
+    if (tid == 0) arm(j + 3);            // buffer j % 3: its phase for stage j completed long ago
+    __syncthreads();                     // stage j + 1 complete in shared memory; buffer j % 3 is free
     issue(j + 3);
-#endif
   }
 
   if (active) {
