@@ -115,6 +115,16 @@ int lrvb_glmm_set_global_block(lrvb_glmm* h, const double* A_dev, void* stream);
  * aligned); rows 2-4 only after order 2.  Borrowed pointer. */
 int lrvb_glmm_obs_weights(lrvb_glmm* h, double** W_dev, int64_t* ld);
 
+/* ---- cross-Hessian with the observation weights ------------------------------------------
+ * Replaces TwoParameterObjective.fun_hessian_free1_vector2 (SparseObjectives.py:429-438) as used
+ * by ParametricSensitivityLinearApproximation (ModelSensitivity.py:555-612) when the
+ * hyperparameter is the vector of observation weights: C = d^2 KL / d free d w is (D x N) with
+ * column n = -grad_free l_n; it is applied, never formed.  Both calls work at the point (and in the
+ * coordinates) of the last lrvb_glmm_eval, for K <= 62.  dw: dev (N) 16-byte aligned, in the
+ * handle's (group-sorted) observation order; v: dev (D). */
+int lrvb_glmm_weight_cross_matvec(lrvb_glmm* h, const double* dw_dev, double* out_dev /* D */, void* stream);
+int lrvb_glmm_weight_cross_rmatvec(lrvb_glmm* h, const double* v_dev, double* out_dev /* N */, void* stream);
+
 /* ---- sparse Hessian export ------------------------------------------------------------
  * Replaces get_sparse_sub_hessian + csr_matrix summation (SparseObjectives.py:591-619):
  * exact zeros dropped, columns sorted, int32 indices, one entry per coordinate.

@@ -344,6 +344,41 @@ class LogisticGLMM(object):
                                           1 if include_A else 0, nat.stream_ptr()))
         return out
 
+    # ---- cross-Hessian with the observation weights (csrc/sensitivity.cu) ------------------
+    def weight_cross_matvec(self, dw):
+        """C dw (D,), C = d^2 KL / d free d w (column n = -grad_free l_n), at the point and in the
+        coordinates of the last evaluation; ``dw`` (N,) in the caller's observation order."""
+        torch = nat.require_cuda()
+        d = to_device(dw).reshape(-1)
+        if d.numel() != self.N:
+            raise ValueError("Wrong size for weights.  Expected {}, got {}".format(self.N, d.numel()))
+        if self.perm is not None:
+            d = d.index_select(0, to_device(self.perm, torch.int64))
+        d = d.contiguous()
+        if d.numel() and d.data_ptr() % 16:
+            d = d.clone()
+        out = torch.empty(self.D, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_weight_cross_matvec(self._h, nat.ptr(d), nat.ptr(out),
+                                                          nat.stream_ptr()))
+        return out
+
+    def weight_cross_rmatvec(self, v):
+        """C^T v (N,) in the caller's observation order: minus the directional derivative of every
+        observation's log-likelihood term along ``v`` (D,)."""
+        torch = nat.require_cuda()
+        vd = to_device(v).reshape(-1).contiguous()
+        if vd.numel() != self.D:
+            raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
+                self.glmm_par.name, self.D, vd.numel()))
+        out = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.lrvb_glmm_weight_cross_rmatvec(self._h, nat.ptr(vd), nat.ptr(out),
+                                                           nat.stream_ptr()))
+        if self.perm is not None:
+            res = torch.empty_like(out)
+            res.index_copy_(0, to_device(self.perm, torch.int64), out)
+            return res
+        return out
+
     # names shared with distributed.ShardedLogisticGLMM (where they add the all-reduce)
     def hvp(self, v):
         return self.hvp_cached(to_device(v).reshape(-1))

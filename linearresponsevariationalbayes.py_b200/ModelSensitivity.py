@@ -122,3 +122,75 @@ class LinearResponseCovariances(object):
         """LRVB covariance of the model's default moments [E mu, E tau, E beta, E u]."""
         j = self.get_moment_jacobian(calculate_moments)
         return self.get_lr_covariance_from_jacobians(j, j)
+
+
+class WeightSensitivityLinearApproximation(object):
+    """Linear approximation of the optimum as a function of the observation weights: the
+    reference's ``ParametricSensitivityLinearApproximation`` (ModelSensitivity.py:555-612) with
+    ``hyper_par`` = the weight vector of the GLMM.  There the sensitivity is the dense matrix
+    ``-cho_solve(chol(H), cross_hessian)`` of shape (D, N); here it is an operator
+
+        d input / d hyper = -H^{-1} C,    C = d^2 KL / d free d w   (column n = -grad l_n)
+
+    applied with the device cross-Hessian products (csrc/sensitivity.cu) and the arrowhead solve,
+    so N = 10^6..10^7 observations are fine.  ``get_dinput_dhyper()`` still returns the dense
+    matrix when it is small enough to be a matrix.
+    """
+    MAX_DENSE = 1 << 24
+
+    def __init__(self, objective, input_val0, hyper_val0=None, method="schur"):
+        self.lr = LinearResponseCovariances(objective, input_val0, method=method)
+        self.model = objective.model
+        if not hasattr(self.model, "weight_cross_matvec"):
+            raise TypeError("the model does not provide the weight cross-Hessian")
+        self.input_val0 = input_val0
+        n = self.model.N
+        if hyper_val0 is None:
+            w = getattr(self.model, "w", None)
+            hyper_val0 = np.ones(n) if w is None else self._to_caller_order(w)
+        self.hyper_val0 = np.asarray(hyper_val0, dtype=np.float64).reshape(-1)
+        if self.hyper_val0.size != n:
+            raise ValueError("Wrong size for weights.  Expected {}, got {}".format(
+                n, self.hyper_val0.size))
+
+    def _to_caller_order(self, w_sorted):
+        w = w_sorted.detach().cpu().numpy()
+        if self.model.perm is None:
+            return w
+        perm = np.asarray(self.model.perm.cpu() if is_torch(self.model.perm) else self.model.perm)
+        out = np.empty_like(w)
+        out[perm] = w
+        return out
+
+    def _ret(self, t):
+        return t if is_torch(self.input_val0) else t.cpu().numpy()
+
+    def get_dinput_dhyper_times(self, hyper_diff):
+        """(d input / d hyper) @ hyper_diff -> (D,): the first-order change of the optimum."""
+        self.lr._ensure_point()
+        return self._ret(-self.lr.hinv(self.model.weight_cross_matvec(hyper_diff)))
+
+    def get_dhyper_influence(self, v):
+        """(d input / d hyper)^T v -> (N,): the influence of every observation's weight on the
+        functional ``v . input`` (e.g. a row of a moment Jacobian)."""
+        self.lr._ensure_point()
+        return self._ret(-self.model.weight_cross_rmatvec(self.lr.hinv(v)))
+
+    def get_dinput_dhyper(self):
+        """The dense (D, N) Jacobian, as in the reference (only when D * N <= 2^24 entries)."""
+        import torch
+        D, n = self.model.D, self.model.N
+        if D * n > self.MAX_DENSE:
+            raise ValueError("d input / d hyper would have {} x {} entries; use "
+                             "get_dinput_dhyper_times / get_dhyper_influence".format(D, n))
+        eye = torch.eye(D, dtype=torch.float64, device=self.model.device)
+        rows = [self.get_dhyper_influence(eye[i]) for i in range(D)]
+        rows = [r if is_torch(r) else torch.from_numpy(r) for r in rows]
+        return self._ret(torch.stack([r.to(self.model.device) for r in rows]))
+
+    def predict_input_par_from_hyperparameters(self, new_hyper_par_value):
+        diff = np.asarray(new_hyper_par_value, dtype=np.float64).reshape(-1) - self.hyper_val0
+        step = self.get_dinput_dhyper_times(diff)
+        if is_torch(self.input_val0):
+            return self.input_val0 + step
+        return np.asarray(self.input_val0, dtype=np.float64) + step

@@ -22,7 +22,8 @@ from .SparseObjectives import (Objective, Logger, Timer, make_index_param,  # no
                                get_sparse_sub_matrix, get_sparse_sub_hessian, pack_csr_matrix,
                                unpack_csr_matrix, safe_matmul)
 from .ConjugateGradient import ConjugateGradientSolver  # noqa: F401
-from .ModelSensitivity import LinearResponseCovariances  # noqa: F401
+from .ModelSensitivity import (LinearResponseCovariances,  # noqa: F401
+                               WeightSensitivityLinearApproximation)
 from .GLMM import LogisticGLMM, GLMMPrior, DeviceCSR  # noqa: F401
 
 __version__ = "0.1.0"

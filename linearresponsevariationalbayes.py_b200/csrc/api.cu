@@ -270,6 +270,7 @@ int lrvb_glmm_set_coords(lrvb_glmm* h, int32_t vector_coords) {
     h->vecmode = vector_coords ? 1 : 0;
     h->hess_valid = 0;
     h->grad_valid = 0;
+    h->point_valid = 0;
   }
   return LRVB_OK;
 }

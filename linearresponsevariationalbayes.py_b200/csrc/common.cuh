@@ -187,6 +187,7 @@ struct lrvb_glmm {
   double* outg = nullptr;     // (1 + Dg + Dg*Dg) packed [KL, grad_g, A] of the last eval
   int hess_valid = 0;
   int grad_valid = 0;
+  int point_valid = 0;        // vec holds the constrained parameters of the last evaluation
   // optional per-kernel timing (bench): events around the whole eval, k_obs and k_gram
   // side stream: the HBM-bound per-group pass runs beside the FP64-bound Gram kernel
   cudaStream_t side = nullptr;

@@ -710,6 +710,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     h->hess_valid = 1;
   }
   if (order >= 1) h->grad_valid = 1;
+  h->point_valid = 1;
   if (h->timing) {
     LRVB_CUDA(cudaEventRecord(h->ev[5], st));
     h->ev_order = order;

@@ -337,7 +337,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
         const double lv = -wn * s.As * h;
         double2* wrow = reinterpret_cast<double2*>(wsm + 6 * lane);
         wrow[0] = make_double2(lm, lv);
-        if (valid) {
+        if (valid && W) {     // W == nullptr: sums only (the weight cross-Hessian matvec)
           W[n] = lm;
           W[ldw + n] = lv;
         }
@@ -348,7 +348,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
           const double c = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
           wrow[1] = make_double2(a, b);
           wrow[2] = make_double2(c, 0.0);
-          if (valid) {
+          if (valid && W) {
             W[2 * ldw + n] = a;
             W[3 * ldw + n] = b;
             W[4 * ldw + n] = c;
