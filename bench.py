@@ -303,6 +303,28 @@ def run_ours(args, wl):
             ", ".join("#%d %.3f" % (i, step_ms[i]) for i in worst)), file=sys.stderr)
     nnz = csr.nnz
 
+    # ---------------- LRVB covariance of the global parameters (second half of the metric) -------
+    # (H^-1)[:Dg,:Dg] by the Schur complement of the local blocks on the cached Hessian: DMMA Gram
+    # over the border matrix [+ all-reduce of S when sharded] + SPD inverse; device timed, max over ranks
+    for _ in range(3):
+        cov = model.global_covariance()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncov = 20
+    c0.record()
+    for _ in range(ncov):
+        if world > 1:
+            model._sinv = None              # the sharded model caches the result: recompute
+        cov = model.global_covariance()
+    c1.record()
+    c1.synchronize()
+    cov_ms = torch.tensor([c0.elapsed_time(c1) / ncov], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(cov_ms, op=dist.ReduceOp.MAX)
+    cov_ms = float(cov_ms.item())
+
     # ---------------- end to end through the public API (host buffers) ----------------
     nat.check(lib.lrvb_glmm_set_timing(local._h, 0))
 
@@ -399,6 +421,8 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": d2h,
                     "api": "Objective.fun_free_hessian/fun_free_grad/fun_free with numpy x; "
                            "scipy CSR + numpy gradient + float returned to the host"},
+            "lrvb_covariance": {"ms": cov_ms, "what": "(H^-1)[:Dg,:Dg] of the cached Hessian, Schur "
+                                "complement (DMMA) + SPD inverse, device time", "Dg": 4 + 2 * K},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": clocks,
         }
