@@ -23,12 +23,11 @@ constexpr int kScanChunk = 2048;  // per CTA (256 threads x 8)
 
 // ---- local rows: one warp per row ------------------------------------------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(256)
-k_csr_local_rows(const double* __restrict__ B, const double* __restrict__ L, int Dg, int G,
+__device__ __forceinline__ void csr_local_rows_body(int bid, const double* __restrict__ B, const double* __restrict__ L, int Dg, int G,
                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ indptr,
                  int32_t* __restrict__ indices, double* __restrict__ data) {
   const int lane = threadIdx.x & 31;
-  const int64_t wg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t wg = (int64_t)bid * 8 + (threadIdx.x >> 5);
   if (wg >= 2 * (int64_t)G) return;
   const int which = (wg >= G) ? 1 : 0;
   const int gi = (int)(wg - (which ? G : 0));
@@ -67,12 +66,11 @@ k_csr_local_rows(const double* __restrict__ B, const double* __restrict__ L, int
 
 // ---- global rows, part 1: the dense block A (one warp per row) -----------------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(256)
-k_csr_A_rows(const double* __restrict__ A, int Dg, int32_t* __restrict__ cntA,
+__device__ __forceinline__ void csr_A_rows_body(int bid, const double* __restrict__ A, int Dg, int32_t* __restrict__ cntA,
              const int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
              double* __restrict__ data) {
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r = bid * 8 + (threadIdx.x >> 5);
   if (r >= Dg) return;
   const double* a = A + (size_t)r * Dg;
   int64_t base = FILL ? indptr[r] : 0;
@@ -96,14 +94,13 @@ k_csr_A_rows(const double* __restrict__ A, int Dg, int32_t* __restrict__ cntA,
 // ---- global rows, part 2: columns of B, chunked over groups -----------------------------------
 // chunkcnt / chunkoff: (nchunk, 2*Dg) int32, column c = side*Dg + r.
 template <bool FILL>
-__global__ void __launch_bounds__(256)
-k_csr_B_cols(const double* __restrict__ B, int Dg, int G, int CG, int32_t* __restrict__ chunkcnt,
+__device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restrict__ B, int Dg, int G, int CG, int32_t* __restrict__ chunkcnt,
              const int32_t* __restrict__ chunkoff, const int32_t* __restrict__ cntA,
              const int32_t* __restrict__ coltot, const int32_t* __restrict__ indptr,
              int32_t* __restrict__ indices, double* __restrict__ data) {
   extern __shared__ double tile[];   // CG x (2*Dg + 1)  (+1: conflict-free column reads)
   const int ncol = 2 * Dg, ld = ncol + 1;
-  const int chunk = blockIdx.x;
+  const int chunk = bid;
   const int g0 = chunk * CG;
   const int ng = (G - g0 < CG) ? (G - g0) : CG;
   const double* src = B + (size_t)g0 * ncol;
@@ -133,6 +130,25 @@ k_csr_B_cols(const double* __restrict__ B, int Dg, int G, int CG, int32_t* __res
       count += __popc(m);
     }
     if (!FILL && lane == 0) chunkcnt[(size_t)chunk * ncol + c] = count;
+  }
+}
+
+// One launch per phase: blocks [0, nA) take the rows of A, the next nB blocks a chunk of B each,
+// the rest the local rows (block-uniform roles; only the B role uses the dynamic shared memory).
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ L,
+           int Dg, int G, int CG, int nA, int nB, int32_t* __restrict__ cntA,
+           int32_t* __restrict__ chunkcnt, const int32_t* __restrict__ chunkoff,
+           const int32_t* __restrict__ coltot, int32_t* __restrict__ rowcnt,
+           const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data) {
+  const int bid = blockIdx.x;
+  if (bid < nA) {
+    csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data);
+  } else if (bid < nA + nB) {
+    csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
+  } else {
+    csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data);
   }
 }
 
@@ -236,7 +252,7 @@ k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restri
 static int csr_chunk_groups(int Dg) {
   // stage CG x (2 Dg + 1) doubles in <= ~96 KB of shared memory
   int cg = 32;
-  while (cg > 4 && sizeof(double) * (size_t)cg * (2 * Dg + 1) > 96 * 1024) cg >>= 1;
+  while (cg > 4 && sizeof(double) * (size_t)cg * (2 * Dg + 1) > 27 * 1024) cg >>= 1;   // the merged pass keeps 8 CTAs/SM
   return cg;
 }
 
@@ -255,8 +271,8 @@ static int ensure_csr_scratch(lrvb_glmm* h) {
   LRVB_CUDA(cudaMalloc((void**)&h->csrwork,
                        sizeof(int32_t) * ((size_t)3 * Dg + (size_t)4 * Dg * nchunk + 4)));
   const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
-  cudaFuncSetAttribute(k_csr_B_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_csr_B_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return LRVB_OK;
 }
 
@@ -298,17 +314,13 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
   int64_t* blk = (int64_t*)h->scanblk;
   const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
 
-  // ---- counts ----
-  k_csr_A_rows<false><<<cdiv(Dg, 8), 256, 0, st>>>(h->A, Dg, cntA, nullptr, nullptr, nullptr);
+  const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
+  // ---- counts: rows of A, columns of B (per chunk) and local rows in one launch ----
+  k_csr_pass<false><<<nA + nB + nL, 256, smem, st>>>(h->A, h->B, h->L, Dg, G, CG, nA, nB, cntA, chunkcnt,
+                                                    nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr);
   LRVB_CHECK_LAUNCH();
   if (G > 0) {
-    k_csr_B_cols<false><<<nchunk, 256, smem, st>>>(h->B, Dg, G, CG, chunkcnt, nullptr, nullptr,
-                                                   nullptr, nullptr, nullptr, nullptr);
-    LRVB_CHECK_LAUNCH();
     k_csr_colscan<<<2 * Dg, 256, 0, st>>>(chunkcnt, chunkoff, coltot, nchunk, 2 * Dg);
-    LRVB_CHECK_LAUNCH();
-    k_csr_local_rows<false><<<cdiv(2 * (int64_t)G, 8), 256, 0, st>>>(h->B, h->L, Dg, G, h->rowcnt,
-                                                                     nullptr, nullptr, nullptr);
     LRVB_CHECK_LAUNCH();
   } else {
     LRVB_CUDA(cudaMemsetAsync(coltot, 0, sizeof(int32_t) * 2 * Dg, st));
@@ -322,17 +334,10 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
   LRVB_CHECK_LAUNCH();
   k_scan_apply<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk, blk + nblk, indptr_dev);
   LRVB_CHECK_LAUNCH();
-  // ---- fill ----
-  k_csr_A_rows<true><<<cdiv(Dg, 8), 256, 0, st>>>(h->A, Dg, nullptr, indptr_dev, indices_dev, data_dev);
+  // ---- fill: the same three roles, one launch ----
+  k_csr_pass<true><<<nA + nB + nL, 256, smem, st>>>(h->A, h->B, h->L, Dg, G, CG, nA, nB, cntA, nullptr,
+                                                   chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev);
   LRVB_CHECK_LAUNCH();
-  if (G > 0) {
-    k_csr_B_cols<true><<<nchunk, 256, smem, st>>>(h->B, Dg, G, CG, nullptr, chunkoff, cntA, coltot,
-                                                  indptr_dev, indices_dev, data_dev);
-    LRVB_CHECK_LAUNCH();
-    k_csr_local_rows<true><<<cdiv(2 * (int64_t)G, 8), 256, 0, st>>>(h->B, h->L, Dg, G, nullptr,
-                                                                    indptr_dev, indices_dev, data_dev);
-    LRVB_CHECK_LAUNCH();
-  }
   return LRVB_OK;
 }
 
