@@ -36,6 +36,9 @@ CASES = {
     # packed-Gram tile shapes: no straddle tile (K = 16), straddle in tile 0 (K = 3)
     "k16": dict(N=3000, K=16, G=30, Q=8, seed=21),
     "k3": dict(N=3000, K=3, G=30, Q=8, seed=22, intercept=True),
+    # several job groups of the rectangle Gram kernel, 16-row stages; zero weights among the rest
+    "k130_job_groups": dict(N=1100, K=130, G=11, Q=4, seed=23),
+    "k21_odd_rows_not_tma": dict(N=2100, K=21, G=20, Q=8, seed=24, weights=True),
 }
 
 
