@@ -1,4 +1,7 @@
 """Timing of the batched exponential-family terms at BASELINE configs[4] (1M local factors)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import torch
 import lrvb_b200 as vb
 ef = vb.ExponentialFamilies

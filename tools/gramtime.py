@@ -1,4 +1,7 @@
 """Gram-kernel time (events inside lrvb_glmm_eval) for several K at fixed N; prints achieved DMMA rates."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import ctypes, sys
 import torch
 import lrvb_b200 as vb

@@ -1,4 +1,7 @@
 """Tiny driver for ncu: a few order-2 evaluations (+ CSR, HVP) at a named config."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import sys
 import torch
 import lrvb_b200 as vb

@@ -1,4 +1,7 @@
 """Scratch timing of the evaluation pipeline at BASELINE configs (not the bench)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import sys, time
 import numpy as np, torch
 import lrvb_b200 as vb

@@ -1,4 +1,7 @@
 """Scratch timing of the evaluation at C2 / C3 (orders 0,1,2), smaller than tools_quicktime."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import sys
 import torch
 import lrvb_b200 as vb
