@@ -48,7 +48,7 @@ class ClockSampler(object):
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
                ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
 
-    def __init__(self, index, period_s=0.010):
+    def __init__(self, index, period_s=0.002):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.power = [], set(), []
         self.handle, self.nvml, self.max_mhz = None, None, None
@@ -78,7 +78,7 @@ class ClockSampler(object):
                 for name, bit in self.REASONS:
                     if mask & bit:
                         self.reasons.add(name)
-                if len(self.samples) % 8 == 1:     # the power query is the slow one: sparse
+                if len(self.samples) % 32 == 1:    # the power query is the slow one: sparse
                     self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
             except Exception:          # noqa: BLE001
                 pass
