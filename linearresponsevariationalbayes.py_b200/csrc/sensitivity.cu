@@ -180,7 +180,7 @@ using namespace lrvb;
 extern "C" {
 
 int lrvb_glmm_weight_cross_matvec(lrvb_glmm* h, const double* dw_dev, double* out_dev, void* stream) {
-  LRVB_REQUIRE(h != nullptr && dw_dev != nullptr && out_dev != nullptr,
+  LRVB_REQUIRE(h != nullptr && out_dev != nullptr && (dw_dev != nullptr || h->N == 0),
                "lrvb_glmm_weight_cross_matvec: NULL argument");
   LRVB_REQUIRE((((uintptr_t)dw_dev) & 15) == 0, "lrvb_glmm_weight_cross_matvec: dw not 16-byte aligned");
   if (!h->point_valid) {
@@ -228,7 +228,7 @@ int lrvb_glmm_weight_cross_matvec(lrvb_glmm* h, const double* dw_dev, double* ou
 }
 
 int lrvb_glmm_weight_cross_rmatvec(lrvb_glmm* h, const double* v_dev, double* out_dev, void* stream) {
-  LRVB_REQUIRE(h != nullptr && v_dev != nullptr && out_dev != nullptr,
+  LRVB_REQUIRE(h != nullptr && v_dev != nullptr && (out_dev != nullptr || h->N == 0),
                "lrvb_glmm_weight_cross_rmatvec: NULL argument");
   if (!h->point_valid) {
     set_error("lrvb_glmm_weight_cross_rmatvec: no evaluation cached (call lrvb_glmm_eval first)");

@@ -154,3 +154,24 @@ def test_cg_and_direct_solve(setup, vb):
     cov_m = lr.get_lr_covariance()
     ref = J @ Hinv @ J.T
     assert_close(cov_m, ref, rtol=1e-8, scale=np.abs(ref).max() * 1e-3, what="moment covariance")
+
+
+def test_no_observations(vb):
+    """N = 0 (a rank that owns no group in a sharded job, or priors only): the data kernels are
+    skipped, the non-data terms and the Hessian pattern must still match the oracle."""
+    from oracle import glmm_oracle as go
+    K, G, Q = 3, 4, 5
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+    X, y, g = np.zeros((0, K)), np.zeros(0), np.zeros(0, np.int64)
+    oracle = go.GLMMOracle(X, y, g, gh_x, gh_w, G=G)
+    model = vb.LogisticGLMM(X, y, g, gh_x=gh_x, gh_w=gh_w, num_groups=G)
+    obj = vb.Objective(model.glmm_par, model)
+    x = go.make_free(model.D, 41)
+    assert_close(obj.fun_free(x), oracle.kl(x), what="KL")
+    ge = oracle.kl_grad(x)
+    assert_close(obj.fun_free_grad(x), ge, scale=np.abs(ge).max() * 1e-3, what="grad")
+    H, He = obj.fun_free_hessian(x), oracle.kl_hessian_csr(x)
+    np.testing.assert_array_equal(H.indptr, He.indptr)
+    np.testing.assert_array_equal(H.indices, He.indices)
+    assert_close(H.data, He.data, scale=np.abs(He.data).max() * 1e-6, what="hessian data")
+    assert np.all(model.weight_cross_matvec(np.zeros(0)).cpu().numpy() == 0.0)
