@@ -17,6 +17,7 @@ from . import Modeling  # noqa: F401
 from . import SparseObjectives  # noqa: F401
 from . import ConjugateGradient  # noqa: F401
 from . import ModelSensitivity  # noqa: F401
+from . import OptimizationUtils  # noqa: F401
 from . import GLMM  # noqa: F401
 from .SparseObjectives import (Objective, Logger, Timer, make_index_param,  # noqa: F401
                                get_sparse_sub_matrix, get_sparse_sub_hessian, pack_csr_matrix,
