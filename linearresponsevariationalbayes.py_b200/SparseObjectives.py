@@ -269,3 +269,46 @@ def unpack_csr_matrix(sp_mat_dict):
     return sp.sparse.csr_matrix(
         (sp_mat_dict["data"], sp_mat_dict["indices"], sp_mat_dict["indptr"]),
         shape=sp_mat_dict["shape"])
+
+
+# ---- JSON wire format of a CSR matrix (:639-657) -------------------------------------------------
+# The reference serialises the three arrays with ``json_tricks.dumps`` (an optional dependency that
+# is not needed here): each becomes the JSON text of
+#   {"__ndarray__": [...], "dtype": "float64", "shape": [n], "Corder": true}
+# These two helpers write and read exactly that text with the standard library, so dictionaries
+# produced by either code base can be read by the other.
+def _ndarray_to_json(a):
+    import json
+    a = np.ascontiguousarray(a)
+    return json.dumps({"__ndarray__": a.tolist(), "dtype": str(a.dtype), "shape": list(a.shape),
+                       "Corder": True})
+
+
+def _ndarray_from_json(text):
+    import json
+    d = json.loads(text) if isinstance(text, str) else text
+    if isinstance(d, dict) and "__ndarray__" in d:
+        a = np.asarray(d["__ndarray__"], dtype=np.dtype(d.get("dtype", "float64")))
+        return a.reshape(d["shape"]) if "shape" in d else a
+    return np.asarray(d)
+
+
+def json_pack_csr_matrix(sp_mat):
+    """:639-647 -- a json-serialisable dict of a CSR matrix (host scipy matrix or DeviceCSR)."""
+    if hasattr(sp_mat, "to_scipy"):
+        sp_mat = sp_mat.to_scipy()
+    assert sp.sparse.isspmatrix_csr(sp_mat)
+    sp_mat = sp.sparse.csr_matrix(sp_mat)
+    return {"data": _ndarray_to_json(sp_mat.data), "indices": _ndarray_to_json(sp_mat.indices),
+            "indptr": _ndarray_to_json(sp_mat.indptr), "shape": tuple(int(v) for v in sp_mat.shape),
+            "type": "csr_matrix"}
+
+
+def json_unpack_csr_matrix(sp_mat_dict):
+    """:651-657 -- the inverse of ``json_pack_csr_matrix``."""
+    assert sp_mat_dict["type"] == "csr_matrix"
+    data = _ndarray_from_json(sp_mat_dict["data"])
+    indices = _ndarray_from_json(sp_mat_dict["indices"])
+    indptr = _ndarray_from_json(sp_mat_dict["indptr"])
+    return sp.sparse.csr_matrix((data, indices, indptr), shape=tuple(sp_mat_dict["shape"]))
+

@@ -21,7 +21,8 @@ from . import OptimizationUtils  # noqa: F401
 from . import GLMM  # noqa: F401
 from .SparseObjectives import (Objective, Logger, Timer, make_index_param,  # noqa: F401
                                get_sparse_sub_matrix, get_sparse_sub_hessian, pack_csr_matrix,
-                               unpack_csr_matrix, safe_matmul)
+                               unpack_csr_matrix, json_pack_csr_matrix,
+                               json_unpack_csr_matrix, safe_matmul)
 from .ConjugateGradient import ConjugateGradientSolver  # noqa: F401
 from .ModelSensitivity import (LinearResponseCovariances,  # noqa: F401
                                WeightSensitivityLinearApproximation)

@@ -190,3 +190,23 @@ def test_cg_mask_helpers_and_generic_solver(vb):
         assert info == 0
         assert np.max(np.abs(hv - np.linalg.solve(H, vm))) < 1e-8
     assert len(solver.times) == 5
+
+
+def test_json_csr_wire_format_round_trip(vb):
+    """SparseObjectives.py:639-657: the JSON dictionary of a CSR matrix survives json.dumps /
+    loads bit-exactly and carries the json_tricks array layout the reference writes."""
+    import json
+    import scipy.sparse
+    rng = np.random.default_rng(9)
+    dense = rng.standard_normal((7, 5)) * (rng.random((7, 5)) < 0.4)
+    m = scipy.sparse.csr_matrix(dense)
+    packed = vb.json_pack_csr_matrix(m)
+    assert packed["type"] == "csr_matrix"
+    arr = json.loads(packed["data"])
+    assert set(arr) >= {"__ndarray__", "dtype", "shape"} and arr["dtype"] == "float64"
+    back = vb.json_unpack_csr_matrix(json.loads(json.dumps(packed)))
+    assert back.shape == m.shape
+    np.testing.assert_array_equal(back.indptr, m.indptr)
+    np.testing.assert_array_equal(back.indices, m.indices)
+    np.testing.assert_array_equal(back.data, m.data)
+    assert back.indices.dtype == m.indices.dtype
