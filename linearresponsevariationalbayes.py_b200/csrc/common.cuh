@@ -83,6 +83,31 @@ __host__ __device__ inline double tetragamma_pos(double x) {
 }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the evaluation / CSR chain starts with pdl_sync(): it lets the NEXT kernel of the
+// stream be scheduled right away (its CTAs start as soon as SM resources free up instead of after
+// a full launch round trip) and then waits until the PREVIOUS kernel has completed and flushed its
+// memory.  Launched without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- warp / block helpers ----------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -142,6 +142,7 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
            int32_t* __restrict__ chunkcnt, const int32_t* __restrict__ chunkoff,
            const int32_t* __restrict__ coltot, int32_t* __restrict__ rowcnt,
            const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data) {
+  pdl_sync();
   const int bid = blockIdx.x;
   if (bid < nA) {
     csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data);
@@ -156,6 +157,7 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
 __global__ void __launch_bounds__(256)
 k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunkoff,
               int32_t* __restrict__ coltot, int nchunk, int ncol) {
+  pdl_sync();
   __shared__ int wsum[8];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -188,6 +190,7 @@ k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunko
 __global__ void k_csr_global_rowcnt(const int32_t* __restrict__ cntA,
                                     const int32_t* __restrict__ coltot, int Dg,
                                     int32_t* __restrict__ rowcnt) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < Dg) rowcnt[r] = cntA[r] + coltot[r] + coltot[Dg + r];
 }
@@ -195,6 +198,7 @@ __global__ void k_csr_global_rowcnt(const int32_t* __restrict__ cntA,
 // ---- exclusive scan of rowcnt (n entries) into indptr (n+1 entries), 3 phases --------------------
 __global__ void __launch_bounds__(256)
 k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk) {
+  pdl_sync();
   __shared__ double red[32];
   const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
   long long s = 0;
@@ -207,6 +211,7 @@ k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk
 
 __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restrict__ total,
                            int64_t* __restrict__ nnz_out) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int64_t run = 0;
   for (int i = 0; i < nblk; ++i) {
@@ -221,6 +226,7 @@ __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restr
 __global__ void __launch_bounds__(256)
 k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restrict__ blk,
              const int64_t* __restrict__ total, int32_t* __restrict__ indptr) {
+  pdl_sync();
   __shared__ int wsum[8];
   const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -316,27 +322,27 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
 
   const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
   // ---- counts: rows of A, columns of B (per chunk) and local rows in one launch ----
-  k_csr_pass<false><<<nA + nB + nL, 256, smem, st>>>(h->A, h->B, h->L, Dg, G, CG, nA, nB, cntA, chunkcnt,
-                                                    nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr);
+  LRVB_CUDA(launch_pdl(k_csr_pass<false>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G,
+                       CG, nA, nB, cntA, chunkcnt, nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr));
   LRVB_CHECK_LAUNCH();
   if (G > 0) {
-    k_csr_colscan<<<2 * Dg, 256, 0, st>>>(chunkcnt, chunkoff, coltot, nchunk, 2 * Dg);
+    LRVB_CUDA(launch_pdl(k_csr_colscan, dim3(2 * Dg), dim3(256), 0, st, chunkcnt, chunkoff, coltot, nchunk, 2 * Dg));
     LRVB_CHECK_LAUNCH();
   } else {
     LRVB_CUDA(cudaMemsetAsync(coltot, 0, sizeof(int32_t) * 2 * Dg, st));
   }
-  k_csr_global_rowcnt<<<cdiv(Dg, 256), 256, 0, st>>>(cntA, coltot, Dg, h->rowcnt);
+  LRVB_CUDA(launch_pdl(k_csr_global_rowcnt, dim3(cdiv(Dg, 256)), dim3(256), 0, st, cntA, coltot, Dg, h->rowcnt));
   LRVB_CHECK_LAUNCH();
   // ---- indptr ----
-  k_scan_sum<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk);
+  LRVB_CUDA(launch_pdl(k_scan_sum, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk));
   LRVB_CHECK_LAUNCH();
-  k_scan_top<<<1, 32, 0, st>>>(blk, nblk, blk + nblk, nnz_dev);
+  LRVB_CUDA(launch_pdl(k_scan_top, dim3(1), dim3(32), 0, st, blk, nblk, blk + nblk, nnz_dev));
   LRVB_CHECK_LAUNCH();
-  k_scan_apply<<<nblk, 256, 0, st>>>(h->rowcnt, D, blk, blk + nblk, indptr_dev);
+  LRVB_CUDA(launch_pdl(k_scan_apply, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, blk + nblk, indptr_dev));
   LRVB_CHECK_LAUNCH();
   // ---- fill: the same three roles, one launch ----
-  k_csr_pass<true><<<nA + nB + nL, 256, smem, st>>>(h->A, h->B, h->L, Dg, G, CG, nA, nB, cntA, nullptr,
-                                                   chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev);
+  LRVB_CUDA(launch_pdl(k_csr_pass<true>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
+                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev));
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }

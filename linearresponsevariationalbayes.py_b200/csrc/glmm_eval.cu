@@ -24,9 +24,13 @@ namespace lrvb {
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep(const double* __restrict__ free_v, double* __restrict__ vec, int K, int G,
-                       lrvb_glmm_bounds bd, int vecmode) {
+                       lrvb_glmm_bounds bd, int vecmode, double* __restrict__ zero, int64_t nzero) {
+  pdl_sync();
   const int64_t D = 4 + 2 * (int64_t)K + 2 * (int64_t)G;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // the global Hessian block starts from zero (order 2): cleared here instead of by a memset node,
+  // which would cut the chain of programmatic launches
+  for (int64_t j = i; j < nzero; j += (int64_t)gridDim.x * blockDim.x) zero[j] = 0.0;
   if (i >= D) return;
   const double f = free_v[i];
   double lb = 0.0;
@@ -433,6 +437,7 @@ k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const d
          double* __restrict__ locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
          const GbSlot* __restrict__ slots, double* __restrict__ A, int K, int G, int n_loc, int n_bor,
          int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode) {
+  pdl_sync();
   const int bid = blockIdx.x;
   const int Dg = 4 + 2 * K;
   if (bid < n_loc) {
@@ -459,6 +464,7 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
          const double* __restrict__ gradpart, int n_gp, const double* __restrict__ locpart,
          int n_lp, double* __restrict__ out, int K, int G, lrvb_glmm_prior pr,
          lrvb_glmm_bounds bd, int include_global, int vecmode) {
+  pdl_sync();
   __shared__ double red[32];
   __shared__ double sh[8];
   extern __shared__ double gsum[];  // 2K
@@ -588,10 +594,11 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   h->hess_valid = 0;
   h->grad_valid = 0;
   if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[4], st));
-  k_prep<<<cdiv(h->D, 256), 256, 0, st>>>(free_dev, h->vec, K, G, h->bounds, h->vecmode);
+  double* outp = out_global ? out_global : h->outg;
+  LRVB_CUDA(launch_pdl(k_prep, dim3(cdiv(h->D, 256)), dim3(256), 0, st, free_dev, h->vec, K, G, h->bounds,
+                       h->vecmode, outp + 1 + Dg, (int64_t)(order >= 2 ? (int64_t)Dg * Dg : 0)));
   LRVB_CHECK_LAUNCH();
 
-  double* outp = out_global ? out_global : h->outg;
   int n_obs_cta = 0;
   if (h->obs_fused) {
     // K <= 62: observation pass and per-group sums in one kernel (obs_fused.cuh)
@@ -599,9 +606,9 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
       const int nch = (K + 1 + 31) / 32;
 #define LRVB_OF(O, C)                                                                          \
-  k_obs_fused<O, C><<<h->of_grid, 32 * h->of_warps, h->of_smem, st>>>(                          \
+  LRVB_CUDA(launch_pdl(k_obs_fused<O, C>, dim3(h->of_grid), dim3(32 * h->of_warps), h->of_smem, st, \
       h->X, h->y, h->g, h->w, h->vec, h->gh, h->gptr, h->W, h->ldw, h->klpart, h->gradpart,    \
-      h->gsc, h->BR, h->bval, N, K, G, Q, h->of_rows_per_warp)
+      h->gsc, h->BR, h->bval, N, K, G, Q, h->of_rows_per_warp))
       if (nch == 1) {
         if (order == 0) LRVB_OF(0, 1);
         else if (order == 1) LRVB_OF(1, 1);
@@ -618,8 +625,8 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     }
     if (order >= 1 && G > 0) {
       const int64_t rpw = h->of_rows_per_warp > 0 ? h->of_rows_per_warp : 32;
-      if (order == 1) k_obs_fixup<1><<<cdiv(G, 8), 256, 0, st>>>(h->gptr, h->bval, h->gsc, h->BR, K, G, rpw);
-      else k_obs_fixup<2><<<cdiv(G, 8), 256, 0, st>>>(h->gptr, h->bval, h->gsc, h->BR, K, G, rpw);
+      if (order == 1) LRVB_CUDA(launch_pdl(k_obs_fixup<1>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G, rpw));
+      else LRVB_CUDA(launch_pdl(k_obs_fixup<2>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G, rpw));
       LRVB_CHECK_LAUNCH();
     }
   } else {
@@ -647,7 +654,6 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   }
   }
   if (order >= 2) {
-    LRVB_CUDA(cudaMemsetAsync(outp + 1 + Dg, 0, sizeof(double) * (size_t)Dg * Dg, st));
     if (N > 0) {
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[2], st));
       if (h->gram_small) {
@@ -656,9 +662,9 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
           return LRVB_ESTATE;
         }
       } else {
-        k_gram_big<<<h->gram_grid_x, 32 * kGbWarps, h->gram_smem, st>>>(
+        LRVB_CUDA(launch_pdl(k_gram_big, dim3(h->gram_grid_x), dim3(32 * kGbWarps), h->gram_smem, st,
             h->X, h->W + 2 * h->ldw, h->ldw, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,
-            h->grampart, N, K, h->gram_tn, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y);
+            h->grampart, N, K, h->gram_tn, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y));
       }
       LRVB_CHECK_LAUNCH();
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
@@ -677,11 +683,11 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     }
     const int grid = n_loc + n_bor + n_gf;
 #define LRVB_FIN(O)                                                                              \
-  k_finish<O><<<grid, 256, 0, st>>>(h->vec, h->gsc, h->BR, gl, h->L, h->B, h->locpart, h->grampart, \
-                                    (const GbJob*)h->jobs, (const GbSlot*)h->gslots, outp + 1 + Dg, K, \
-                                    G, n_loc, n_bor, h->gram_small, NT, h->gram_grid_y,           \
-                                    h->gram_small ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
-                                    h->bounds, h->vecmode)
+  LRVB_CUDA(launch_pdl(k_finish<O>, dim3(grid), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
+                       h->locpart, h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,   \
+                       outp + 1 + Dg, K, G, n_loc, n_bor, h->gram_small, NT, h->gram_grid_y,       \
+                       h->gram_small ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
+                       h->bounds, h->vecmode))
     if (order == 0) LRVB_FIN(0);
     else if (order == 1) LRVB_FIN(1);
     else LRVB_FIN(2);
@@ -690,9 +696,9 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   }
   const size_t gsm = sizeof(double) * 2 * (size_t)K;
 #define LRVB_GLOB(O)                                                                          \
-  k_global<O><<<1, 256, gsm, st>>>(h->vec, h->klpart, n_obs_cta, h->gradpart, n_obs_cta,       \
-                                   h->locpart, h->loc_grid, outp, K, G, h->prior, h->bounds,   \
-                                   h->include_global, h->vecmode)
+  LRVB_CUDA(launch_pdl(k_global<O>, dim3(1), dim3(256), gsm, st, h->vec, h->klpart, n_obs_cta, \
+                       h->gradpart, n_obs_cta, h->locpart, h->loc_grid, outp, K, G, h->prior,    \
+                       h->bounds, h->include_global, h->vecmode))
   if (order == 0) LRVB_GLOB(0);
   else if (order == 1) LRVB_GLOB(1);
   else LRVB_GLOB(2);

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(32 * kGbWarps, kGbCtasPerSM)
 k_gram_big(const double* __restrict__ X, const double* __restrict__ Wabc, int64_t ldw,
            const GbJob* __restrict__ jobs, const GbSlot* __restrict__ slots,
            double* __restrict__ part, int64_t N, int K, int TN, int n_groups, int n_chunk) {
+  pdl_sync();
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane & 3, lc = lane >> 2;

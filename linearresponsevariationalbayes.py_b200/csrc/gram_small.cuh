@@ -109,6 +109,7 @@ template <int T2, int T0, bool HAS_M>
 __global__ void __launch_bounds__(32 * kGsWarps, LRVB_GS_MINB)
 k_gram_small(const double* __restrict__ X, const double* __restrict__ Wabc,
              double* __restrict__ part, int64_t N, int64_t ldw, int K) {
+  pdl_sync();
   constexpr int TS = HAS_M ? T0 : -1;        // straddle tile
   constexpr int TB = HAS_M ? T0 + 1 : T0;    // first pure-s tile
   constexpr int NT = T2 * (T2 + 1) / 2;
@@ -348,8 +349,8 @@ inline bool launch_gram_small(const double* X, const double* Wabc, double* part,
                            (int)smem);                                                       \
       configured = smem;                                                                     \
     }                                                                                        \
-    k_gram_small<T2_, T0_, M_><<<grid, 32 * kGsWarps, smem, st>>>(X, Wabc, part, N, ldw, K); \
-    return true;                                                                             \
+    return launch_pdl(k_gram_small<T2_, T0_, M_>, dim3(grid), dim3(32 * kGsWarps), smem, st, X, Wabc, \
+                      part, N, ldw, K) == cudaSuccess;                                         \
   }
   LRVB_GS(1, 0, true)
   LRVB_GS(2, 0, true)

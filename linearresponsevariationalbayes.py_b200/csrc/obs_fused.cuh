@@ -150,6 +150,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
             double* __restrict__ klpart, double* __restrict__ gradpart, double* __restrict__ gsc,
             double* __restrict__ BR, double* __restrict__ bval, int64_t N, int K, int G, int Q,
             int64_t rows_per_warp) {
+  pdl_sync();
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int stage_elems = obs_fused_stage_elems(K);
@@ -458,6 +459,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(256)
 k_obs_fixup(const int32_t* __restrict__ gptr, const double* __restrict__ bval,
             double* __restrict__ gsc, double* __restrict__ BR, int K, int G, int64_t rows_per_warp) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int nb = 5 + 4 * K;
   const int gi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
