@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256)
 k_hvp_groups(const double* __restrict__ B, const double* __restrict__ L,
              const double* __restrict__ v, double* __restrict__ out,
              double* __restrict__ hvppart, const int* __restrict__ flags, int Dg, int G) {
+  pdl_sync();
   if (flags && flags[0]) return;
   extern __shared__ double sm[];
   double* vg = sm;             // Dg
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256)
 k_hvp_global(const double* __restrict__ A, const double* __restrict__ v,
              const double* __restrict__ hvppart, int npart, double* __restrict__ out,
              const int* __restrict__ flags, int Dg, int include_A) {
+  pdl_sync();
   if (flags && flags[0]) return;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -78,10 +80,10 @@ int launch_hvp(lrvb_glmm* h, const double* v, double* out, int include_A, const 
                cudaStream_t st) {
   const int Dg = h->Dg, G = h->G;
   const size_t smem = sizeof(double) * 9 * (size_t)Dg;
-  k_hvp_groups<<<h->hvp_grid, 256, smem, st>>>(h->B, h->L, v, out, h->hvppart, flags, Dg, G);
+  LRVB_CUDA(launch_pdl(k_hvp_groups, dim3(h->hvp_grid), dim3(256), smem, st, h->B, h->L, v, out, h->hvppart, flags, Dg, G));
   LRVB_CHECK_LAUNCH();
-  k_hvp_global<<<cdiv(Dg, 8), 256, 0, st>>>(h->A, v, h->hvppart, h->hvp_grid, out, flags, Dg,
-                                             include_A);
+  LRVB_CUDA(launch_pdl(k_hvp_global, dim3(cdiv(Dg, 8)), dim3(256), 0, st, h->A, v, h->hvppart, h->hvp_grid, out, flags, Dg,
+                                             include_A));
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256)
 k_dot(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
       const double* __restrict__ d, int64_t n, double* __restrict__ part,
       const int* __restrict__ flags) {
+  pdl_sync();
   if (flags && flags[0]) return;
   __shared__ double red[32];
   double s0 = 0.0, s1 = 0.0;
@@ -147,6 +150,7 @@ k_dot(const double* __restrict__ a, const double* __restrict__ b, const double* 
 // atol = rtol * ||b||; flags: done if ||b|| == 0
 __global__ void k_cg_init(const double* __restrict__ bbpart, int npart, double rtol,
                           double* __restrict__ scal, int* __restrict__ flags) {
+  pdl_sync();
   __shared__ double red[32];
   const double bb = reduce_parts(bbpart, npart, 2, red);
   if (threadIdx.x == 0) {
@@ -164,6 +168,7 @@ k_cg_precond(const double* __restrict__ r, double* __restrict__ z, const double*
              const double* __restrict__ Linv, const double* __restrict__ rrpart, int npart,
              double* __restrict__ rzpart, double* __restrict__ scal, int* __restrict__ flags,
              int Dg, int G, int precond) {
+  pdl_sync();
   if (flags[0]) return;
   __shared__ double red[32];
   const double rr = reduce_parts(rrpart, npart, 2, red);
@@ -201,6 +206,7 @@ k_cg_precond(const double* __restrict__ r, double* __restrict__ z, const double*
 // flags[2] (set by k_cg_precond of this iteration) -> flags[0]; separate tiny kernel so that no
 // CTA of k_cg_precond can observe the flag it is about to set.
 __global__ void k_cg_latch(int* flags) {
+  pdl_sync();
   if (flags[2]) flags[0] = 1;
 }
 
@@ -208,6 +214,7 @@ __global__ void k_cg_latch(int* flags) {
 __global__ void __launch_bounds__(256)
 k_cg_dir(const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ rzpart,
          int npart, double* __restrict__ scal, const int* __restrict__ flags, int64_t D, int it) {
+  pdl_sync();
   if (flags[0]) return;
   __shared__ double red[32];
   const double rho = reduce_parts(rzpart, npart, 2, red);
@@ -224,6 +231,7 @@ k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __rest
             const double* __restrict__ q, const double* __restrict__ pqpart, int npart,
             double* __restrict__ rrpart, const double* __restrict__ scal, int* __restrict__ flags,
             int64_t D, int it) {
+  pdl_sync();
   if (flags[0]) return;
   __shared__ double red[32];
   const double pq = reduce_parts(pqpart, npart, 2, red);
@@ -246,6 +254,7 @@ k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __rest
 
 __global__ void k_axpby(double* __restrict__ out, const double* __restrict__ a, double alpha,
                         const double* __restrict__ b, double beta, int64_t n) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = alpha * (a ? a[i] : 0.0) + beta * (b ? b[i] : 0.0);
@@ -253,6 +262,7 @@ __global__ void k_axpby(double* __restrict__ out, const double* __restrict__ a, 
 
 // inverse of the local 2x2 blocks, (G,3) as (mm, mi, ii)
 __global__ void k_linv(const double* __restrict__ L, double* __restrict__ Linv, int G) {
+  pdl_sync();
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= G) return;
   const double l0 = L[(size_t)gi * 3], l1 = L[(size_t)gi * 3 + 1], l2 = L[(size_t)gi * 3 + 2];
@@ -301,6 +311,7 @@ __device__ __forceinline__ void schur_ksteps(double (&acc)[kRT][kRT][2],
 __global__ void __launch_bounds__(256)
 k_schur(const double* __restrict__ B, const double* __restrict__ Linv, double* __restrict__ part,
         int Dg, int G, int R, int n_jobs, int n_chunk) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int job = wg % n_jobs, chunk = wg / n_jobs;
@@ -366,6 +377,7 @@ k_schur(const double* __restrict__ B, const double* __restrict__ Linv, double* _
 __global__ void __launch_bounds__(256)
 k_schur_finish(const double* __restrict__ part, const double* __restrict__ A,
                double* __restrict__ S, int Dg, int R, int n_jobs, int n_chunk, int include_A) {
+  pdl_sync();
   __shared__ double red[4][64];
   const int job = blockIdx.x / (kRT * kRT), t = blockIdx.x % (kRT * kRT);
   int ri = 0, rem = job;
@@ -397,6 +409,7 @@ k_schur_finish(const double* __restrict__ part, const double* __restrict__ A,
 // No pivoting is needed for SPD input; a non-positive pivot aborts with info = its index + 1.
 __global__ void __launch_bounds__(1024)
 k_spd_inverse(double* __restrict__ S, int n, int* __restrict__ info, int use_smem) {
+  pdl_sync();
   extern __shared__ double sm[];
   double* row = sm;        // n   scaled pivot row
   double* col = sm + n;    // n   pivot column
@@ -440,6 +453,7 @@ k_spd_inverse(double* __restrict__ S, int n, int* __restrict__ info, int use_sme
 __global__ void __launch_bounds__(256)
 k_solve_reduce(const double* __restrict__ B, const double* __restrict__ Linv,
                const double* __restrict__ b, double* __restrict__ part, int Dg, int G) {
+  pdl_sync();
   extern __shared__ double acc[];  // 8 * Dg
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < 8 * Dg; c += blockDim.x) acc[c] = 0.0;
@@ -465,6 +479,7 @@ k_solve_reduce(const double* __restrict__ B, const double* __restrict__ Linv,
 __global__ void __launch_bounds__(256)
 k_solve_reduce_finish(const double* __restrict__ part, int npart, const double* __restrict__ b,
                       double* __restrict__ rhs, int Dg, int include_bg) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= Dg) return;
@@ -478,6 +493,7 @@ k_solve_reduce_finish(const double* __restrict__ part, int npart, const double* 
 __global__ void __launch_bounds__(256)
 k_solve_global(const double* __restrict__ Sinv, const double* __restrict__ rhs,
                double* __restrict__ x, int Dg) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= Dg) return;
@@ -492,6 +508,7 @@ k_solve_global(const double* __restrict__ Sinv, const double* __restrict__ rhs,
 __global__ void __launch_bounds__(256)
 k_solve_local(const double* __restrict__ B, const double* __restrict__ Linv,
               const double* __restrict__ b, double* __restrict__ x, int Dg, int G) {
+  pdl_sync();
   extern __shared__ double xg[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < Dg; c += blockDim.x) xg[c] = x[c];
@@ -520,6 +537,7 @@ k_solve_local(const double* __restrict__ B, const double* __restrict__ Linv,
 __global__ void __launch_bounds__(256)
 k_local_cov(const double* __restrict__ B, const double* __restrict__ Linv,
             const double* __restrict__ Sinv, double* __restrict__ cov, int Dg, int G) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int gi = blockIdx.x * 8 + warp; gi < G; gi += gridDim.x * 8) {
     const double* b0 = B + (size_t)gi * 2 * Dg;
@@ -564,7 +582,7 @@ static int require_hess(lrvb_glmm* h, const char* who) {
 
 static int prepare_linv(lrvb_glmm* h, cudaStream_t st) {
   if (h->G > 0) {
-    k_linv<<<cdiv(h->G, 256), 256, 0, st>>>(h->L, h->Linv, h->G);
+    LRVB_CUDA(launch_pdl(k_linv, dim3(cdiv(h->G, 256)), dim3(256), 0, st, h->L, h->Linv, h->G));
     LRVB_CHECK_LAUNCH();
   }
   return LRVB_OK;
@@ -607,20 +625,20 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   LRVB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
   if (precond) LRVB_TRY(prepare_linv(h, st));
   // ||b||, x, r
-  k_dot<<<vgrid, 256, 0, st>>>(b_dev, b_dev, nullptr, nullptr, D, pqpart, nullptr);
+  LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, b_dev, b_dev, nullptr, nullptr, D, pqpart, nullptr));
   LRVB_CHECK_LAUNCH();
-  k_cg_init<<<1, 256, 0, st>>>(pqpart, vgrid, rtol, h->scal, flags);
+  LRVB_CUDA(launch_pdl(k_cg_init, dim3(1), dim3(256), 0, st, pqpart, vgrid, rtol, h->scal, flags));
   LRVB_CHECK_LAUNCH();
   if (x0_dev) {
     if (x0_dev != x) LRVB_CUDA(cudaMemcpyAsync(x, x0_dev, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
     LRVB_TRY(launch_hvp(h, x, q, 1, nullptr, st));
-    k_axpby<<<vgrid, 256, 0, st>>>(r, b_dev, 1.0, q, -1.0, D);
+    LRVB_CUDA(launch_pdl(k_axpby, dim3(vgrid), dim3(256), 0, st, r, b_dev, 1.0, q, -1.0, D));
   } else {
     LRVB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * D, st));
-    k_axpby<<<vgrid, 256, 0, st>>>(r, b_dev, 1.0, nullptr, 0.0, D);
+    LRVB_CUDA(launch_pdl(k_axpby, dim3(vgrid), dim3(256), 0, st, r, b_dev, 1.0, nullptr, 0.0, D));
   }
   LRVB_CHECK_LAUNCH();
-  k_dot<<<vgrid, 256, 0, st>>>(r, r, nullptr, nullptr, D, rrpart, nullptr);
+  LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, r, r, nullptr, nullptr, D, rrpart, nullptr));
   LRVB_CHECK_LAUNCH();
 
   int hflags[4] = {0, 0, 0, 0};
@@ -629,13 +647,13 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   while (it < maxiter) {
     const int end = (it + batch < maxiter) ? it + batch : maxiter;
     for (; it < end; ++it) {
-      k_cg_precond<<<vgrid, 256, 0, st>>>(r, z, h->A, h->Linv, rrpart, vgrid, rzpart, h->scal, flags,
-                                          Dg, G, precond);
-      k_cg_latch<<<1, 1, 0, st>>>(flags);
-      k_cg_dir<<<vgrid, 256, 0, st>>>(z, p, rzpart, vgrid, h->scal, flags, D, it);
+      LRVB_CUDA(launch_pdl(k_cg_precond, dim3(vgrid), dim3(256), 0, st, r, z, h->A, h->Linv, rrpart, vgrid, rzpart, h->scal, flags,
+                                          Dg, G, precond));
+      LRVB_CUDA(launch_pdl(k_cg_latch, dim3(1), dim3(1), 0, st, flags));
+      LRVB_CUDA(launch_pdl(k_cg_dir, dim3(vgrid), dim3(256), 0, st, z, p, rzpart, vgrid, h->scal, flags, D, it));
       LRVB_TRY(launch_hvp(h, p, q, 1, flags, st));
-      k_dot<<<vgrid, 256, 0, st>>>(p, q, nullptr, nullptr, D, pqpart, flags);
-      k_cg_update<<<vgrid, 256, 0, st>>>(x, r, p, q, pqpart, vgrid, rrpart, h->scal, flags, D, it);
+      LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, p, q, nullptr, nullptr, D, pqpart, flags));
+      LRVB_CUDA(launch_pdl(k_cg_update, dim3(vgrid), dim3(256), 0, st, x, r, p, q, pqpart, vgrid, rrpart, h->scal, flags, D, it));
       g_launches += 4;  // precond, latch, dir, dot share the check below
       LRVB_CHECK_LAUNCH();
     }
@@ -674,11 +692,11 @@ int lrvb_glmm_schur(lrvb_glmm* h, double* S_dev, int32_t include_A, void* stream
     LRVB_CUDA(cudaMalloc((void**)&h->schurpart, sizeof(double) * need));
     h->schur_grid = n_chunk;
   }
-  k_schur<<<cdiv((int64_t)n_jobs * n_chunk, 8), 256, 0, st>>>(h->B, h->Linv, h->schurpart, Dg, G, R,
-                                                              n_jobs, n_chunk);
+  LRVB_CUDA(launch_pdl(k_schur, dim3(cdiv((int64_t)n_jobs * n_chunk, 8)), dim3(256), 0, st, h->B, h->Linv, h->schurpart, Dg, G, R,
+                                                              n_jobs, n_chunk));
   LRVB_CHECK_LAUNCH();
-  k_schur_finish<<<n_jobs * kRT * kRT, 256, 0, st>>>(h->schurpart, h->A, S_dev, Dg, R, n_jobs,
-                                                     n_chunk, include_A);
+  LRVB_CUDA(launch_pdl(k_schur_finish, dim3(n_jobs * kRT * kRT), dim3(256), 0, st, h->schurpart, h->A, S_dev, Dg, R, n_jobs,
+                                                     n_chunk, include_A));
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -696,7 +714,7 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
     smem = sizeof(double) * 2 * (size_t)n;
   }
   cudaFuncSetAttribute(k_spd_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_spd_inverse<<<1, 1024, smem, st>>>(S_dev, n, dinfo, use_smem);
+  LRVB_CUDA(launch_pdl(k_spd_inverse, dim3(1), dim3(1024), smem, st, S_dev, n, dinfo, use_smem));
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(info_host, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -717,10 +735,10 @@ int lrvb_glmm_solve_reduce_rhs(lrvb_glmm* h, const double* b_dev, int32_t nrhs,
   LRVB_TRY(prepare_linv(h, st));
   for (int j = 0; j < nrhs; ++j) {
     const double* b = b_dev + (size_t)j * h->D;
-    k_solve_reduce<<<h->hvp_grid, 256, sizeof(double) * 8 * (size_t)Dg, st>>>(h->B, h->Linv, b,
-                                                                              h->hvppart, Dg, G);
-    k_solve_reduce_finish<<<cdiv(Dg, 8), 256, 0, st>>>(h->hvppart, h->hvp_grid, b,
-                                                       rhs_g_dev + (size_t)j * Dg, Dg, include_bg);
+    LRVB_CUDA(launch_pdl(k_solve_reduce, dim3(h->hvp_grid), dim3(256), sizeof(double) * 8 * (size_t)Dg, st, h->B, h->Linv, b,
+                                                                              h->hvppart, Dg, G));
+    LRVB_CUDA(launch_pdl(k_solve_reduce_finish, dim3(cdiv(Dg, 8)), dim3(256), 0, st, h->hvppart, h->hvp_grid, b,
+                                                       rhs_g_dev + (size_t)j * Dg, Dg, include_bg));
     LRVB_CHECK_LAUNCH();
   }
   return LRVB_OK;
@@ -735,10 +753,10 @@ int lrvb_glmm_solve_finish(lrvb_glmm* h, const double* Sinv_dev, const double* r
   const int Dg = h->Dg, G = h->G;
   for (int j = 0; j < nrhs; ++j) {
     double* x = x_dev + (size_t)j * h->D;
-    k_solve_global<<<cdiv(Dg, 8), 256, 0, st>>>(Sinv_dev, rhs_g_dev + (size_t)j * Dg, x, Dg);
+    LRVB_CUDA(launch_pdl(k_solve_global, dim3(cdiv(Dg, 8)), dim3(256), 0, st, Sinv_dev, rhs_g_dev + (size_t)j * Dg, x, Dg));
     if (G > 0)
-      k_solve_local<<<h->hvp_grid, 256, sizeof(double) * (size_t)Dg, st>>>(
-          h->B, h->Linv, b_dev + (size_t)j * h->D, x, Dg, G);
+      LRVB_CUDA(launch_pdl(k_solve_local, dim3(h->hvp_grid), dim3(256), sizeof(double) * (size_t)Dg, st, 
+          h->B, h->Linv, b_dev + (size_t)j * h->D, x, Dg, G));
     LRVB_CHECK_LAUNCH();
   }
   return LRVB_OK;
@@ -752,7 +770,7 @@ int lrvb_glmm_local_cov(lrvb_glmm* h, const double* Sinv_dev, double* cov_dev, v
   if (h->G > 0) {
     int grid = cdiv(h->G, 8);
     if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-    k_local_cov<<<grid, 256, 0, st>>>(h->B, h->Linv, Sinv_dev, cov_dev, h->Dg, h->G);
+    LRVB_CUDA(launch_pdl(k_local_cov, dim3(grid), dim3(256), 0, st, h->B, h->Linv, Sinv_dev, cov_dev, h->Dg, h->G));
     LRVB_CHECK_LAUNCH();
   }
   return LRVB_OK;
