@@ -92,7 +92,7 @@ int ensure_solver_scratch(lrvb_glmm* h) {
   if (h->cgbuf) return LRVB_OK;
   const int Dg = h->Dg, G = h->G;
   h->hvp_grid = cdiv(G, 8 * 4);
-  if (h->hvp_grid > 2 * kNumSMs) h->hvp_grid = 2 * kNumSMs;
+  if (h->hvp_grid > 8 * kNumSMs) h->hvp_grid = 8 * kNumSMs;   // latency-bound streaming: 64 warps per SM
   if (h->hvp_grid < 1) h->hvp_grid = 1;
   h->dot_grid = cdiv(h->D, 256 * 8);
   if (h->dot_grid > 2 * kNumSMs) h->dot_grid = 2 * kNumSMs;
