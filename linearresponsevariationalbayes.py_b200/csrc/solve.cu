@@ -414,32 +414,36 @@ k_spd_inverse(double* __restrict__ S, int n, int* __restrict__ info, int use_sme
   double* row = sm;        // n   scaled pivot row
   double* col = sm + n;    // n   pivot column
   double* M = use_smem ? sm + 2 * n : S;
-  __shared__ int bad;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) bad = 0;
   if (use_smem)
     for (int i = tid; i < n * n; i += nt) M[i] = S[i];
   __syncthreads();
+  // thread -> (row stripe i0 + k TI, column lane jj): no integer division in the sweep, the pivot
+  // column entry of a row stays in a register; every thread sees the same pivot, so the
+  // "not positive definite" exit is uniform and needs no shared flag (two barriers per pivot)
+  const int TJ = 8, TI = nt / TJ;
+  const int i0 = tid / TJ, jj = tid - i0 * TJ;
+  int bad = 0;
   for (int k = 0; k < n; ++k) {
     const double d = M[(size_t)k * n + k];
     if (!(d > 0.0)) {
-      if (tid == 0) bad = k + 1;
+      bad = k + 1;
+      break;
     }
-    __syncthreads();
-    if (bad) break;
     const double pinv = 1.0 / d;
     for (int j = tid; j < n; j += nt) {
       row[j] = M[(size_t)k * n + j] * pinv;
       col[j] = M[(size_t)j * n + k];
     }
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += nt) {
-      const int i = idx / n, j = idx - i * n;
-      double v;
-      if (i == k) v = (j == k) ? pinv : row[j];
-      else if (j == k) v = -col[i] * pinv;
-      else v = M[idx] - col[i] * row[j];
-      M[idx] = v;
+    for (int i = i0; i < n; i += TI) {
+      double* mi = M + (size_t)i * n;
+      if (i == k) {
+        for (int j = jj; j < n; j += TJ) mi[j] = (j == k) ? pinv : row[j];
+      } else {
+        const double ci = col[i];
+        for (int j = jj; j < n; j += TJ) mi[j] = (j == k) ? -ci * pinv : fma(-ci, row[j], mi[j]);
+      }
     }
     __syncthreads();
   }
@@ -705,8 +709,8 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
   LRVB_REQUIRE(S_dev && info_host, "lrvb_spd_inverse: NULL argument");
   LRVB_REQUIRE(n >= 1 && n <= 4 + 2 * kMaxK, "lrvb_spd_inverse: n = %d out of range", n);
   cudaStream_t st = (cudaStream_t)stream;
-  int* dinfo = nullptr;
-  LRVB_CUDA(cudaMalloc((void**)&dinfo, sizeof(int)));
+  static int* dinfo = nullptr;   // one device word per process (no malloc / free per call)
+  if (!dinfo) LRVB_CUDA(cudaMalloc((void**)&dinfo, sizeof(int)));
   size_t smem = sizeof(double) * (2 * (size_t)n + (size_t)n * n);
   int use_smem = 1;
   if (smem > 200 * 1024) {
@@ -718,7 +722,6 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(info_host, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(dinfo);
   if (e != cudaSuccess) {
     set_error("lrvb_spd_inverse failed: %s", cudaGetErrorString(e));
     return LRVB_ECUDA;
