@@ -210,6 +210,8 @@ def run_ours(args, wl):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
     if args.gpus != world and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
@@ -265,6 +267,9 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+        flush.zero_()
+        csr = device_step()                 # the first collective after a barrier pays a re-sync: untimed
+        torch.cuda.synchronize()
     launches0 = lib.lrvb_launch_count()
     step_ms, gram_ms, obs_ms, eval_ms = [], [], [], []
     import ctypes
