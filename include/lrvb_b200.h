@@ -105,6 +105,11 @@ int lrvb_glmm_dims(const lrvb_glmm* h, int64_t* D, int32_t* Dg);
  * local block as (mm, mi, ii)) for the calls below. */
 int lrvb_glmm_eval(lrvb_glmm* h, const double* free_dev, int32_t order, double* out_global_dev,
                    double* grad_local_dev, void* stream);
+/* The handle's own result buffers (borrowed, fixed for the handle's lifetime): out_global
+ * [KL, grad_g (Dg), A (Dg*Dg)] and grad_local (2G).  lrvb_glmm_eval with NULL output pointers
+ * writes there and nowhere else (no device-to-device copy at the end of an evaluation); a sharded
+ * job all-reduces out_global in place, which also updates the cached global block A. */
+int lrvb_glmm_result_buffers(lrvb_glmm* h, double** out_global_dev, double** grad_local_dev);
 /* Device pointers of the cached blocks (borrowed; valid until the next eval / destroy). */
 int lrvb_glmm_blocks(lrvb_glmm* h, double** A_dev, double** B_dev, double** L_dev);
 /* Overwrite the cached global block (after the all-reduce of out_global in a sharded job). */

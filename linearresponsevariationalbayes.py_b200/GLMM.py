@@ -196,9 +196,11 @@ class LogisticGLMM(object):
         self._h = h
         self._lib = lib
         dev = self.X.device
-        self._out_global = torch.zeros(1 + self.Dg + self.Dg * self.Dg, dtype=torch.float64,
-                                       device=dev)
-        self._grad_local = torch.zeros(2 * self.G, dtype=torch.float64, device=dev)
+        # views of the handle's own result buffers: an evaluation writes there directly
+        og, gl = ctypes.c_void_p(), ctypes.c_void_p()
+        nat.check(lib.lrvb_glmm_result_buffers(h, ctypes.byref(og), ctypes.byref(gl)))
+        self._out_global = _view(og.value, (1 + self.Dg + self.Dg * self.Dg,), self)
+        self._grad_local = _view(gl.value, (2 * self.G,), self)
         self._x_dev = torch.zeros(self.D, dtype=torch.float64, device=dev)
         self._x_pin = torch.zeros(self.D, dtype=torch.float64).pin_memory()
         self._x_event = None
@@ -282,8 +284,7 @@ class LogisticGLMM(object):
             nat.check(self._lib.lrvb_glmm_set_coords(self._h, 1 if coords == "vector" else 0))
             self._coords = coords
         self._stage_x(x)
-        nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(self._x_dev), int(order),
-                                           nat.ptr(self._out_global), nat.ptr(self._grad_local),
+        nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(self._x_dev), int(order), None, None,
                                            nat.stream_ptr()))
         self._cache = dict(
             x=(x.detach().reshape(-1).clone() if is_torch(x)

@@ -42,6 +42,7 @@ SIGNATURES = {
     "lrvb_glmm_eval": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
     "lrvb_glmm_blocks": (c_int32, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "lrvb_glmm_set_global_block": (c_int32, [_P, _P, _P]),
+    "lrvb_glmm_result_buffers": (c_int32, [_P, POINTER(c_void_p), POINTER(c_void_p)]),
     "lrvb_glmm_obs_weights": (c_int32, [_P, POINTER(c_void_p), POINTER(c_int64)]),
     "lrvb_glmm_weight_cross_matvec": (c_int32, [_P, _P, _P, _P]),
     "lrvb_glmm_weight_cross_rmatvec": (c_int32, [_P, _P, _P, _P]),

@@ -290,6 +290,13 @@ int lrvb_glmm_eval(lrvb_glmm* h, const double* free_dev, int32_t order, double* 
   return launch_eval(h, free_dev, order, out_global_dev, grad_local_dev, (cudaStream_t)stream);
 }
 
+int lrvb_glmm_result_buffers(lrvb_glmm* h, double** out_global_dev, double** grad_local_dev) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_result_buffers: NULL handle");
+  if (out_global_dev) *out_global_dev = h->outg;
+  if (grad_local_dev) *grad_local_dev = h->gradl;
+  return LRVB_OK;
+}
+
 int lrvb_glmm_blocks(lrvb_glmm* h, double** A_dev, double** B_dev, double** L_dev) {
   LRVB_REQUIRE(h != nullptr, "lrvb_glmm_blocks: NULL handle");
   if (!h->hess_valid) {

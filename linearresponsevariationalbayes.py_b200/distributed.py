@@ -196,9 +196,8 @@ class ShardedLogisticGLMM(object):
         Dg = self.Dg
         n = 1 + (Dg if order >= 1 else 0) + (Dg * Dg if order >= 2 else 0)
         buf = self.local._out_global
-        self._allreduce(buf[:n])            # NCCL, on the compute stream, behind the eval
-        if order >= 2:
-            self.local.set_global_block(buf[1 + Dg:])
+        self._allreduce(buf[:n])            # NCCL, on the compute stream, behind the eval; `buf` is the
+        #                                     handle's own buffer, so the cached global block A is reduced too
         self._sinv = None
         # the cache key stays where the point lives: a device clone for tensors (no host sync)
         self._cache = dict(

@@ -41,15 +41,20 @@ class OracleLocal(object):
             grad = grad.copy()
             grad[:self.Dg] -= grade
             blk = dict(A=blk["A"] - blke["A"], B=blk["B"], L=blk["L"])
-        self.blk = {k: v.copy() for k, v in blk.items()}
+        self._blk = {k: v.copy() for k, v in blk.items() if k != "A"}
         Dg = self.Dg
         self._out_global[0] = kl
         self._out_global[1:1 + Dg] = torch.from_numpy(grad[:Dg])
         self._out_global[1 + Dg:] = torch.from_numpy(blk["A"].reshape(-1))
         self._grad_local[:] = torch.from_numpy(grad[Dg:])
 
-    def set_global_block(self, A):
-        self.blk["A"] = A.numpy().reshape(self.Dg, self.Dg).copy()
+    @property
+    def blk(self):
+        """B, L of the last evaluation and the LIVE global block: like the device model, A is the
+        tail of ``_out_global``, so an in-place all-reduce of that buffer updates it."""
+        d = dict(self._blk)
+        d["A"] = self._out_global[1 + self.Dg:].numpy().reshape(self.Dg, self.Dg).copy()
+        return d
 
     def blocks(self):
         return (torch.from_numpy(self.blk["A"]), torch.from_numpy(self.blk["B"]),
