@@ -64,6 +64,17 @@ struct GHSumsF {
 //   y = 1/((1+e)(2+e))   (MUFU seed + 3 Newton steps),  r = y (2+e),  u = e/(2+e) = e y (1+e),
 //   log1p(e) = 2 atanh(u) = 2 u P(u^2)   (minimax degree 10 on u^2 <= 1/9, error 1.3e-18).
 // Verified against mpmath on [-630, 0]: 2.2e-16 (exp) and 4.9e-16 (log1p o exp) max relative error.
+// polynomial coefficients in the constant bank: DFMA takes them as c[bank][offset] operands, which
+// saves the two moves per 64-bit immediate the compiler would otherwise issue for every use
+__constant__ double kExpC[10] = {0x1.af683d6885e31p-26, 0x1.28b8302ee0724p-22, 0x1.71ddf2a82093ep-19,
+                                 0x1.a0198d1fda4aap-16, 0x1.a01a01b251e85p-13, 0x1.6c16c189b379fp-10,
+                                 0x1.111111110ef94p-7,  0x1.555555554e879p-5,  0x1.555555555555bp-3,
+                                 0x1.0000000000012p-1};
+__constant__ double kAtanhC[10] = {0x1.5d1081172f887p-4, 0x1.54f8c703ce149p-5, 0x1.f00852a5c69fap-5,
+                                   0x1.106443d797a85p-4, 0x1.3b1e2bc8a12dep-4, 0x1.745caf74cbe5ep-4,
+                                   0x1.c71c7445b2127p-4, 0x1.249249201beacp-3, 0x1.99999999a1c4fp-3,
+                                   0x1.5555555555527p-2};
+
 __device__ __forceinline__ double exp_nonpos(double x) {
   x = fmax(x, -708.0);                                   // below: e < 1e-307, contributes nothing
   const double magic = 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-int trick
@@ -72,16 +83,9 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   nd -= magic;
   double f = fma(nd, -6.93147180369123816490e-01, x);    // ln2 hi / lo (fdlibm split)
   f = fma(nd, -1.90821492927058770002e-10, f);
-  double p = 0x1.af683d6885e31p-26;
-  p = fma(p, f, 0x1.28b8302ee0724p-22);
-  p = fma(p, f, 0x1.71ddf2a82093ep-19);
-  p = fma(p, f, 0x1.a0198d1fda4aap-16);
-  p = fma(p, f, 0x1.a01a01b251e85p-13);
-  p = fma(p, f, 0x1.6c16c189b379fp-10);
-  p = fma(p, f, 0x1.111111110ef94p-7);
-  p = fma(p, f, 0x1.555555554e879p-5);
-  p = fma(p, f, 0x1.555555555555bp-3);
-  p = fma(p, f, 0x1.0000000000012p-1);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 10; ++i) p = fma(p, f, kExpC[i]);
   p = fma(p, f, 1.0);
   p = fma(p, f, 1.0);
   return p * __hiloint2double((n + 1023) << 20, 0);      // n in [-1022, 0]
@@ -101,16 +105,9 @@ __device__ __forceinline__ void rcp_log1p_unit(double e, double& r, double& L) {
   r = y * b;
   const double u = e * (y * a);
   const double v = u * u;
-  double p = 0x1.5d1081172f887p-4;
-  p = fma(p, v, 0x1.54f8c703ce149p-5);
-  p = fma(p, v, 0x1.f00852a5c69fap-5);
-  p = fma(p, v, 0x1.106443d797a85p-4);
-  p = fma(p, v, 0x1.3b1e2bc8a12dep-4);
-  p = fma(p, v, 0x1.745caf74cbe5ep-4);
-  p = fma(p, v, 0x1.c71c7445b2127p-4);
-  p = fma(p, v, 0x1.249249201beacp-3);
-  p = fma(p, v, 0x1.99999999a1c4fp-3);
-  p = fma(p, v, 0x1.5555555555527p-2);
+  double p = kAtanhC[0];
+#pragma unroll
+  for (int i = 1; i < 10; ++i) p = fma(p, v, kAtanhC[i]);
   p = fma(p, v, 1.0);
   L = (u + u) * p;
 }
