@@ -210,8 +210,9 @@ def run_ours(args, wl):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout (one JSON line)
+        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so
+        # that stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     if args.gpus != world and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
