@@ -405,6 +405,71 @@ k_schur_finish(const double* __restrict__ part, const double* __restrict__ A,
   S[(size_t)q * Dg + p] = v;
 }
 
+// ---- in-place inverse of a small SPD matrix, n <= 128: register-resident Gauss-Jordan ----------
+// Thread (i, jj) = (tid / 8, tid % 8) keeps the entries j = jj, jj + 8, ... of row i in registers.
+// Per pivot k: the (unscaled) pivot row comes from a double-buffered shared row, the pivot-column
+// entry of a row from a shuffle inside the 8 lanes that hold the row; one block barrier per pivot.
+template <int NQ>   // NQ = ceil(n / 8) register entries per thread
+__global__ void __launch_bounds__(1024)
+k_spd_inverse_reg(double* __restrict__ S, int n, int* __restrict__ info) {
+  pdl_sync();
+  __shared__ double rowbuf[2][128];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = tid >> 3, jj = tid & 7;
+  double m[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int j = jj + 8 * q;
+    m[q] = (i < n && j < n) ? S[(size_t)i * n + j] : 0.0;
+  }
+  if (i == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (jj + 8 * q < n) rowbuf[0][jj + 8 * q] = m[q];
+  }
+  __syncthreads();
+  int bad = 0;
+#pragma unroll
+  for (int kq = 0; kq < NQ; ++kq) {
+    for (int kr = 0; kr < 8; ++kr) {
+      const int k = 8 * kq + kr;
+      if (k >= n || bad) break;
+      const double* row = rowbuf[k & 1];
+      const double d = row[k];
+      if (!(d > 0.0)) {      // the same value in every thread: uniform exit
+        bad = k + 1;
+        break;
+      }
+      const double pinv = 1.0 / d;
+      const double ci = __shfl_sync(0xffffffffu, m[kq], (lane & ~7) | kr);   // M[i][k]
+      const bool piv = (i == k);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int j = jj + 8 * q;
+        if (j < n) {
+          const double rj = row[j] * pinv;
+          double v;
+          if (j == k) v = piv ? pinv : -ci * pinv;
+          else v = piv ? rj : fma(-ci, rj, m[q]);
+          m[q] = v;
+        }
+      }
+      if (i == k + 1) {      // the next pivot row, already updated
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (jj + 8 * q < n) rowbuf[(k + 1) & 1][jj + 8 * q] = m[q];
+      }
+      __syncthreads();
+    }
+  }
+  if (!bad && i < n) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (jj + 8 * q < n) S[(size_t)i * n + jj + 8 * q] = m[q];
+  }
+  if (tid == 0) *info = bad;
+}
+
 // ---- in-place inverse of a small SPD matrix (Gauss-Jordan sweeps, one CTA) ---------------------
 // No pivoting is needed for SPD input; a non-positive pivot aborts with info = its index + 1.
 __global__ void __launch_bounds__(1024)
@@ -717,8 +782,22 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
     use_smem = 0;
     smem = sizeof(double) * 2 * (size_t)n;
   }
-  cudaFuncSetAttribute(k_spd_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  LRVB_CUDA(launch_pdl(k_spd_inverse, dim3(1), dim3(1024), smem, st, S_dev, n, dinfo, use_smem));
+  if (n <= 128) {
+    const int threads = 8 * ((n + 3) / 4 * 4);     // whole warps: 4 rows of 8 lanes each
+    const int nq = (n + 7) / 8;
+    cudaError_t le;
+#define LRVB_SPD(Q) le = launch_pdl(k_spd_inverse_reg<Q>, dim3(1), dim3(threads), 0, st, S_dev, (int)n, dinfo)
+    if (nq <= 2) LRVB_SPD(2);
+    else if (nq <= 4) LRVB_SPD(4);
+    else if (nq <= 6) LRVB_SPD(6);
+    else if (nq <= 8) LRVB_SPD(8);
+    else LRVB_SPD(16);
+#undef LRVB_SPD
+    LRVB_CUDA(le);
+  } else {
+    cudaFuncSetAttribute(k_spd_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LRVB_CUDA(launch_pdl(k_spd_inverse, dim3(1), dim3(1024), smem, st, S_dev, n, dinfo, use_smem));
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(info_host, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
