@@ -209,10 +209,13 @@ def run_ours(args, wl):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout must carry the one JSON line only, but native libraries write there too (NCCL prints its
+    # version banner with printf): point fd 1 at stderr for the whole run and keep the real stdout
+    # for the result line
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so
-        # that stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     if args.gpus != world and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
@@ -441,10 +444,14 @@ def run_ours(args, wl):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(result_fd, 1)
+    os.close(result_fd)
 
 
 def _hbm_peak():

@@ -89,6 +89,11 @@ int lrvb_glmm_last_timing(lrvb_glmm* h, float* ms3_host);
  * 1 = constrained "vector" coordinates (Objective.fun_vector*, :127-181).  Invalidates the
  * cached Hessian. */
 int lrvb_glmm_set_coords(lrvb_glmm* h, int32_t vector_coords);
+/* Observation-sharded jobs: this handle owns groups [g0, g0 + G) of a job with
+ * G_total groups.  Afterwards lrvb_glmm_eval's free_dev is the job's FULL flat vector
+ * (4 + 2K + 2 G_total entries, layout above) and the handle reads its own entries out of it;
+ * every output stays in the handle's local layout.  G_total = 0 restores the default. */
+int lrvb_glmm_set_shard(lrvb_glmm* h, int64_t g0, int64_t G_total);
 /* D = 4 + 2K + 2G, Dg = 4 + 2K. */
 int lrvb_glmm_dims(const lrvb_glmm* h, int64_t* D, int32_t* Dg);
 
@@ -213,6 +218,29 @@ int lrvb_gh_logistic_term(const double* z_mean, const double* z_sd, int64_t M,
 /* Deterministic sum of a device vector into out_dev[0] (used to aggregate the terms above
  * the way the reference's np.sum does). */
 int lrvb_sum(const double* x_dev, int64_t M, double* out_dev, void* stream);
+
+/* ---- all-reduce of the replicated blocks over NVLink peer memory ---------------------------
+ * The reference has no distributed path (SURVEY.md 8e is new): an observation-sharded job sums
+ * [KL, grad_g, H_gg] (lrvb_glmm_eval's out_global), the global rows of an HVP, the Schur
+ * complement and CG's dot products over the ranks.  These messages are tens of KB, so the cost
+ * is latency: one kernel per rank pushes its block into a window of every peer (CUDA IPC, one
+ * process per GPU), waits for the peers' blocks and adds them in rank order -- bitwise identical
+ * on every rank.  csrc/p2p.cu.
+ *  create:   allocates this rank's window for messages of up to max_elems doubles (syncs);
+ *  export:   writes lrvb_p2p_handle_bytes() bytes the peers need to map the window
+ *            (exchanged by the host, e.g. torch.distributed.all_gather_object);
+ *  connect:  handles = world * lrvb_p2p_handle_bytes() bytes, rank-major; maps the peers;
+ *  allreduce_sum: in place on buf_dev (n <= max_elems), enqueued on `stream`; EVERY rank must
+ *            issue the same sequence of calls;
+ *  status:   0, or 1 + r when rank r did not arrive within ~2 s (syncs the stream). */
+typedef struct lrvb_p2p lrvb_p2p;
+int lrvb_p2p_create(lrvb_p2p** out, int32_t rank, int32_t world, int64_t max_elems);
+int lrvb_p2p_handle_bytes(void);
+int lrvb_p2p_export(lrvb_p2p* h, void* handle_out);
+int lrvb_p2p_connect(lrvb_p2p* h, const void* handles);
+int lrvb_p2p_allreduce_sum(lrvb_p2p* h, double* buf_dev, int64_t n, void* stream);
+int lrvb_p2p_status(lrvb_p2p* h, int32_t* status_out, void* stream);
+int lrvb_p2p_destroy(lrvb_p2p* h);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _native as nat
-from ._tensors import is_torch, to_device
+from ._tensors import PointKey, is_torch, to_device
 from .GammaParams import GammaParam
 from .NormalParams import UVNParam, UVNParamVector
 from .ParameterDictionary import ModelParamsDict
@@ -205,6 +205,7 @@ class LogisticGLMM(object):
         self._x_pin = torch.zeros(self.D, dtype=torch.float64).pin_memory()
         self._x_event = None
         self._cache = dict(x=None, order=-1, coords=None)
+        self._D_in = self.D
         self._coords = "free"
         self.device = dev
 
@@ -237,41 +238,47 @@ class LogisticGLMM(object):
             self._h = None
 
     # ---- evaluation -------------------------------------------------------------------------
+    def set_shard(self, g0, G_total):
+        """This model is the shard [g0, g0 + G) of a job with ``G_total`` groups: ``evaluate``
+        then takes the job's FULL flat vector and the device gathers its own entries
+        (lrvb_glmm_set_shard); results stay in the local layout.  ``G_total = 0`` undoes it."""
+        nat.check(self._lib.lrvb_glmm_set_shard(self._h, int(g0), int(G_total)))
+        self._D_in = self.D if not G_total else self.Dg + 2 * int(G_total)
+        if self._D_in != self._x_dev.numel():
+            torch = nat.require_cuda()
+            self._x_dev = torch.zeros(self._D_in, dtype=torch.float64, device=self.device)
+            self._x_pin = torch.zeros(self._D_in, dtype=torch.float64).pin_memory()
+        self.invalidate()
+
     def _stage_x(self, x):
-        """Evaluation point -> device tensor (pinned staging for host input)."""
+        """Evaluation point -> device tensor the kernels read: a contiguous fp64 CUDA tensor is
+        used where it is (kept alive until the next evaluation), anything else goes through the
+        staging buffer (pinned for host input)."""
         torch = nat.require_cuda()
         if is_torch(x):
-            if x.numel() != self.D:
+            if x.numel() != self._D_in:
                 raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
-                    self.glmm_par.name, self.D, x.numel()))
-            if x.is_cuda:
-                self._x_dev.copy_(x.reshape(-1))
-            else:
-                self._x_dev.copy_(x.reshape(-1))
-            return
+                    self.glmm_par.name, self._D_in, x.numel()))
+            xd = x.detach()
+            if xd.is_cuda and xd.dtype == torch.float64 and xd.is_contiguous() and xd.device == self.device:
+                return xd
+            self._x_dev.copy_(xd.reshape(-1))
+            return self._x_dev
         xa = np.asarray(x, dtype=np.float64).reshape(-1)
-        if xa.size != self.D:
+        if xa.size != self._D_in:
             raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
-                self.glmm_par.name, self.D, xa.size))
+                self.glmm_par.name, self._D_in, xa.size))
         if self._x_event is not None:
             self._x_event.synchronize()  # the previous async copy has left the pinned buffer
         self._x_pin.numpy()[:] = xa
         self._x_dev.copy_(self._x_pin, non_blocking=True)
         self._x_event = torch.cuda.Event()
         self._x_event.record()
+        return self._x_dev
 
     def _same_point(self, x, coords):
         c = self._cache
-        if c["x"] is None or c["coords"] != coords:
-            return False
-        if is_torch(x):
-            import torch
-            if not is_torch(c["x"]):
-                return False
-            return c["x"].shape == x.reshape(-1).shape and bool(torch.equal(c["x"], x.reshape(-1)))
-        if is_torch(c["x"]):
-            return False
-        return np.array_equal(c["x"], np.asarray(x, dtype=np.float64).reshape(-1))
+        return c["x"] is not None and c["coords"] == coords and c["x"].matches(x)
 
     def evaluate(self, x, order, coords="free", force=False):
         """Runs the fused evaluation of ``order`` (0 value, 1 +gradient, 2 +Hessian blocks) at
@@ -283,13 +290,10 @@ class LogisticGLMM(object):
         if coords != self._coords:
             nat.check(self._lib.lrvb_glmm_set_coords(self._h, 1 if coords == "vector" else 0))
             self._coords = coords
-        self._stage_x(x)
-        nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(self._x_dev), int(order), None, None,
+        xd = self._stage_x(x)
+        nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(xd), int(order), None, None,
                                            nat.stream_ptr()))
-        self._cache = dict(
-            x=(x.detach().reshape(-1).clone() if is_torch(x)
-               else np.array(x, dtype=np.float64).reshape(-1)),
-            order=int(order), coords=coords)
+        self._cache = dict(x=PointKey(x), order=int(order), coords=coords)
 
     def invalidate(self):
         self._cache = dict(x=None, order=-1, coords=None)

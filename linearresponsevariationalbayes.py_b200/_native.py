@@ -38,6 +38,7 @@ SIGNATURES = {
     "lrvb_glmm_set_timing": (c_int32, [_P, c_int32]),
     "lrvb_glmm_last_timing": (c_int32, [_P, POINTER(ctypes.c_float)]),
     "lrvb_glmm_set_coords": (c_int32, [_P, c_int32]),
+    "lrvb_glmm_set_shard": (c_int32, [_P, c_int64, c_int64]),
     "lrvb_glmm_dims": (c_int32, [_P, POINTER(c_int64), POINTER(c_int32)]),
     "lrvb_glmm_eval": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
     "lrvb_glmm_blocks": (c_int32, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
@@ -67,6 +68,13 @@ SIGNATURES = {
     "lrvb_gh_logistic_term": (c_int32, [_P, _P, c_int64, POINTER(c_double), POINTER(c_double),
                                         c_int32, _P, _P]),
     "lrvb_sum": (c_int32, [_P, c_int64, _P, _P]),
+    "lrvb_p2p_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int64]),
+    "lrvb_p2p_handle_bytes": (c_int32, []),
+    "lrvb_p2p_export": (c_int32, [_P, _P]),
+    "lrvb_p2p_connect": (c_int32, [_P, _P]),
+    "lrvb_p2p_allreduce_sum": (c_int32, [_P, _P, c_int64, _P]),
+    "lrvb_p2p_status": (c_int32, [_P, POINTER(c_int32), _P]),
+    "lrvb_p2p_destroy": (c_int32, [_P]),
 }
 
 _lib = None

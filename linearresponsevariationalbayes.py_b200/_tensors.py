@@ -32,3 +32,32 @@ def like_input(t, *inputs):
     if out.ndim == 0:
         return float(out)
     return out
+
+
+class PointKey(object):
+    """Identity of an evaluation point for the "already evaluated here?" check of the models.
+
+    numpy input: a private copy, compared by value (host work only).  torch input: the tensor
+    itself (kept alive) with its storage address, shape, strides and torch's in-place version
+    counter -- comparing VALUES of device tensors would cost a kernel, a device-to-host read and
+    a stream synchronisation on every call.  A tensor that is modified in place through torch
+    bumps its version and is re-evaluated; an equal-valued copy is simply evaluated again."""
+
+    __slots__ = ("arr", "ref", "sig")
+
+    def __init__(self, x):
+        if is_torch(x):
+            self.arr, self.ref, self.sig = None, x, self._sig(x)
+        else:
+            self.arr, self.ref, self.sig = np.array(x, dtype=np.float64).reshape(-1), None, None
+
+    @staticmethod
+    def _sig(x):
+        return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x.device, x._version)
+
+    def matches(self, x):
+        if is_torch(x):
+            return self.ref is not None and self.sig == self._sig(x)
+        if self.arr is None:
+            return False
+        return np.array_equal(self.arr, np.asarray(x, dtype=np.float64).reshape(-1))

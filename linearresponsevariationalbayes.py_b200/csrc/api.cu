@@ -275,6 +275,17 @@ int lrvb_glmm_set_coords(lrvb_glmm* h, int32_t vector_coords) {
   return LRVB_OK;
 }
 
+int lrvb_glmm_set_shard(lrvb_glmm* h, int64_t g0, int64_t G_total) {
+  LRVB_REQUIRE(h != nullptr, "lrvb_glmm_set_shard: NULL handle");
+  LRVB_REQUIRE(G_total == 0 || (g0 >= 0 && g0 + h->G <= G_total),
+               "lrvb_glmm_set_shard: groups [%lld, %lld) are not inside [0, %lld)", (long long)g0,
+               (long long)(g0 + h->G), (long long)G_total);
+  h->shard_g0 = G_total > 0 ? g0 : 0;
+  h->shard_G = G_total;
+  h->point_valid = 0;
+  return LRVB_OK;
+}
+
 int lrvb_glmm_dims(const lrvb_glmm* h, int64_t* D, int32_t* Dg) {
   LRVB_REQUIRE(h != nullptr, "lrvb_glmm_dims: NULL handle");
   if (D) *D = h->D;

@@ -175,6 +175,7 @@ struct lrvb_glmm {
   int K = 0, G = 0, Q = 0, Dg = 0, KT = 0;  // KT = ceil(K/8) feature tiles
   int include_global = 1;
   int vecmode = 0;            // 1: evaluate in the constrained ("vector") parameterisation
+  int64_t shard_g0 = 0, shard_G = 0;   // shard_G > 0: eval reads the FULL layout of a job with shard_G groups
   const double *X = nullptr, *y = nullptr, *w = nullptr;
   const int32_t* g = nullptr;
   lrvb_glmm_prior prior;

@@ -23,8 +23,11 @@
 namespace lrvb {
 
 // ------------------------------------------------------------------------------------------
+// shard_G > 0: free_v is the full flat vector of a sharded job with shard_G groups of which this
+// handle owns [shard_g0, shard_g0 + G); the gather into the local layout happens here.
 __global__ void k_prep(const double* __restrict__ free_v, double* __restrict__ vec, int K, int G,
-                       lrvb_glmm_bounds bd, int vecmode, double* __restrict__ zero, int64_t nzero) {
+                       lrvb_glmm_bounds bd, int vecmode, double* __restrict__ zero, int64_t nzero,
+                       int64_t shard_g0, int64_t shard_G) {
   pdl_sync();
   const int64_t D = 4 + 2 * (int64_t)K + 2 * (int64_t)G;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,7 +35,9 @@ __global__ void k_prep(const double* __restrict__ free_v, double* __restrict__ v
   // which would cut the chain of programmatic launches
   for (int64_t j = i; j < nzero; j += (int64_t)gridDim.x * blockDim.x) zero[j] = 0.0;
   if (i >= D) return;
-  const double f = free_v[i];
+  int64_t si = i;
+  if (shard_G > 0 && i >= 4 + 2 * K) si = (i < 4 + 2 * K + G) ? i + shard_g0 : i - G + shard_G + shard_g0;
+  const double f = free_v[si];
   double lb = 0.0;
   bool con = true;
   if (i == 0) con = false;
@@ -596,7 +601,8 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[4], st));
   double* outp = out_global ? out_global : h->outg;
   LRVB_CUDA(launch_pdl(k_prep, dim3(cdiv(h->D, 256)), dim3(256), 0, st, free_dev, h->vec, K, G, h->bounds,
-                       h->vecmode, outp + 1 + Dg, (int64_t)(order >= 2 ? (int64_t)Dg * Dg : 0)));
+                       h->vecmode, outp + 1 + Dg, (int64_t)(order >= 2 ? (int64_t)Dg * Dg : 0), h->shard_g0,
+                       h->shard_G));
   LRVB_CHECK_LAUNCH();
 
   int n_obs_cta = 0;

@@ -22,7 +22,7 @@ results out, identical on every rank.
 """
 import numpy as np
 
-from ._tensors import is_torch
+from ._tensors import PointKey, is_torch
 
 
 def partition_groups(counts, world):
@@ -59,6 +59,78 @@ def local_index_map(Dg, g0, g1, G_total):
                            Dg + G_total + np.arange(g0, g1)]).astype(np.int64)
 
 
+class PeerAllReduce(object):
+    """Sum of small fp64 device buffers over the ranks through NVLink peer memory
+    (csrc/p2p.cu): one kernel per rank pushes its block into a window of every peer, waits for
+    theirs and adds them in rank order -- bitwise identical on all ranks, one NVLink traversal,
+    in-stream behind the producer (no NCCL stream hand-over).  Collective constructor: every rank
+    of ``process_group`` must call it.  ``PeerAllReduce.create`` returns None when the ranks are
+    not one-process-per-GPU on one box or a window cannot be mapped; callers then use NCCL."""
+
+    def __init__(self, handle, lib, max_elems, rank, world):
+        self._h, self._lib = handle, lib
+        self.max_elems, self.rank, self.world = int(max_elems), rank, world
+
+    @classmethod
+    def create(cls, max_elems, process_group=None):
+        import ctypes
+        import os
+        import socket
+        import torch
+        import torch.distributed as dist
+        from . import _native as nat
+        if os.environ.get("LRVB_P2P_ALLREDUCE", "1") == "0" or not torch.cuda.is_available():
+            return None
+        if dist.get_backend(process_group) != "nccl":
+            return None
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        if world < 2 or world > 16:
+            return None
+        lib = nat.load()
+        h = ctypes.c_void_p()
+        ok = lib.lrvb_p2p_create(ctypes.byref(h), rank, world, int(max_elems)) == 0
+        nbytes = lib.lrvb_p2p_handle_bytes()
+        blob = ctypes.create_string_buffer(nbytes)
+        ok = ok and lib.lrvb_p2p_export(h, blob) == 0
+        infos = [None] * world
+        dist.all_gather_object(infos, (socket.gethostname(), torch.cuda.current_device(), bool(ok),
+                                       bytes(blob.raw)), group=process_group)
+        same_box = len({i[0] for i in infos}) == 1 and len({i[1] for i in infos}) == world
+        ok = ok and same_box and all(i[2] for i in infos)
+        if ok:
+            ok = lib.lrvb_p2p_connect(h, b"".join(i[3] for i in infos)) == 0
+        oks = [None] * world
+        dist.all_gather_object(oks, bool(ok), group=process_group)   # also: every window is mapped
+        if not all(oks):
+            if h.value:
+                lib.lrvb_p2p_destroy(h)
+            return None
+        return cls(h, lib, max_elems, rank, world)
+
+    def fits(self, t):
+        import torch
+        return (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and t.numel() <= self.max_elems)
+
+    def all_reduce_(self, t):
+        """In-place sum over the ranks on torch's current stream."""
+        from . import _native as nat
+        nat.check(self._lib.lrvb_p2p_allreduce_sum(self._h, nat.ptr(t), t.numel(), nat.stream_ptr()))
+        return t
+
+    def status(self):
+        import ctypes
+        from . import _native as nat
+        s = ctypes.c_int32()
+        nat.check(self._lib.lrvb_p2p_status(self._h, ctypes.byref(s), nat.stream_ptr()))
+        return s.value
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.lrvb_p2p_destroy(self._h)
+        self._h = None
+
+
 class ShardedLogisticGLMM(object):
     _lrvb_device_model = True
 
@@ -92,6 +164,14 @@ class ShardedLogisticGLMM(object):
                                  beta_info=min_info, u_info=min_info)
         self._cache = dict(x=None, order=-1, coords=None)
         self._sinv = None
+        # small replicated blocks are summed through NVLink peer memory when the ranks are the GPUs
+        # of one box (collective decision, identical on every rank); otherwise NCCL / gloo
+        self._peer = None
+        self._full_input = hasattr(local, "set_shard")
+        if self._full_input:
+            local.set_shard(self.g0, self.G)
+        if getattr(local, "_h", None) is not None and getattr(self.device, "type", "") == "cuda":
+            self._peer = PeerAllReduce.create(max(1 + self.Dg + self.Dg * self.Dg, 4096), process_group)
 
     # ---- construction ----------------------------------------------------------------------
     @classmethod
@@ -136,6 +216,8 @@ class ShardedLogisticGLMM(object):
 
     # ---- helpers -----------------------------------------------------------------------------
     def _allreduce(self, t):
+        if self._peer is not None and self._peer.fits(t):
+            return self._peer.all_reduce_(t)
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
         return t
@@ -172,37 +254,28 @@ class ShardedLogisticGLMM(object):
 
     def _same_point(self, x, coords):
         c = self._cache
-        if c["x"] is None or c["coords"] != coords:
-            return False
-        if is_torch(x):
-            import torch
-            if not is_torch(c["x"]):
-                return False
-            xf = x.detach().reshape(-1).to(c["x"].device)
-            return c["x"].shape == xf.shape and bool(torch.equal(c["x"], xf))
-        if is_torch(c["x"]):
-            return False
-        return np.array_equal(c["x"], np.asarray(x, dtype=np.float64).reshape(-1))
+        return c["x"] is not None and c["coords"] == coords and c["x"].matches(x)
 
     # ---- the model interface used by Objective / ConjugateGradientSolver / LRVB --------------
     def evaluate(self, x, order, coords="free", force=False):
         if not force and self._cache["order"] >= order and self._same_point(x, coords):
             return
-        xd = self._dev(x)
-        if xd.numel() != self.D:
+        n_in = x.numel() if is_torch(x) else np.asarray(x).size
+        if n_in != self.D:
             raise ValueError("Wrong size for parameter {}.  Expected {}, got {}".format(
-                self.glmm_par.name, self.D, xd.numel()))
-        self.local.evaluate(self.to_local(xd), order, coords, force=True)
+                self.glmm_par.name, self.D, n_in))
+        if self._full_input:
+            # the shard's kernels read their entries out of the full vector: no gather kernel
+            self.local.evaluate(x, order, coords, force=True)
+        else:
+            self.local.evaluate(self.to_local(self._dev(x)), order, coords, force=True)
         Dg = self.Dg
         n = 1 + (Dg if order >= 1 else 0) + (Dg * Dg if order >= 2 else 0)
         buf = self.local._out_global
-        self._allreduce(buf[:n])            # NCCL, on the compute stream, behind the eval; `buf` is the
-        #                                     handle's own buffer, so the cached global block A is reduced too
+        self._allreduce(buf[:n])            # on the compute stream, behind the eval; `buf` is the handle's
+        #                                     own buffer, so the cached global block A is reduced too
         self._sinv = None
-        # the cache key stays where the point lives: a device clone for tensors (no host sync)
-        self._cache = dict(
-            x=(x.detach().reshape(-1).clone() if is_torch(x)
-               else np.array(x, dtype=np.float64).reshape(-1)), order=int(order), coords=coords)
+        self._cache = dict(x=PointKey(x), order=int(order), coords=coords)
 
     def kl_tensor(self):
         return self.local._out_global[0]

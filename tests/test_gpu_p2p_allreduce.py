@@ -1,0 +1,111 @@
+"""GPU (>= 2 devices): the NVLink peer-memory all-reduce (csrc/p2p.cu) against the exact sum, and
+the sharded GLMM -- one process per GPU over NCCL, replicated blocks summed through the peer
+windows -- against the oracle.  Skipped on a one-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import glmm_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import lrvb_b200 as vb
+        from lrvb_b200.distributed import PeerAllReduce, ShardedLogisticGLMM
+        res = {}
+        peer = PeerAllReduce.create(5000)
+        res["created"] = peer is not None
+        if peer is None:
+            out[rank] = res
+            return
+        # exact sums: integers (any order of addition gives the same bits), many epochs, ragged sizes
+        worst, same = 0.0, True
+        for it, n in enumerate([1, 2, 511, 512, 513, 1981, 4999, 5000, 7, 1981, 1981, 3000]):
+            gen = torch.Generator().manual_seed(100 + it)
+            parts = torch.randint(-1000, 1000, (world, n), generator=gen).double()
+            t = parts[rank].to(dev).contiguous()
+            peer.all_reduce_(t)
+            worst = max(worst, float((t.cpu() - parts.sum(0)).abs().max()))
+        # non-integers: identical bits on every rank (fixed rank order of the additions)
+        t = torch.randn(1981, generator=torch.Generator().manual_seed(7 + rank), dtype=torch.float64).to(dev)
+        ref = t.clone()
+        peer.all_reduce_(t)
+        dist.all_reduce(ref)
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        same = all(torch.equal(gathered[0], gr) for gr in gathered)
+        res["sum_err"] = worst
+        res["bitwise_same"] = bool(same)
+        res["vs_nccl"] = float((t - ref).abs().max() / ref.abs().max())
+        res["status"] = peer.status()
+        peer.close()
+
+        N, K, G, Q = 6000, 7, 41, 8
+        X, y, g = go.make_glmm_data(N, K, G, seed=41)
+        model = ShardedLogisticGLMM.from_full(X, y, g, G, num_gh_points=Q)
+        res["model_peer"] = model._peer is not None
+        obj = vb.Objective(model.glmm_par, model)
+        order = np.argsort(g, kind="stable")
+        gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+        oracle = go.GLMMOracle(X[order], y[order], g[order], gh_x, gh_w, G=G)
+        x = go.make_free(oracle.lay.D, 41)
+        res["kl"] = abs(obj.fun_free(x) - oracle.kl(x)) / abs(oracle.kl(x))
+        ge = oracle.kl_grad(x)
+        res["grad"] = np.abs(obj.fun_free_grad(x) - ge).max() / np.abs(ge).max()
+        H = obj.fun_free_hessian(x)
+        He = oracle.kl_hessian_csr(x)
+        res["pattern"] = float(not (np.array_equal(H.indptr, He.indptr)
+                                    and np.array_equal(H.indices, He.indices)))
+        res["hess"] = np.abs(H.data - He.data).max() / np.abs(He.data).max()
+        v = np.random.default_rng(42).standard_normal(x.size)
+        hve = oracle.kl_hvp(x, v)
+        res["hvp"] = np.abs(obj.fun_free_hvp(x, v) - hve).max() / np.abs(hve).max()
+        lr = vb.LinearResponseCovariances(obj, x)
+        Hinv = np.linalg.inv(He.toarray())
+        Dg = oracle.lay.Dg
+        res["cov_g"] = np.abs(lr.get_global_covariance() - Hinv[:Dg, :Dg]).max() / np.abs(Hinv).max()
+        res["status2"] = model._peer.status() if model._peer is not None else 0
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_allreduce_and_sharded_model_two_gpus():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        res = out[rank]
+        assert res["created"], "peer windows could not be mapped on a multi-GPU box"
+        assert res["sum_err"] == 0.0
+        assert res["bitwise_same"]
+        assert res["vs_nccl"] < 1e-14
+        assert res["status"] == 0 and res["status2"] == 0
+        assert res["model_peer"]
+        assert res["pattern"] == 0.0
+        for key in ("kl", "grad", "hess", "hvp"):
+            assert res[key] < 1e-9, (rank, key, res[key])
+        assert res["cov_g"] < 1e-8
