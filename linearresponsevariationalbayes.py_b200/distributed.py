@@ -109,8 +109,10 @@ class PeerAllReduce(object):
 
     def fits(self, t):
         import torch
+        # one-shot: every rank receives (world - 1) * n lines; beyond ~200k doubles in flight per
+        # rank NCCL's bandwidth-oriented algorithms win (profiles/r01_peer_allreduce_latency.txt)
         return (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
-                and t.numel() <= self.max_elems)
+                and t.numel() <= self.max_elems and t.numel() * (self.world - 1) <= 200000)
 
     def all_reduce_(self, t):
         """In-place sum over the ranks on torch's current stream."""

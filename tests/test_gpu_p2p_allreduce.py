@@ -91,8 +91,8 @@ def _worker(rank, world, port, out):
 
 @pytest.mark.timeout(600)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_peer_allreduce_and_sharded_model_two_gpus():
-    world = 2
+def test_peer_allreduce_and_sharded_model_all_gpus():
+    world = min(torch.cuda.device_count(), 8)     # every GPU of the box, one process each
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
