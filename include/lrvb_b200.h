@@ -219,6 +219,39 @@ int lrvb_gh_logistic_term(const double* z_mean, const double* z_sd, int64_t M,
  * the way the reference's np.sum does). */
 int lrvb_sum(const double* x_dev, int64_t M, double* out_dev, void* stream);
 
+/* ---- matrix- and simplex-valued parameter types, batched (MatrixParameters.py, SimplexParams.py)
+ * All pointers dev, row-major; M = number of parameters; v = k (k + 1) / 2, packed lower triangle
+ * in numpy.tril_indices order ((0,0), (1,0), (1,1), (2,0), ...); k <= 8, 2 <= d <= 64.
+ * The reference handles one matrix / one simplex row per Python iteration
+ * (MatrixParameters.py:236-249, SimplexParams.py:105-150) and differentiates with autograd. */
+/* :122-127 unpack_posdef_matrix: free (M, v) -> mat (M, k, k) = L L^T + diag_lb I with
+ * L = exp_matrix_diagonal(unvectorize_ld_matrix(free)). */
+int lrvb_posdef_unpack(const double* free_dev, int32_t k, int64_t M, double diag_lb, double* mat_dev,
+                       void* stream);
+/* :114-119 pack_posdef_matrix: mat (M, k, k) (lower triangle read) -> free (M, v).  A matrix with
+ * mat - diag_lb I not positive definite gives NaN and is counted in *not_posdef_dev (nullable,
+ * int32, caller zeroes it) where numpy.linalg.cholesky raises. */
+int lrvb_posdef_pack(const double* mat_dev, int32_t k, int64_t M, double diag_lb, double* free_dev,
+                     int32_t* not_posdef_dev, void* stream);
+/* :145-147 pos_def_matrix_free_to_vector: free (M, v) -> vectorize_ld_matrix(unpack(free)) (M, v). */
+int lrvb_posdef_free_to_vector(const double* free_dev, int32_t k, int64_t M, double diag_lb,
+                               double* vec_dev, void* stream);
+/* :149-152 its Jacobian (M, v, v), jac[m][r][c] = d vec_r / d free_c, and Hessian (M, v, v, v),
+ * hess[m][r][c1][c2]; the blocks PosDefMatrixParamVector.free_to_vector_jac / _hess (:251-297)
+ * scatter into block-diagonal sparse matrices. */
+int lrvb_posdef_free_to_vector_jac(const double* free_dev, int32_t k, int64_t M, double diag_lb,
+                                   double* jac_dev, void* stream);
+int lrvb_posdef_free_to_vector_hess(const double* free_dev, int32_t k, int64_t M, double diag_lb,
+                                    double* hess_dev, void* stream);
+/* SimplexParams.py:11-18 constrain_simplex_matrix: free (M, d-1) -> z (M, d), softmax of [0, free]. */
+int lrvb_simplex_constrain(const double* free_dev, int64_t M, int32_t d, double* z_dev, void* stream);
+/* :21-23 unconstrain_simplex_matrix: z (M, d) -> free (M, d-1). */
+int lrvb_simplex_unconstrain(const double* z_dev, int64_t M, int32_t d, double* free_dev, void* stream);
+/* :33-38 constrain_grad_from_moment per row: jac (M, d, d-1); :42-63 constrain_hess_from_moment:
+ * hess (M, d, d-1, d-1) -- both taken at z = constrain(free). */
+int lrvb_simplex_jac(const double* free_dev, int64_t M, int32_t d, double* jac_dev, void* stream);
+int lrvb_simplex_hess(const double* free_dev, int64_t M, int32_t d, double* hess_dev, void* stream);
+
 /* ---- all-reduce of the replicated blocks over NVLink peer memory ---------------------------
  * The reference has no distributed path (SURVEY.md 8e is new): an observation-sharded job sums
  * [KL, grad_g, H_gg] (lrvb_glmm_eval's out_global), the global rows of an HVP, the Schur

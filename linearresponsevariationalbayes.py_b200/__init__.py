@@ -12,6 +12,11 @@ from .Parameters import (ScalarParam, VectorParam, ArrayParam, constrain, uncons
 from .ParameterDictionary import ModelParamsDict  # noqa: F401
 from .NormalParams import UVNParam, UVNParamVector, UVNParamArray  # noqa: F401
 from .GammaParams import GammaParam  # noqa: F401
+from .MatrixParameters import (PosDefMatrixParam, PosDefMatrixParamVector,  # noqa: F401
+                               PosDefMatrixParamArray)
+from .SimplexParams import SimplexParam  # noqa: F401
+from . import MatrixParameters  # noqa: F401
+from . import SimplexParams  # noqa: F401
 from . import ExponentialFamilies  # noqa: F401
 from . import Modeling  # noqa: F401
 from . import SparseObjectives  # noqa: F401

@@ -68,6 +68,15 @@ SIGNATURES = {
     "lrvb_gh_logistic_term": (c_int32, [_P, _P, c_int64, POINTER(c_double), POINTER(c_double),
                                         c_int32, _P, _P]),
     "lrvb_sum": (c_int32, [_P, c_int64, _P, _P]),
+    "lrvb_posdef_unpack": (c_int32, [_P, c_int32, c_int64, c_double, _P, _P]),
+    "lrvb_posdef_pack": (c_int32, [_P, c_int32, c_int64, c_double, _P, _P, _P]),
+    "lrvb_posdef_free_to_vector": (c_int32, [_P, c_int32, c_int64, c_double, _P, _P]),
+    "lrvb_posdef_free_to_vector_jac": (c_int32, [_P, c_int32, c_int64, c_double, _P, _P]),
+    "lrvb_posdef_free_to_vector_hess": (c_int32, [_P, c_int32, c_int64, c_double, _P, _P]),
+    "lrvb_simplex_constrain": (c_int32, [_P, c_int64, c_int32, _P, _P]),
+    "lrvb_simplex_unconstrain": (c_int32, [_P, c_int64, c_int32, _P, _P]),
+    "lrvb_simplex_jac": (c_int32, [_P, c_int64, c_int32, _P, _P]),
+    "lrvb_simplex_hess": (c_int32, [_P, c_int64, c_int32, _P, _P]),
     "lrvb_p2p_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int64]),
     "lrvb_p2p_handle_bytes": (c_int32, []),
     "lrvb_p2p_export": (c_int32, [_P, _P]),

@@ -178,12 +178,117 @@ def forward_cases(mods):
     print("forward.npz:", len(out), "arrays")
 
 
+def _reference_packing_modules():
+    """The reference's MatrixParameters / SimplexParams call two functions that only exist in
+    autograd's numpy wrapper (``np.make_diagonal``) and in scipy < 1.0 (``sp.misc.logsumexp``).  They
+    are supplied through module-local namespace proxies -- the reference source is not modified and
+    numpy / scipy themselves are not patched."""
+    import types
+    import scipy
+    import scipy.special
+    import LinearResponseVariationalBayes.MatrixParameters as mp
+    import LinearResponseVariationalBayes.SimplexParams as sx
+
+    def make_diagonal(d, offset=0, axis1=-1, axis2=-2):
+        d = np.asarray(d)
+        out = np.zeros(d.shape + (d.shape[-1],), dtype=d.dtype)
+        i = np.arange(d.shape[-1])
+        out[..., i, i] = d
+        return out
+    np_proxy = types.ModuleType("numpy_with_make_diagonal")
+    np_proxy.__dict__.update({k: v for k, v in np.__dict__.items() if not k.startswith("__")})
+    np_proxy.make_diagonal = make_diagonal
+    mp.np = np_proxy
+    sp_proxy = types.ModuleType("scipy_with_misc_logsumexp")
+    sp_proxy.__dict__.update({k: v for k, v in scipy.__dict__.items() if not k.startswith("__")})
+    sp_proxy.misc = types.SimpleNamespace(logsumexp=scipy.special.logsumexp)
+    sx.sp = sp_proxy
+    return mp, sx
+
+
+def _richardson_jac(f, x, h=1e-2, levels=4):
+    """Central differences of f at x, Richardson-extrapolated over h, h/2, ...: (len f, len x)."""
+    def cd(hh):
+        cols = []
+        for i in range(x.size):
+            e = np.zeros_like(x)
+            e[i] = hh
+            cols.append((f(x + e) - f(x - e)) / (2 * hh))
+        return np.stack(cols, axis=-1)
+    T = [cd(h / 2 ** l) for l in range(levels)]
+    for m in range(1, levels):
+        T = [(4 ** m * T[l + 1] - T[l]) / (4 ** m - 1) for l in range(len(T) - 1)]
+    return T[0]
+
+
+def packing_cases():
+    """Outputs of the reference's own packing functions (value maps; simplex Jacobian / Hessian from
+    constrain_*_from_moment and from SimplexParam's sparse assembly) and extrapolated differences of
+    its pos_def_matrix_free_to_vector (the reference differentiates that with autograd)."""
+    mp, sx = _reference_packing_modules()
+    rng = np.random.default_rng(77)
+    out = {}
+    for k in (1, 2, 3, 4):
+        v = k * (k + 1) // 2
+        for lb in (0.0, 0.3):
+            tag = "pd_k%d_lb%s" % (k, "0" if lb == 0.0 else "p3")
+            free = rng.normal(scale=0.7, size=(5, v))
+            mats = np.array([mp.unpack_posdef_matrix(f, diag_lb=lb) for f in free])
+            out[tag + "_free"] = free
+            out[tag + "_mat"] = mats
+            out[tag + "_pack"] = np.array([mp.pack_posdef_matrix(m, diag_lb=lb) for m in mats])
+            out[tag + "_vec"] = np.array([mp.pos_def_matrix_free_to_vector(f, diag_lb=lb) for f in free])
+            out[tag + "_sym"] = np.array([mp.unvectorize_symmetric_matrix(mp.vectorize_ld_matrix(m))
+                                          for m in mats])
+            jac = np.array([_richardson_jac(lambda t: mp.pos_def_matrix_free_to_vector(t, diag_lb=lb), f)
+                            for f in free])
+            out[tag + "_jac_fd"] = jac
+            if k <= 3:
+                hess = []
+                for f in free:
+                    # Hessian of every vector entry = Jacobian of the extrapolated Jacobian
+                    Hm = _richardson_jac(
+                        lambda t: _richardson_jac(
+                            lambda u: mp.pos_def_matrix_free_to_vector(u, diag_lb=lb), t).reshape(-1),
+                        f).reshape(v, v, v)
+                    hess.append(Hm)
+                out[tag + "_hess_fd"] = np.array(hess)
+    # PosDefMatrixParamVector round trip through the reference class
+    pv = mp.PosDefMatrixParamVector(length=4, matrix_size=3, diag_lb=0.2)
+    fr = rng.normal(scale=0.5, size=pv.free_size())
+    pv.set_free(fr)
+    out["pdvec_free"] = fr
+    out["pdvec_val"] = np.array(pv.get())
+    out["pdvec_vector"] = pv.get_vector()
+    out["pdvec_free_back"] = pv.get_free()
+    for d in (2, 3, 5):
+        tag = "sx_d%d" % d
+        free = rng.normal(scale=1.5, size=(6, d - 1))
+        free[0] *= 20.0           # a nearly degenerate simplex
+        z = sx.constrain_simplex_matrix(free)
+        out[tag + "_free"] = free
+        out[tag + "_z"] = z
+        out[tag + "_unc"] = sx.unconstrain_simplex_matrix(z)
+        out[tag + "_jac"] = np.array([sx.constrain_grad_from_moment(zr) for zr in z])
+        out[tag + "_hess"] = np.array([sx.constrain_hess_from_moment(zr) for zr in z])
+        par = sx.SimplexParam(shape=(6, d))
+        # np.product (removed from numpy 2) is only used by free_size / vector_size
+        par.free_size = lambda d=d: 6 * (d - 1)
+        par.vector_size = lambda d=d: 6 * d
+        out[tag + "_jac_sparse"] = par.free_to_vector_jac(free.flatten()).toarray()
+        hs = par.free_to_vector_hess(free.flatten())
+        out[tag + "_hess_sparse"] = np.array([h.toarray() for h in hs])
+    np.savez_compressed(os.path.join(OUT, "packing.npz"), **out)
+    print("packing.npz:", len(out), "arrays")
+
+
 def main():
     vb = import_reference()
     import LinearResponseVariationalBayes.Modeling as M
     import LinearResponseVariationalBayes.ExponentialFamilies as ef
     mods = (vb, M, ef)
     forward_cases(mods)          # before gammaln is continued: pure reference behaviour
+    packing_cases()
     complex_safe_gammaln()
     glmm_case(mods, "glmm_small", N=400, K=3, G=12, Q=4, seed=11, lb=0.0, weights=True,
               empty=[5], full_hessian=True)
