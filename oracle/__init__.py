@@ -25,4 +25,9 @@ Parity status
   gradient/Hessian appears in any reference test, so for derivatives the
   reference's own tests leave **parity unpinned**; (iii) is the strongest pin
   available.
+* Matrix / simplex parameter packing (``packing_oracle.py``): value maps and the simplex
+  Jacobian / Hessian are PINNED to outputs of the reference's own functions
+  (``tests/golden/packing.npz``); the log-Cholesky Jacobian / Hessian, which the reference obtains
+  from autograd, are pinned to Richardson-extrapolated differences of the reference's forward map
+  (1e-8 / 1e-6) and cross-checked against torch-fp64 autodiff (1e-13).
 """
