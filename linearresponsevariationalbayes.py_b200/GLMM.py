@@ -204,6 +204,7 @@ class LogisticGLMM(object):
         self._x_dev = torch.zeros(self.D, dtype=torch.float64, device=dev)
         self._x_pin = torch.zeros(self.D, dtype=torch.float64).pin_memory()
         self._x_event = None
+        self._g_pin = None
         self._cache = dict(x=None, order=-1, coords=None)
         self._D_in = self.D
         self._coords = "free"
@@ -305,6 +306,17 @@ class LogisticGLMM(object):
     def grad_tensor(self):
         import torch
         return torch.cat([self._out_global[1:1 + self.Dg], self._grad_local])
+
+    def grad_host(self):
+        """Gradient of the last evaluation as a fresh numpy array: the global and the local part go
+        to one pinned buffer by two asynchronous copies (one synchronisation, no device concat)."""
+        torch = nat.require_cuda()
+        if self._g_pin is None:
+            self._g_pin = torch.empty(self.D, dtype=torch.float64).pin_memory()
+        self._g_pin[:self.Dg].copy_(self._out_global[1:1 + self.Dg], non_blocking=True)
+        self._g_pin[self.Dg:].copy_(self._grad_local, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._g_pin.numpy().copy()
 
     def blocks(self):
         """(A (Dg,Dg), B (G,2,Dg), L (G,3)) views of the cached Hessian (free or vector

@@ -111,14 +111,22 @@ class Objective(object):
         self.model = fun
         self.preconditioner = None
         self.logger = Logger()
+        self._par_key, self._par_coords = None, None
 
     # ---- helpers ----
     def _set_par(self, x, coords):
+        # ``par`` follows the evaluation point (:142-150).  The model keeps one key object per
+        # evaluated point; while that object is unchanged ``par`` already holds this point (value,
+        # gradient and Hessian requested at the same x set it once, not three times).
+        key = getattr(self.model, "_cache", {}).get("x")
+        if key is not None and self._par_key is key and self._par_coords == coords:
+            return
         xh = _host(x).reshape(-1)
         if coords == "free":
             self.par.set_free(xh)
         else:
             self.par.set_vector(xh)
+        self._par_key, self._par_coords = key, coords
 
     def _value(self, x, coords):
         self.model.evaluate(x, 0, coords)
@@ -129,8 +137,11 @@ class Objective(object):
     def _grad(self, x, coords):
         self.model.evaluate(x, 1, coords)
         self._set_par(x, coords)
-        g = self.model.grad_tensor()
-        return g if is_torch(x) else g.cpu().numpy()
+        if is_torch(x):
+            return self.model.grad_tensor()
+        if hasattr(self.model, "grad_host"):
+            return self.model.grad_host()
+        return self.model.grad_tensor().cpu().numpy()
 
     def _hessian(self, x, coords):
         self.model.evaluate(x, 2, coords)
