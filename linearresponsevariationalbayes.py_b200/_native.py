@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_double, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblrvb_b200.so")
+# LRVB_LIB_PATH: another build of the same library (A/B timing of kernel changes)
+LIB_PATH = os.environ.get("LRVB_LIB_PATH") or os.path.join(_HERE, "lib", "liblrvb_b200.so")
 
 LRVB_OK, LRVB_EINVAL, LRVB_ECUDA, LRVB_ESTATE = 0, -1, -2, -3
 

@@ -255,6 +255,60 @@ k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restri
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) indptr[n] = (int32_t)(*total);
 }
 
+// Small problems (D <= kIndptrOneCta): row counts of the global rows + exclusive scan + nnz in ONE
+// CTA -- replaces k_csr_global_rowcnt, k_scan_sum, k_scan_top, k_scan_apply (four dependent launches,
+// each a few microseconds of latency on a 20k-element array).
+constexpr int64_t kIndptrOneCta = 262144;
+__global__ void __launch_bounds__(1024)
+k_csr_indptr_small(const int32_t* __restrict__ cntA, const int32_t* __restrict__ coltot, int Dg,
+                   const int32_t* __restrict__ rowcnt, int64_t n, int32_t* __restrict__ indptr,
+                   int64_t* __restrict__ nnz_out) {
+  pdl_sync();
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long carry = 0;
+  constexpr int U = 8;     // tiles in flight: the loads of U tiles are issued before the first scan
+  for (int64_t s0 = 0; s0 < n; s0 += 1024 * U) {
+    int cs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = s0 + (int64_t)u * 1024 + threadIdx.x;
+      cs[u] = 0;
+      if (i < n) cs[u] = (i < Dg) ? cntA[i] + coltot[i] + coltot[Dg + i] : rowcnt[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = s0 + (int64_t)u * 1024 + threadIdx.x;
+      if (s0 + (int64_t)u * 1024 >= n) break;
+      const int c = cs[u];
+      int v = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      __syncthreads();
+      if (lane == 31) wsum[wid] = v;
+      __syncthreads();
+      const int ws = wsum[lane];                 // every warp scans the 32 warp totals
+      int wv = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wv, o);
+        if (lane >= o) wv += t;
+      }
+      const int tot = __shfl_sync(0xffffffffu, wv, 31);
+      const int off = __shfl_sync(0xffffffffu, wv - ws, wid);
+      if (i < n) indptr[i] = (int32_t)(carry + off + v - c);
+      carry += tot;
+    }
+  }
+  if (threadIdx.x == 0) {
+    indptr[n] = (int32_t)carry;
+    if (nnz_out) *nnz_out = carry;
+  }
+}
+
 static int csr_chunk_groups(int Dg) {
   // stage CG x (2 Dg + 1) doubles in <= ~96 KB of shared memory
   int cg = 32;
@@ -331,15 +385,21 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
   } else {
     LRVB_CUDA(cudaMemsetAsync(coltot, 0, sizeof(int32_t) * 2 * Dg, st));
   }
-  LRVB_CUDA(launch_pdl(k_csr_global_rowcnt, dim3(cdiv(Dg, 256)), dim3(256), 0, st, cntA, coltot, Dg, h->rowcnt));
-  LRVB_CHECK_LAUNCH();
   // ---- indptr ----
-  LRVB_CUDA(launch_pdl(k_scan_sum, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk));
-  LRVB_CHECK_LAUNCH();
-  LRVB_CUDA(launch_pdl(k_scan_top, dim3(1), dim3(32), 0, st, blk, nblk, blk + nblk, nnz_dev));
-  LRVB_CHECK_LAUNCH();
-  LRVB_CUDA(launch_pdl(k_scan_apply, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, blk + nblk, indptr_dev));
-  LRVB_CHECK_LAUNCH();
+  if (D <= kIndptrOneCta) {
+    LRVB_CUDA(launch_pdl(k_csr_indptr_small, dim3(1), dim3(1024), 0, st, cntA, coltot, Dg, h->rowcnt, D,
+                         indptr_dev, (int64_t*)nnz_dev));
+    LRVB_CHECK_LAUNCH();
+  } else {
+    LRVB_CUDA(launch_pdl(k_csr_global_rowcnt, dim3(cdiv(Dg, 256)), dim3(256), 0, st, cntA, coltot, Dg, h->rowcnt));
+    LRVB_CHECK_LAUNCH();
+    LRVB_CUDA(launch_pdl(k_scan_sum, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk));
+    LRVB_CHECK_LAUNCH();
+    LRVB_CUDA(launch_pdl(k_scan_top, dim3(1), dim3(32), 0, st, blk, nblk, blk + nblk, nnz_dev));
+    LRVB_CHECK_LAUNCH();
+    LRVB_CUDA(launch_pdl(k_scan_apply, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, blk + nblk, indptr_dev));
+    LRVB_CHECK_LAUNCH();
+  }
   // ---- fill: the same three roles, one launch ----
   LRVB_CUDA(launch_pdl(k_csr_pass<true>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
                        nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev));

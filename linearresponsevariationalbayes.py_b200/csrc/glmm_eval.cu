@@ -475,6 +475,13 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
   extern __shared__ double gsum[];  // 2K
   const int tid = threadIdx.x;
   const int Dg = 4 + 2 * K;
+  // the special functions of tau.shape are long serial chains: one lane of four different warps
+  // evaluates one each while the block reduces the partials (joined at the barriers below)
+  __shared__ double spec[4];
+  if (tid == 32) spec[0] = digamma_pos(vec[2]);
+  else if (tid == 64) spec[1] = trigamma_pos(vec[2]);
+  else if (tid == 96) spec[2] = tetragamma_pos(vec[2]);
+  else if (tid == 128) spec[3] = lgamma(vec[2]);
   double v = 0.0;
   for (int i = tid; i < n_kl; i += blockDim.x) v += klpart[i];
   const double data_ll = block_sum(v, red);
@@ -507,7 +514,7 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
   double* A = out + 1 + Dg;
 
   if (tid == 0) {
-    const double psi = digamma_pos(a), psi1 = trigamma_pos(a), psi2 = tetragamma_pos(a);
+    const double psi = spec[0], psi1 = spec[1], psi2 = spec[2];
     const double elt = psi - log(b);
     double F = ll - 0.5 * E * Ssum + 0.5 * Gl * elt + 0.5 * (-logsum + Gl * (1.0 + l2pi));
     double g0 = -E * dsum;
@@ -520,7 +527,7 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
     double a22 = 0.5 * Gl * psi2, a23 = 0.5 * Ssum / (b * b);
     double a33 = -a * Ssum / (b * b * b) + 0.5 * Gl / (b * b);
     if (include_global) {
-      F += 0.5 * (-log(mu_i) + 1.0 + l2pi) + a - log(b) + lgamma(a) + (1.0 - a) * psi;
+      F += 0.5 * (-log(mu_i) + 1.0 + l2pi) + a - log(b) + spec[3] + (1.0 - a) * psi;
       F += -0.5 * pr.mu_info * ((mu_m - pr.mu_mean) * (mu_m - pr.mu_mean) + 1.0 / mu_i);
       F += (pr.tau_shape - 1.0) * elt - pr.tau_rate * E;
       g0 += -pr.mu_info * (mu_m - pr.mu_mean);

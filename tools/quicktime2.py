@@ -25,7 +25,20 @@ def run(N, K, G, Q, reps=10):
             model.evaluate(x, order, force=True)
         e1.record(); torch.cuda.synchronize()
         out.append(e0.elapsed_time(e1) / reps)
-    print("N=%d K=%d G=%d Q=%d: order0 %.3f  order1 %.3f  order2 %.3f ms" % ((N, K, G, Q) + tuple(out)), flush=True)
+    keep = None
+    def step():
+        model.evaluate(x, 2, force=True)
+        return model.hessian_csr()
+    for _ in range(3):
+        keep = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        keep = step()
+    e1.record(); torch.cuda.synchronize()
+    out.append(e0.elapsed_time(e1) / reps)
+    print("N=%d K=%d G=%d Q=%d: order0 %.3f  order1 %.3f  order2 %.3f  order2+csr %.3f ms" % ((N, K, G, Q) + tuple(out)), flush=True)
 
 if __name__ == "__main__":
     run(1000000, 20, 10000, 8)
