@@ -439,8 +439,7 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": d2h,
                     "api": "Objective.fun_free_hessian/fun_free_grad/fun_free with numpy x; "
                            "scipy CSR + numpy gradient + float returned to the host"},
-            "lrvb_covariance": {"ms": cov_ms, "what": "(H^-1)[:Dg,:Dg] of the cached Hessian, Schur "
-                                "complement (DMMA) + SPD inverse, device time", "Dg": 4 + 2 * K},
+            "lrvb_covariance": _cov_entry(cov_ms, K, G, world, peak_tf),
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -452,6 +451,20 @@ def run_ours(args, wl):
     sys.stdout.flush()
     os.dup2(result_fd, 1)
     os.close(result_fd)
+
+
+def _cov_entry(cov_ms, K, G, world, peak_tf):
+    """Second half of the metric: wall time of the global-parameter LRVB covariance and its fraction
+    of the FP64 tensor roofline.  Algorithmic flops: per group B_g^T L_g^-1 B_g on the upper
+    triangle (2 Dg^2 + 8 Dg), plus Dg^3 for the SPD inverse; at Dg = 44 the work is ~40 MFLOP per
+    GPU, i.e. the number is launch / latency bound, not tensor bound."""
+    Dg = 4 + 2 * K
+    flops = world * G * (2 * Dg * Dg + 8 * Dg) + Dg ** 3
+    tf = flops / (cov_ms * 1e-3) / 1e12
+    return {"ms": cov_ms, "what": "(H^-1)[:Dg,:Dg] of the cached Hessian: Schur complement (DMMA) "
+            "[+ sum over ranks] + SPD inverse, device time, max over ranks", "Dg": Dg,
+            "algorithmic_flops": flops, "achieved_tflops": tf, "peak_tflops": peak_tf,
+            "frac": tf / peak_tf, "bound": "latency (work far below one wave of the tensor pipe)"}
 
 
 def _hbm_peak():
