@@ -274,6 +274,16 @@ int lrvb_p2p_connect(lrvb_p2p* h, const void* handles);
 int lrvb_p2p_allreduce_sum(lrvb_p2p* h, double* buf_dev, int64_t n, void* stream);
 int lrvb_p2p_status(lrvb_p2p* h, int32_t* status_out, void* stream);
 int lrvb_p2p_destroy(lrvb_p2p* h);
+/* ConjugateGradientSolver.get_hinv_vec (ConjugateGradient.py:81-85) over the shards of one job:
+ * lrvb_glmm_cg on vectors in the shard's local layout [globals | u.mean | u.info of the shard's
+ * groups] (globals replicated on every rank), with two peer all-reduces per iteration
+ * ([r.r, r.z] and [(H p)_g, p_l.q_l]).  root = 1 on the one rank that counts the global entries
+ * in dot products and adds the (all-reduced) global block A in the Hessian-vector product.
+ * Every rank calls it with the same precond / rtol / maxiter (> 0; scipy's default is 10 x the
+ * dimension of the whole job).  info / iters as lrvb_glmm_cg.  Syncs every 8 iterations. */
+int lrvb_glmm_cg_sharded(lrvb_glmm* h, lrvb_p2p* comm, const double* b_dev, const double* x0_dev,
+                         int32_t precond, double rtol, int32_t maxiter, int32_t root, double* x_dev,
+                         int32_t* info_host, int32_t* iters_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,8 @@ SIGNATURES = {
     "lrvb_p2p_allreduce_sum": (c_int32, [_P, _P, c_int64, _P]),
     "lrvb_p2p_status": (c_int32, [_P, POINTER(c_int32), _P]),
     "lrvb_p2p_destroy": (c_int32, [_P]),
+    "lrvb_glmm_cg_sharded": (c_int32, [_P, _P, _P, _P, c_int32, c_double, c_int32, c_int32, _P,
+                                       POINTER(c_int32), POINTER(c_int32), _P]),
 }
 
 _lib = None

@@ -252,6 +252,113 @@ k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __rest
   }
 }
 
+// ---- sharded variants (lrvb_glmm_cg_sharded) ---------------------------------------------------------
+// z = M r and the partials of r.r (slot 0) and r.z (slot 1) over the entries [lo, D) this rank counts
+__global__ void __launch_bounds__(256)
+k_cg_precond2(const double* __restrict__ r, double* __restrict__ z, const double* __restrict__ A,
+              const double* __restrict__ Linv, double* __restrict__ part, const int* __restrict__ flags,
+              int Dg, int G, int precond, int64_t lo) {
+  pdl_sync();
+  if (flags[0]) return;
+  __shared__ double red[32];
+  const int64_t D = Dg + 2 * (int64_t)G;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double zi;
+    const double ri = r[i];
+    if (!precond) zi = ri;
+    else if (i < Dg) zi = ri / A[(size_t)i * Dg + i];
+    else if (i < Dg + G) {
+      const int64_t gi = i - Dg;
+      zi = Linv[gi * 3] * ri + Linv[gi * 3 + 1] * r[i + G];
+    } else {
+      const int64_t gi = i - Dg - G;
+      zi = Linv[gi * 3 + 1] * r[i - G] + Linv[gi * 3 + 2] * ri;
+    }
+    z[i] = zi;
+    if (i >= lo) {
+      s0 = fma(ri, ri, s0);
+      s1 = fma(ri, zi, s1);
+    }
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * 2] = s0;
+    part[blockIdx.x * 2 + 1] = s1;
+  }
+}
+
+// per-CTA partials (npart, 2) -> the two scalars of this rank's message
+__global__ void __launch_bounds__(256)
+k_cg_fold(const double* __restrict__ part, int npart, double* __restrict__ sc, const int* __restrict__ flags) {
+  pdl_sync();
+  if (flags && flags[0]) return;
+  __shared__ double red[32];
+  const double a = reduce_parts(part, npart, 2, red);
+  const double b = reduce_parts(part + 1, npart, 2, red);
+  if (threadIdx.x == 0) { sc[0] = a; sc[1] = b; }
+}
+
+// convergence test on the summed r.r, then p = z + (rho / rho_prev) p with the summed rho = r.z
+__global__ void __launch_bounds__(256)
+k_cg_dir2(const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc,
+          double* __restrict__ scal, int* __restrict__ flags, int64_t D, int it) {
+  pdl_sync();
+  if (flags[0]) return;
+  const double rn = sqrt(sc[0]);
+  if (rn < scal[2]) {
+    // identical on every CTA and every rank: a CTA that starts late and already sees the flag
+    // returns at the top, which is the same decision
+    if (blockIdx.x == 0 && threadIdx.x == 0) { flags[0] = 1; scal[3] = rn; }
+    return;
+  }
+  const double rho = sc[1];
+  const double beta = (it > 0) ? rho / scal[4 + ((it - 1) & 1)] : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[4 + (it & 1)] = rho;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = (it > 0) ? fma(beta, p[i], z[i]) : z[i];
+}
+
+// message of the second collective: [q_g (Dg) | sum of the local p.q partials]
+__global__ void __launch_bounds__(256)
+k_cg_pack(const double* __restrict__ q, const double* __restrict__ part, int npart, double* __restrict__ msg,
+          int Dg, const int* __restrict__ flags) {
+  pdl_sync();
+  if (flags[0]) return;
+  __shared__ double red[32];
+  for (int i = threadIdx.x; i < Dg; i += blockDim.x) msg[i] = q[i];
+  const double s = reduce_parts(part, npart, 2, red);
+  if (threadIdx.x == 0) msg[Dg] = s;
+}
+
+// q_g <- summed global rows; alpha = rho / (p_g.q_g + summed local part); x += alpha p; r -= alpha q
+__global__ void __launch_bounds__(256)
+k_cg_update2(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+             double* __restrict__ q, const double* __restrict__ msg, const double* __restrict__ scal,
+             int* __restrict__ flags, int64_t D, int Dg, int it) {
+  pdl_sync();
+  if (flags[0]) return;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < Dg; i += blockDim.x) s = fma(p[i], msg[i], s);
+  s = block_sum(s, red);
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = s + msg[Dg];
+  __syncthreads();
+  const double alpha = scal[4 + (it & 1)] / bc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double qi = (i < Dg) ? msg[i] : q[i];
+    if (i < Dg) q[i] = qi;
+    x[i] = fma(alpha, p[i], x[i]);
+    r[i] = fma(-alpha, qi, r[i]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) flags[1] = it + 1;
+}
+
 __global__ void k_axpby(double* __restrict__ out, const double* __restrict__ a, double alpha,
                         const double* __restrict__ b, double beta, int64_t n) {
   pdl_sync();
@@ -733,6 +840,94 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   if (!hflags[0]) {
     // scipy tests convergence at the top of the next iteration only inside the loop: after
     // maxiter updates it reports maxiter without another test.
+    *info = maxiter;
+  } else {
+    *info = 0;
+  }
+  if (iters) *iters = hflags[1];
+  return LRVB_OK;
+}
+
+// ---- conjugate gradient over the shards of one job ------------------------------------------------
+// Same iteration as lrvb_glmm_cg on vectors in the shard's local layout [globals | u.mean | u.info of
+// the shard's groups]: the global entries are replicated on every rank (bitwise: they evolve from
+// all-reduced quantities only), the local ones are private.  Per iteration TWO collectives over the
+// NVLink peer windows (csrc/p2p.cu), both folded messages:
+//   [r.r, r.z]                          after the preconditioner (2 doubles)
+//   [(H p)_g (Dg doubles), p_l.q_l]     after the Hessian-vector product (Dg + 1 doubles)
+// Dot products count the global entries once (`root` = the rank that owns them).  As in the single-GPU
+// solver no scalar visits the host; the converged flag is read back every 8 iterations.
+int lrvb_glmm_cg_sharded(lrvb_glmm* h, lrvb_p2p* comm_h, const double* b_dev, const double* x0_dev,
+                         int32_t precond, double rtol, int32_t maxiter, int32_t root, double* x_dev,
+                         int32_t* info, int32_t* iters, void* stream) {
+  LRVB_TRY(require_hess(h, "lrvb_glmm_cg_sharded"));
+  LRVB_REQUIRE(comm_h != nullptr, "lrvb_glmm_cg_sharded: the peer all-reduce handle is NULL");
+  LRVB_REQUIRE(b_dev && x_dev && info, "lrvb_glmm_cg_sharded: NULL argument");
+  LRVB_REQUIRE(precond == 0 || precond == 1, "lrvb_glmm_cg_sharded: precond = %d not in {0,1}", precond);
+  LRVB_REQUIRE(maxiter > 0, "lrvb_glmm_cg_sharded: maxiter must be positive (10 x the JOB's dimension in scipy)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t D = h->D;
+  const int Dg = h->Dg, G = h->G;
+  double* r = h->cgbuf;
+  double* z = r + D;
+  double* p = z + D;
+  double* q = p + D;
+  double* msg = q + D;            // Dg + 1
+  double* sc = msg + D;           // 2 scalars
+  double* x = x_dev;
+  double* part = h->dotpart;      // (dot_grid, 2)
+  int* flags = h->flags;
+  const int vgrid = h->dot_grid;
+  const int64_t lo = root ? 0 : Dg;      // first entry this rank counts in dot products
+  LRVB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
+  if (precond) LRVB_TRY(prepare_linv(h, st));
+#define LRVB_AR(buf, n) LRVB_TRY(lrvb_p2p_allreduce_sum(comm_h, (buf), (n), stream))
+  // atol = rtol ||b||
+  LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, b_dev + lo, b_dev + lo, nullptr, nullptr, D - lo, part, nullptr));
+  LRVB_CHECK_LAUNCH();
+  LRVB_CUDA(launch_pdl(k_cg_fold, dim3(1), dim3(256), 0, st, part, vgrid, sc, nullptr));
+  LRVB_CHECK_LAUNCH();
+  LRVB_AR(sc, 2);
+  LRVB_CUDA(launch_pdl(k_cg_init, dim3(1), dim3(256), 0, st, sc, 1, rtol, h->scal, flags));
+  LRVB_CHECK_LAUNCH();
+  if (x0_dev) {
+    if (x0_dev != x) LRVB_CUDA(cudaMemcpyAsync(x, x0_dev, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+    LRVB_TRY(launch_hvp(h, x, q, root ? 1 : 0, nullptr, st));
+    LRVB_AR(q, Dg);
+    LRVB_CUDA(launch_pdl(k_axpby, dim3(vgrid), dim3(256), 0, st, r, b_dev, 1.0, q, -1.0, D));
+  } else {
+    LRVB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * D, st));
+    LRVB_CUDA(launch_pdl(k_axpby, dim3(vgrid), dim3(256), 0, st, r, b_dev, 1.0, nullptr, 0.0, D));
+  }
+  LRVB_CHECK_LAUNCH();
+
+  int hflags[4] = {0, 0, 0, 0};
+  int it = 0;
+  const int batch = 8;
+  while (it < maxiter) {
+    const int end = (it + batch < maxiter) ? it + batch : maxiter;
+    for (; it < end; ++it) {
+      LRVB_CUDA(launch_pdl(k_cg_precond2, dim3(vgrid), dim3(256), 0, st, r, z, h->A, h->Linv, part, flags, Dg, G,
+                           precond, lo));
+      LRVB_CUDA(launch_pdl(k_cg_fold, dim3(1), dim3(256), 0, st, part, vgrid, sc, flags));
+      g_launches += 2;
+      LRVB_AR(sc, 2);
+      LRVB_CUDA(launch_pdl(k_cg_dir2, dim3(vgrid), dim3(256), 0, st, z, p, sc, h->scal, flags, D, it));
+      LRVB_TRY(launch_hvp(h, p, q, root ? 1 : 0, flags, st));
+      LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, p + Dg, q + Dg, nullptr, nullptr, D - Dg, part, flags));
+      LRVB_CUDA(launch_pdl(k_cg_pack, dim3(1), dim3(256), 0, st, q, part, vgrid, msg, Dg, flags));
+      g_launches += 3;
+      LRVB_AR(msg, (int64_t)Dg + 1);
+      LRVB_CUDA(launch_pdl(k_cg_update2, dim3(vgrid), dim3(256), 0, st, x, r, p, q, msg, h->scal, flags, D, Dg, it));
+      LRVB_CHECK_LAUNCH();
+    }
+    LRVB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    LRVB_CUDA(cudaStreamSynchronize(st));
+    if (hflags[0]) break;
+  }
+#undef LRVB_AR
+  if (!hflags[0]) {
+    // one more convergence test would need another collective: scipy reports maxiter here as well
     *info = maxiter;
   } else {
     *info = 0;

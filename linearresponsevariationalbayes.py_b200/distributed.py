@@ -355,6 +355,18 @@ class ShardedLogisticGLMM(object):
         import torch
         if maxiter <= 0:
             maxiter = 10 * self.D
+        if self._peer is not None and self.Dg + 1 <= self._peer.max_elems:
+            # device-resident iteration, two peer all-reduces per step (lrvb_glmm_cg_sharded)
+            import ctypes
+            from . import _native as nat
+            b = b.contiguous()
+            x = torch.empty_like(b)
+            info, iters = ctypes.c_int32(), ctypes.c_int32()
+            nat.check(self.local._lib.lrvb_glmm_cg_sharded(
+                self.local._h, self._peer._h, nat.ptr(b), nat.ptr(None if x0 is None else x0.contiguous()),
+                int(precond), float(rtol), int(min(maxiter, 2000000000)), 1 if self.rank == 0 else 0,
+                nat.ptr(x), ctypes.byref(info), ctypes.byref(iters), nat.stream_ptr()))
+            return x, info.value, iters.value
         bnrm = torch.sqrt(self._dot(b, b)[0]).item()
         if bnrm == 0.0:
             return b.clone(), 0, 0

@@ -79,8 +79,30 @@ def _worker(rank, world, port, out):
         v = np.random.default_rng(42).standard_normal(x.size)
         hve = oracle.kl_hvp(x, v)
         res["hvp"] = np.abs(obj.fun_free_hvp(x, v) - hve).max() / np.abs(hve).max()
+        # conjugate gradient over the shards: device-resident iteration with two peer all-reduces per
+        # step (lrvb_glmm_cg_sharded) against the dense solve and against the torch / NCCL iteration
+        Hd = He.toarray()
+        xe = np.linalg.solve(Hd, v)
+        for tag, pre in (("cg_jacobi", 1), ("cg_plain", 0)):
+            xs, info, iters = model.cg(v, precond=pre, rtol=1e-11)
+            res[tag] = float(info) + np.abs(xs.cpu().numpy() - xe).max() / np.abs(xe).max()
+            res[tag + "_iters"] = iters
+        xs0, info0, iters0 = model.cg(v, x0_full=xe * (1 + 1e-3), precond=1, rtol=1e-11)
+        res["cg_x0"] = float(info0) + np.abs(xs0.cpu().numpy() - xe).max() / np.abs(xe).max()
+        res["cg_x0_fewer"] = float(iters0 < res["cg_jacobi_iters"])
+        peer = model._peer
+        model._peer = None
+        xs_t, info_t, iters_t = model.cg(v, precond=1, rtol=1e-11)
+        model._peer = peer
+        res["cg_vs_torch_iters"] = abs(iters_t - res["cg_jacobi_iters"])
+        res["cg_torch"] = float(info_t) + np.abs(xs_t.cpu().numpy() - xe).max() / np.abs(xe).max()
+        solver = vb.ConjugateGradientSolver(obj.fun_free_hvp, x)
+        solver.tol = 1e-11
+        solver.preconditioner = "block_jacobi"
+        xs_s, info_s = solver.get_hinv_vec(v)
+        res["cg_solver"] = float(info_s) + np.abs(xs_s - xe).max() / np.abs(xe).max()
         lr = vb.LinearResponseCovariances(obj, x)
-        Hinv = np.linalg.inv(He.toarray())
+        Hinv = np.linalg.inv(Hd)
         Dg = oracle.lay.Dg
         res["cov_g"] = np.abs(lr.get_global_covariance() - Hinv[:Dg, :Dg]).max() / np.abs(Hinv).max()
         res["status2"] = model._peer.status() if model._peer is not None else 0
@@ -109,3 +131,7 @@ def test_peer_allreduce_and_sharded_model_all_gpus():
         for key in ("kl", "grad", "hess", "hvp"):
             assert res[key] < 1e-9, (rank, key, res[key])
         assert res["cov_g"] < 1e-8
+        for key in ("cg_jacobi", "cg_plain", "cg_x0", "cg_torch", "cg_solver"):
+            assert res[key] < 1e-8, (rank, key, res[key])
+        assert res["cg_x0_fewer"] == 1.0
+        assert res["cg_vs_torch_iters"] <= 2, res["cg_vs_torch_iters"]

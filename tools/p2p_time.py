@@ -67,6 +67,21 @@ def main():
     model._peer = p
     out.append("sharded evaluate only (peer)      %.4f ms" % ev_time(lambda: model.evaluate(x, 2, force=True), 200))
     out.append("local evaluate only               %.4f ms" % ev_time(lambda: loc.evaluate(x, 2, force=True), 200))
+    import time
+    v = torch.randn(model.D, dtype=torch.float64, device=dev)
+    dist.broadcast(v, 0)
+    for label in ("peer", "nccl"):
+        if label == "nccl":
+            model._peer = None
+        model.cg(v, precond=1, rtol=1e-10, maxiter=16)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        xs, info, iters = model.cg(v, precond=1, rtol=1e-30, maxiter=96)   # fixed work: 96 iterations
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out.append("sharded CG (%s): %d iterations, info %d, %.3f ms = %.1f us / iteration" % (
+            label, iters, info, dt * 1e3, dt * 1e6 / max(iters, 1)))
+    model._peer = p
     if rank == 0:
         print("world %d  status %d" % (world, st), file=sys.stderr)
         print("\n".join(out), file=sys.stderr)
