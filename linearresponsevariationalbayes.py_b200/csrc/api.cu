@@ -1,11 +1,13 @@
 // C-ABI entry points: handle life-cycle and evaluation (see include/lrvb_b200.h).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 #include "common.cuh"
 #include "gram_small.cuh"
 #include "obs_fused.cuh"
+#include "gram_mid.cuh"
 #include "gram_big.cuh"
 
 namespace lrvb {
@@ -192,6 +194,12 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     if (K <= 20) {
       // small K: every warp owns the whole packed upper triangle (gram_small.cuh), one CTA per SM
       h->gram_small = 1;
+      h->gram_grid_x = kNumSMs;
+      h->gram_grid_y = 1;
+      npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;
+    } else if (K <= kGmMaxK && !(getenv("LRVB_GRAM_MID") && getenv("LRVB_GRAM_MID")[0] == '0')) {
+      // 20 < K <= 52: still one warp = the whole packed triangle, 8 - 12 warps per SM (gram_mid.cuh)
+      h->gram_mid = 1;
       h->gram_grid_x = kNumSMs;
       h->gram_grid_y = 1;
       npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;

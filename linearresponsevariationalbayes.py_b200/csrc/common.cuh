@@ -191,6 +191,7 @@ struct lrvb_glmm {
   double* klpart = nullptr;   // (obs_grid) per-CTA partials of sum w*l
   double* gradpart = nullptr; // (obs_grid, 2, K) per-CTA partials of X^T l_m , S^T l_v
   // fused observation + group pass (K <= 62, obs_fused.cuh)
+  int gram_mid = 0;           // 20 < K <= 52: every warp owns the packed triangle (gram_mid.cuh)
   int obs_fused = 0, of_grid = 0, of_warps = 0;
   size_t of_smem = 0;
   int64_t of_rows_per_warp = 0;

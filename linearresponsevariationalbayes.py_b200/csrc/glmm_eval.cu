@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gram_small.cuh"
 #include "obs_fused.cuh"
+#include "gram_mid.cuh"
 #define LRVB_GRAM_BIG_KERNELS
 #include "gram_big.cuh"
 
@@ -674,6 +675,11 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
           set_error("launch_eval: small-K Gram kernel rejected K = %d / alignment", K);
           return LRVB_ESTATE;
         }
+      } else if (h->gram_mid) {
+        if (!launch_gram_mid(h->X, h->W + 2 * h->ldw, h->grampart, N, h->ldw, K, h->gram_grid_x, st)) {
+          set_error("launch_eval: mid-K Gram kernel rejected K = %d / alignment", K);
+          return LRVB_ESTATE;
+        }
       } else {
         LRVB_CUDA(launch_pdl(k_gram_big, dim3(h->gram_grid_x), dim3(32 * kGbWarps), h->gram_smem, st,
             h->X, h->W + 2 * h->ldw, h->ldw, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,
@@ -690,16 +696,17 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     if (order >= 2) {
       if (G > 0) n_bor = cdiv((int64_t)G * Dg, 256);
       if (N > 0) {
-        if (h->gram_small) { NT = gram_small_shape(K).NT; n_gf = NT; }
+        if (h->gram_small || h->gram_mid) { NT = gram_small_shape(K).NT; n_gf = NT; }
         else n_gf = h->gram_jobs * 16;
       }
     }
     const int grid = n_loc + n_bor + n_gf;
+    const int packed_gram = (h->gram_small || h->gram_mid) ? 1 : 0;   // partial layout (n_cta, NT, 64)
 #define LRVB_FIN(O)                                                                              \
   LRVB_CUDA(launch_pdl(k_finish<O>, dim3(grid), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
                        h->locpart, h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,   \
-                       outp + 1 + Dg, K, G, n_loc, n_bor, h->gram_small, NT, h->gram_grid_y,       \
-                       h->gram_small ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
+                       outp + 1 + Dg, K, G, n_loc, n_bor, packed_gram, NT, h->gram_grid_y,         \
+                       packed_gram ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
                        h->bounds, h->vecmode))
     if (order == 0) LRVB_FIN(0);
     else if (order == 1) LRVB_FIN(1);

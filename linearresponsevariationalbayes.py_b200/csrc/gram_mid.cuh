@@ -1,0 +1,312 @@
+// Weighted Grams of the beta block for 20 < K <= 52 on the FP64 tensor cores (DMMA.8x8x4), sm_100a.
+//
+// Same packed formulation as gram_small.cuh (ONE weighted Gram of z = [x | s], upper triangle of
+// the T2 x T2 tile grid, tile classes pure-x / straddle / pure-s) and the same execution model:
+// EVERY WARP OWNS THE WHOLE TRIANGLE for its rows, streams its own stages through a private
+// shared-memory ring filled by bulk async copies, and all warps of all CTAs do identical work --
+// so the four FP64 pipes of an SM are evenly loaded, which the rectangle jobs of gram_big.cuh
+// never quite achieve (0.52 - 0.63 of the DMMA peak there).  What changes against gram_small is
+// the register budget: up to NT = 91 accumulator tiles (182 registers) per thread at T2 = 13, so
+//   * a CTA has 8 warps (12 for T2 <= 9) at up to 255 registers, one CTA per SM;
+//   * there is no register prefetch of the next k-step: a k-step is 23 - 92 independent DMMAs
+//     (370 - 1470 pipe cycles), the second warp of the sub-partition covers the ~100 cycles in which
+//     the first one fetches its 13 operands;
+//   * the weighted B operands are formed per column tile right before its DMMAs instead of for the
+//     whole k-step up front;
+//   * the per-lane offsets of the packed columns are compile-time constants plus one base;
+//   * the CTA's warps add their accumulators into one shared tile set one after the other (fixed
+//     order) because 8 x 91 tiles do not fit in shared memory at once.
+// Output layout = gram_small's: part (gridDim.x, NT, 64), tile (i <= j) at slot j (j+1)/2 + i.
+#pragma once
+#include "common.cuh"
+#include "gram_small.cuh"   // mbarrier / bulk-copy / lds / vmul helpers
+
+namespace lrvb {
+
+constexpr int kGmRows = 16;       // rows per stage (4 k-steps)
+constexpr int kGmStages = 3;      // ring depth per team
+constexpr int kGmMaxK = 52;       // T2 = ceil(2K / 8) <= 13
+
+// launch geometry by tile-grid size: T2 <= 8 leaves room for 12 single-warp teams at 168 registers;
+// 9 and 10 need the 255-register budget (8 warps); from 11 on the triangle is split between the two
+// warps of a team (8 warps = 4 teams)
+struct GramMidGeom {
+  int warps, P;
+};
+__host__ __device__ constexpr GramMidGeom gram_mid_geom(int T2) {
+  return T2 <= 6 ? GramMidGeom{16, 1} : (T2 <= 8 ? GramMidGeom{12, 1} : (T2 <= 10 ? GramMidGeom{12, 2} : GramMidGeom{8, 2}));
+}
+// first column tile of the second warp of a team: balances the DMMA counts of the two halves
+__host__ __device__ constexpr int gram_mid_split(int T2, bool has_m, int T0) {
+  int best = 1, best_max = 1 << 30;
+  const int total = T2 * (T2 + 1) / 2 + (has_m ? 1 : 0);
+  for (int j0 = 1; j0 < T2; ++j0) {
+    const int a = j0 * (j0 + 1) / 2 + ((has_m && T0 < j0) ? 1 : 0);
+    const int b = total - a;
+    const int m = a > b ? a : b;
+    if (m < best_max) { best_max = m; best = j0; }
+  }
+  return best;
+}
+__host__ __device__ inline size_t gram_mid_stage_elems(int K) { return (size_t)kGmRows * K + 3 * kGmRows; }
+inline size_t gram_mid_smem(int K, int T2) {
+  const GramMidGeom g = gram_mid_geom(T2);
+  const int teams = g.warps / g.P;
+  const size_t ring = sizeof(double) * teams * kGmStages * gram_mid_stage_elems(K) +
+                      sizeof(unsigned long long) * teams * kGmStages * 2;
+  const size_t red = sizeof(double) * (size_t)(T2 * (T2 + 1) / 2) * 64;
+  return ring > red ? ring : red;
+}
+
+// The stream of one warp: column tiles [JLO, JHI) of the packed upper triangle over the stages of
+// its team.  PRODUCER issues the bulk copies (the first warp of a team).
+template <int T2, int T0, bool HAS_M, int P, int JLO, int JHI, bool PRODUCER>
+__device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const double* __restrict__ Wabc,
+                                             double* __restrict__ red, int64_t N, int64_t ldw, int K,
+                                             unsigned ring_u, unsigned full_u, unsigned empty_u, double* ring,
+                                             int gt, int tt, int warp, int nwarps) {
+  constexpr int TS = HAS_M ? T0 : -1;        // straddle tile
+  constexpr int TB = HAS_M ? T0 + 1 : T0;    // first pure-s tile
+  constexpr int T_LO = JLO * (JLO + 1) / 2;
+  constexpr int NTL = JHI * (JHI + 1) / 2 - T_LO;     // accumulator tiles of this warp
+  constexpr int KSTEPS = kGmRows / 4;
+  const int lane = threadIdx.x & 31;
+  const int lr = lane & 3, lc = lane >> 2;
+  const int stage_elems = kGmRows * K + 3 * kGmRows;
+
+  // packed column `col = 8 t + lc` of tile t sits at x column `col` (x class) or `col - K` (s class)
+  // of the staged row: compile-time per tile except in the straddle tile and beyond 2K in the last
+  const int base = lr * K + lc;                                   // + 8 t (x tiles), + 8 t - K (s tiles)
+  bool cls1 = false, valid_m = true, valid_last = true;
+  int off_m = 0, off_last = 0;
+  if (HAS_M) {
+    const int col = 8 * TS + lc;
+    cls1 = col >= K;
+    valid_m = col < 2 * K;
+    off_m = lr * K + (valid_m ? (cls1 ? col - K : col) : 0);
+  }
+  {
+    const int col = 8 * (T2 - 1) + lc;
+    valid_last = col < 2 * K;
+    off_last = lr * K + (valid_last ? col - K : 0);
+  }
+
+  double acc[NTL][2];
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) acc[t][0] = acc[t][1] = 0.0;
+
+  // 32-bit stage counters (N < 2^35): registers are the scarce resource of this kernel
+  const int nstage = (int)((N + kGmRows - 1) / kGmRows);
+  const int nfull = (int)(N / kGmRows);
+  const unsigned xbytes = (unsigned)(kGmRows * K * sizeof(double));
+  const unsigned wbytes = (unsigned)(kGmRows * sizeof(double));
+
+  auto issue = [&](int s, int slot) {
+    if (s < nfull && lane < 4) {
+      const unsigned bar = full_u + 8 * slot;
+      const unsigned dst = ring_u + (unsigned)(slot * stage_elems * sizeof(double));
+      const int64_t n0 = (int64_t)s * kGmRows;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, xbytes + 3 * wbytes);
+        bulk_g2s(dst, X + n0 * K, xbytes, bar);
+      } else {
+        bulk_g2s(dst + xbytes + (lane - 1) * wbytes, Wabc + (int64_t)(lane - 1) * ldw + n0, wbytes, bar);
+      }
+    }
+  };
+
+  if (PRODUCER) {
+#pragma unroll
+    for (int p = 0; p < kGmStages; ++p) issue(gt + p * tt, p);
+  }
+
+  int slot = 0, pslot = 0;
+  unsigned phase = 0, pphase = 0;
+  bool first = true;
+  for (int s = gt; s < nstage; s += tt) {
+    // ---- make the stage readable ----
+    if (s < nfull) {
+      mbar_wait(full_u + 8 * slot, phase);
+    } else if (PRODUCER) {   // ragged last stage: filled by the producer warp itself, zero rows beyond N
+      if (P > 1 && (s - gt) / tt >= kGmStages) mbar_wait(empty_u + 8 * slot, phase ^ 1u);   // previous use released
+      double* xs = ring + (size_t)slot * stage_elems;
+      double* ws = xs + kGmRows * K;
+      const int64_t n0 = (int64_t)s * kGmRows;
+      const int rows = (int)(N - n0);
+      for (int e = lane; e < kGmRows * K; e += 32) xs[e] = (e < rows * K) ? X[n0 * K + e] : 0.0;
+      for (int e = lane; e < 3 * kGmRows; e += 32) {
+        const int f = e / kGmRows, r = e % kGmRows;
+        ws[e] = (r < rows) ? Wabc[(int64_t)f * ldw + n0 + r] : 0.0;
+      }
+      __syncwarp();
+      if (P > 1 && lane == 0) mbar_arrive(full_u + 8 * slot);
+    } else {
+      mbar_wait(full_u + 8 * slot, phase);
+    }
+    const unsigned xs_u = ring_u + (unsigned)(slot * stage_elems * sizeof(double));
+    const unsigned ws_u = xs_u + 8u * (unsigned)(kGmRows * K + lr);
+#pragma unroll 1
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const unsigned row_u = xs_u + 8u * (unsigned)(4 * ks * K);
+      double z[JHI];                     // row tiles 0 .. JHI-1 are all this warp ever multiplies
+#pragma unroll
+      for (int t = 0; t < JHI; ++t) {
+        int o;
+        if (t == TS) o = off_m;
+        else if (t == T2 - 1 && t >= TB) o = off_last;
+        else o = base + ((t < T0) ? 8 * t : 8 * t - K);
+        z[t] = lds_f64(row_u + 8u * (unsigned)o);
+      }
+      const double wa = lds_f64(ws_u + 8u * (unsigned)(4 * ks));
+      const double wb = lds_f64(ws_u + 8u * (unsigned)(kGmRows + 4 * ks));
+      const double wc = lds_f64(ws_u + 8u * (unsigned)(2 * kGmRows + 4 * ks));
+#pragma unroll
+      for (int t = 0; t < JHI; ++t) {
+        if (t == TS) {
+          const double xx = vmul(z[t], z[t]);
+          z[t] = cls1 ? xx : z[t];
+          if (!valid_m) z[t] = 0.0;
+        } else if (t >= TB) {
+          z[t] = vmul(z[t], z[t]);
+          if (t == T2 - 1 && !valid_last) z[t] = 0.0;
+        }
+      }
+      double aw2 = 0.0;
+      if (HAS_M && JHI > TS) aw2 = vmul(z[(HAS_M && JHI > TS) ? TS : 0], cls1 ? wc : wb);
+#pragma unroll
+      for (int j = JLO; j < JHI; ++j) {
+        const int cb = j * (j + 1) / 2 - T_LO;
+        // B operands of column tile j: x rows see (a | b), s rows see c
+        double bw0 = 0.0, bc = 0.0;
+        if (T0 > 0 || j == TS) bw0 = vmul(z[j], (j < T0) ? wa : ((j == TS) ? (cls1 ? wb : wa) : wb));
+        if (j >= TB) bc = vmul(z[j], wc);
+#pragma unroll
+        for (int i = 0; i < T0; ++i)
+          if (i <= j) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bw0);
+        if (HAS_M && j == TS) {
+          dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? 0.0 : z[j], bw0);   // x rows of the tile
+          dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? z[j] : 0.0, aw2);   // s rows of the tile
+        }
+        if (HAS_M && j > TS)
+          dmma884(acc[cb + (HAS_M ? TS : 0)][0], acc[cb + (HAS_M ? TS : 0)][1], aw2, z[j]);
+#pragma unroll
+        for (int i = TB; i < T2; ++i)
+          if (i <= j) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bc);
+      }
+    }
+    __syncwarp();            // every lane has read its last operands of this slot
+    if (P == 1) {
+      issue(s + kGmStages * tt, slot);
+    } else {
+      if (lane == 0) mbar_arrive(empty_u + 8 * slot);
+      if (PRODUCER) {
+        // refill the slot of the PREVIOUS stage once both warps of the team have released it: the
+        // producer may run one stage ahead of its partner instead of meeting it at every stage
+        if (!first) {
+          mbar_wait(empty_u + 8 * pslot, pphase);
+          issue(s - tt + kGmStages * tt, pslot);
+        }
+        pslot = slot;
+        pphase = phase;
+        first = false;
+      }
+    }
+    if (++slot == kGmStages) { slot = 0; phase ^= 1u; }
+  }
+  __syncthreads();           // every warp of the CTA is done with the rings: they become the tile buffer
+  for (int e = threadIdx.x; e < (T2 * (T2 + 1) / 2) * 64; e += blockDim.x) red[e] = 0.0;
+  __syncthreads();
+
+  // the warps add their accumulators into one tile set, one warp after the other (fixed order)
+  const int e0 = (lane >> 2) * 8 + 2 * (lane & 3);
+#pragma unroll 1
+  for (int w = 0; w < nwarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) {
+        double* d = red + (size_t)(T_LO + t) * 64 + e0;
+        d[0] += acc[t][0];
+        d[1] += acc[t][1];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int T2, int T0, bool HAS_M, int WARPS, int P>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double* __restrict__ part,
+           int64_t N, int64_t ldw, int K) {
+  pdl_sync();
+  constexpr int NT = T2 * (T2 + 1) / 2;
+  constexpr int TEAMS = WARPS / P;
+  constexpr int J0 = gram_mid_split(T2, HAS_M, T0);
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp % TEAMS, role = warp / TEAMS;      // partners sit on the same sub-partition
+  const int stage_elems = kGmRows * K + 3 * kGmRows;
+  double* ring = sm + (size_t)team * kGmStages * stage_elems;
+  unsigned long long* bars =
+      reinterpret_cast<unsigned long long*>(sm + (size_t)TEAMS * kGmStages * stage_elems) + team * kGmStages * 2;
+  const unsigned ring_u = smem_u32(ring), full_u = smem_u32(bars), empty_u = full_u + 8 * kGmStages;
+  if (role == 0 && lane == 0) {
+#pragma unroll
+    for (int p = 0; p < kGmStages; ++p) {
+      mbar_init(full_u + 8 * p, 1);
+      mbar_init(empty_u + 8 * p, P);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int gt = (int)blockIdx.x * TEAMS + team, tt = (int)gridDim.x * TEAMS;
+  double* red = sm;          // the rings are reused as the (NT, 64) tile buffer at the end
+  if (P == 1) {
+    gram_mid_run<T2, T0, HAS_M, 1, 0, T2, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
+                                                 warp, WARPS);
+  } else if (role == 0) {
+    gram_mid_run<T2, T0, HAS_M, 2, 0, J0, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
+                                                 warp, WARPS);
+  } else {
+    gram_mid_run<T2, T0, HAS_M, 2, J0, T2, false>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
+                                                   warp, WARPS);
+  }
+  double* out = part + (size_t)blockIdx.x * NT * 64;
+  for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) out[e] = red[e];
+}
+
+// launch the instantiation for K (20 < K <= 52); false when K / alignment is outside its range
+inline bool launch_gram_mid(const double* X, const double* Wabc, double* part, int64_t N, int64_t ldw,
+                            int K, int grid, cudaStream_t st) {
+  if (K <= 20 || K > kGmMaxK || (ldw & 1) || (((uintptr_t)X) & 15) || (((uintptr_t)Wabc) & 15)) return false;
+  const int T2 = (2 * K + 7) / 8, T0 = K / 8;
+  const bool M = (K % 8) != 0;
+  const size_t smem = gram_mid_smem(K, T2);
+#define LRVB_GM(T2_, T0_, M_)                                                                       \
+  if (T2 == T2_ && T0 == T0_ && M == M_) {                                                          \
+    constexpr GramMidGeom g = gram_mid_geom(T2_);                                                   \
+    static size_t configured = 48 * 1024;                                                           \
+    if (smem > configured) {                                                                        \
+      cudaFuncSetAttribute(k_gram_mid<T2_, T0_, M_, g.warps, g.P>,                                  \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+      configured = smem;                                                                            \
+    }                                                                                               \
+    return launch_pdl(k_gram_mid<T2_, T0_, M_, g.warps, g.P>, dim3(grid), dim3(32 * g.warps), smem, st, X, \
+                      Wabc, part, N, ldw, K) == cudaSuccess;                                        \
+  }
+  LRVB_GM(6, 2, true)
+  LRVB_GM(6, 3, false)
+  LRVB_GM(7, 3, true)
+  LRVB_GM(8, 3, true)
+  LRVB_GM(8, 4, false)
+  LRVB_GM(9, 4, true)
+  LRVB_GM(10, 4, true)
+  LRVB_GM(10, 5, false)
+  LRVB_GM(11, 5, true)
+  LRVB_GM(12, 5, true)
+  LRVB_GM(12, 6, false)
+  LRVB_GM(13, 6, true)
+#undef LRVB_GM
+  return false;
+}
+
+}  // namespace lrvb
