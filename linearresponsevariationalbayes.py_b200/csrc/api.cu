@@ -191,7 +191,7 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   // Gram geometry
   {
     size_t npart;
-    if (K <= 20) {
+    if (K <= 20 && !(getenv("LRVB_GRAM_SMALL") && getenv("LRVB_GRAM_SMALL")[0] == '0')) {
       // small K: every warp owns the whole packed upper triangle (gram_small.cuh), one CTA per SM
       h->gram_small = 1;
       h->gram_grid_x = kNumSMs;

@@ -277,7 +277,7 @@ k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double
 // launch the instantiation for K (20 < K <= 52); false when K / alignment is outside its range
 inline bool launch_gram_mid(const double* X, const double* Wabc, double* part, int64_t N, int64_t ldw,
                             int K, int grid, cudaStream_t st) {
-  if (K <= 20 || K > kGmMaxK || (ldw & 1) || (((uintptr_t)X) & 15) || (((uintptr_t)Wabc) & 15)) return false;
+  if (K < 1 || K > kGmMaxK || (ldw & 1) || (((uintptr_t)X) & 15) || (((uintptr_t)Wabc) & 15)) return false;
   const int T2 = (2 * K + 7) / 8, T0 = K / 8;
   const bool M = (K % 8) != 0;
   const size_t smem = gram_mid_smem(K, T2);
@@ -293,6 +293,13 @@ inline bool launch_gram_mid(const double* X, const double* Wabc, double* part, i
     return launch_pdl(k_gram_mid<T2_, T0_, M_, g.warps, g.P>, dim3(grid), dim3(32 * g.warps), smem, st, X, \
                       Wabc, part, N, ldw, K) == cudaSuccess;                                        \
   }
+  LRVB_GM(1, 0, true)
+  LRVB_GM(2, 0, true)
+  LRVB_GM(2, 1, false)
+  LRVB_GM(3, 1, true)
+  LRVB_GM(4, 1, true)
+  LRVB_GM(4, 2, false)
+  LRVB_GM(5, 2, true)
   LRVB_GM(6, 2, true)
   LRVB_GM(6, 3, false)
   LRVB_GM(7, 3, true)

@@ -39,6 +39,18 @@ CASES = {
     # several job groups of the rectangle Gram kernel, 16-row stages; zero weights among the rest
     "k130_job_groups": dict(N=1100, K=130, G=11, Q=4, seed=23),
     "k21_odd_rows_not_tma": dict(N=2100, K=21, G=20, Q=8, seed=24, weights=True),
+    # k_gram_mid: every tile-grid size of the two-warp teams (T2 = 9 .. 13, with and without a straddle
+    # tile), ragged last stage (N not a multiple of 16), and enough rows that a team's 3-slot ring wraps
+    # (148 SMs x 4 teams x 16 rows x 3 slots = 28k rows) with the producer one stage ahead of its partner
+    "k36_team": dict(N=2501, K=36, G=25, Q=8, seed=25),
+    "k37_team": dict(N=2500, K=37, G=25, Q=6, seed=26, weights=True),
+    "k40_team": dict(N=2503, K=40, G=20, Q=8, seed=27),
+    "k44_team_ragged": dict(N=3011, K=44, G=30, Q=8, seed=28, ragged=True),
+    "k47_team": dict(N=2005, K=47, G=20, Q=4, seed=29),
+    "k48_team": dict(N=2000, K=48, G=20, Q=4, seed=30, weights=True),
+    "k52_team": dict(N=1999, K=52, G=20, Q=4, seed=31),
+    "k50_team_ring_wrap": dict(N=70003, K=50, G=70, Q=4, seed=32, weights=True),
+    "k28_ring_wrap": dict(N=120011, K=28, G=120, Q=4, seed=33),
 }
 
 
