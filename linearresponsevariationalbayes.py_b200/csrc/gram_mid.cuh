@@ -260,15 +260,17 @@ k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double
   __syncthreads();
   const int gt = (int)blockIdx.x * TEAMS + team, tt = (int)gridDim.x * TEAMS;
   double* red = sm;          // the rings are reused as the (NT, 64) tile buffer at the end
-  if (P == 1) {
+  if constexpr (P == 1) {
     gram_mid_run<T2, T0, HAS_M, 1, 0, T2, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
                                                  warp, WARPS);
-  } else if (role == 0) {
-    gram_mid_run<T2, T0, HAS_M, 2, 0, J0, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
-                                                 warp, WARPS);
   } else {
-    gram_mid_run<T2, T0, HAS_M, 2, J0, T2, false>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
+    if (role == 0) {
+      gram_mid_run<T2, T0, HAS_M, 2, 0, J0, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
                                                    warp, WARPS);
+    } else {
+      gram_mid_run<T2, T0, HAS_M, 2, J0, T2, false>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt,
+                                                     tt, warp, WARPS);
+    }
   }
   double* out = part + (size_t)blockIdx.x * NT * 64;
   for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) out[e] = red[e];
