@@ -391,7 +391,7 @@ def run_ours(args, wl):
                 traffic = json.load(open(tpath)).get(args.workload, {})
             except Exception:
                 traffic = {}
-        gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K <= 20 else
+        gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
                        "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp pair)" if K <= 52 else
                        "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
         roof_gram = {"bound": "tensor", "kernel": gram_kernel,

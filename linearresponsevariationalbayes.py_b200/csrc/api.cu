@@ -191,7 +191,11 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   // Gram geometry
   {
     size_t npart;
-    if (K <= 20 && !(getenv("LRVB_GRAM_SMALL") && getenv("LRVB_GRAM_SMALL")[0] == '0')) {
+    // K < 16: gram_small (register prefetch pays when a k-step is only a handful of DMMAs); from 16 on
+    // gram_mid's 16 warps without prefetch are 3-4 % faster (profiles/r01_gram_mid_sweep.log)
+    const char* gs_env = getenv("LRVB_GRAM_SMALL");
+    const int gs_max = gs_env ? (gs_env[0] == '0' ? 0 : 20) : 15;
+    if (K <= gs_max) {
       // small K: every warp owns the whole packed upper triangle (gram_small.cuh), one CTA per SM
       h->gram_small = 1;
       h->gram_grid_x = kNumSMs;
