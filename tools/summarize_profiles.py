@@ -58,6 +58,29 @@ def launches(path, out, title):
         f.write("| total | %.1f | |\n" % tot)
 
 
+def launches_agg(path, out, title):
+    """Whole-command launch list aggregated by kernel: count, mean duration, share of the summed
+    duration of OUR kernels (lrvb::*)."""
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5 and r[0].isdigit()]
+    agg, order = {}, []
+    for r in rows:
+        v, u = float(r[-1]), r[-2]
+        v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
+        n = r[4].split("(")[0]
+        if n not in agg:
+            agg[n] = [0, 0.0]
+            order.append(n)
+        agg[n][0] += 1
+        agg[n][1] += v
+    ours = sum(t for n, (c, t) in agg.items() if "lrvb::" in n)
+    with open(out, "w") as f:
+        f.write("# %s\n\n(every launch of the command; cold-cache, serialised under ncu: compare SHARES)\n\n" % title)
+        f.write("| kernel | launches | mean us | share of lrvb:: time |\n|---|---|---|---|\n")
+        for n in order:
+            c, t = agg[n]
+            f.write("| %s | %d | %.1f | %s |\n" % (n, c, t / c, ("%.1f%%" % (100 * t / ours)) if "lrvb::" in n else "-"))
+
+
 def ncu(out, title, reps):
     with open(out, "w") as f:
         f.write("# %s\n" % title)
@@ -92,6 +115,8 @@ if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "launches":
         launches(*sys.argv[2:5])
+    elif cmd == "launches_agg":
+        launches_agg(*sys.argv[2:5])
     elif cmd == "ncu":
         ncu(sys.argv[2], sys.argv[3], sys.argv[4:])
     elif cmd == "traffic":
