@@ -392,7 +392,7 @@ def run_ours(args, wl):
             except Exception:
                 traffic = {}
         gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
-                       "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp pair)" if K <= 52 else
+                       "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
                        "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
         roof_gram = {"bound": "tensor", "kernel": gram_kernel,
                      "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12, "peak": peak_tf,

@@ -25,7 +25,7 @@ namespace lrvb {
 
 constexpr int kGmRows = 16;       // rows per stage (4 k-steps)
 constexpr int kGmStages = 3;      // ring depth per team
-constexpr int kGmMaxK = 52;       // T2 = ceil(2K / 8) <= 13
+constexpr int kGmMaxK = 104;      // T2 = ceil(2K / 8) <= 26
 
 // launch geometry by tile-grid size: T2 <= 8 leaves room for 12 single-warp teams at 168 registers;
 // 9 and 10 need the 255-register budget (8 warps); from 11 on the triangle is split between the two
@@ -33,20 +33,36 @@ constexpr int kGmMaxK = 52;       // T2 = ceil(2K / 8) <= 13
 struct GramMidGeom {
   int warps, P;
 };
+// T2 <= 8: 12-16 single-warp teams at <= 168 registers; 9..13: pairs of warps; 14..18: teams of four;
+// 19..26: one team of eight (8 warps x 255 registers from T2 = 11 on)
 __host__ __device__ constexpr GramMidGeom gram_mid_geom(int T2) {
-  return T2 <= 6 ? GramMidGeom{16, 1} : (T2 <= 8 ? GramMidGeom{12, 1} : (T2 <= 10 ? GramMidGeom{12, 2} : GramMidGeom{8, 2}));
+  return T2 <= 6 ? GramMidGeom{16, 1}
+       : T2 <= 8 ? GramMidGeom{12, 1}
+       : T2 <= 10 ? GramMidGeom{12, 2}
+       : T2 <= 13 ? GramMidGeom{8, 2}
+       : T2 <= 18 ? GramMidGeom{8, 4} : GramMidGeom{8, 8};
 }
-// first column tile of the second warp of a team: balances the DMMA counts of the two halves
-__host__ __device__ constexpr int gram_mid_split(int T2, bool has_m, int T0) {
-  int best = 1, best_max = 1 << 30;
-  const int total = T2 * (T2 + 1) / 2 + (has_m ? 1 : 0);
-  for (int j0 = 1; j0 < T2; ++j0) {
-    const int a = j0 * (j0 + 1) / 2 + ((has_m && T0 < j0) ? 1 : 0);
-    const int b = total - a;
-    const int m = a > b ? a : b;
-    if (m < best_max) { best_max = m; best = j0; }
+// Tiles of the packed upper triangle in column-major order: t(i, j) = j (j + 1) / 2 + i, i <= j.  Role r
+// of a P-warp team owns the tiles [bound(r), bound(r + 1)): equal DMMA counts (the diagonal straddle
+// tile costs two).
+__host__ __device__ constexpr int gram_mid_col(int t) {
+  int j = 0;
+  while ((j + 1) * (j + 2) / 2 <= t) ++j;
+  return j;
+}
+__host__ __device__ constexpr int gram_mid_bound(int T2, int T0, bool has_m, int P, int r) {
+  const int NT = T2 * (T2 + 1) / 2;
+  if (r <= 0) return 0;
+  if (r >= P) return NT;
+  const int ts = has_m ? T0 * (T0 + 1) / 2 + T0 : -1;      // the straddle diagonal tile
+  const int total = NT + (has_m ? 1 : 0);
+  const int want = (int)(((long long)total * r + P / 2) / P);
+  int acc = 0;
+  for (int t = 0; t < NT; ++t) {
+    if (acc >= want) return t;
+    acc += (t == ts) ? 2 : 1;
   }
-  return best;
+  return NT;
 }
 __host__ __device__ inline size_t gram_mid_stage_elems(int K) { return (size_t)kGmRows * K + 3 * kGmRows; }
 inline size_t gram_mid_smem(int K, int T2) {
@@ -60,15 +76,17 @@ inline size_t gram_mid_smem(int K, int T2) {
 
 // The stream of one warp: column tiles [JLO, JHI) of the packed upper triangle over the stages of
 // its team.  PRODUCER issues the bulk copies (the first warp of a team).
-template <int T2, int T0, bool HAS_M, int P, int JLO, int JHI, bool PRODUCER>
+template <int T2, int T0, bool HAS_M, int P, int TLO, int THI, bool PRODUCER>
 __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const double* __restrict__ Wabc,
                                              double* __restrict__ red, int64_t N, int64_t ldw, int K,
                                              unsigned ring_u, unsigned full_u, unsigned empty_u, double* ring,
                                              int gt, int tt, int warp, int nwarps) {
   constexpr int TS = HAS_M ? T0 : -1;        // straddle tile
   constexpr int TB = HAS_M ? T0 + 1 : T0;    // first pure-s tile
-  constexpr int T_LO = JLO * (JLO + 1) / 2;
-  constexpr int NTL = JHI * (JHI + 1) / 2 - T_LO;     // accumulator tiles of this warp
+  constexpr int JLO = gram_mid_col(TLO), JHI = gram_mid_col(THI - 1) + 1;   // column tiles touched
+  constexpr int T_LO = TLO;
+  constexpr int NTL = THI - TLO;                       // accumulator tiles of this warp
+  auto mine = [](int i, int j) constexpr { return j * (j + 1) / 2 + i >= TLO && j * (j + 1) / 2 + i < THI; };
   constexpr int KSTEPS = kGmRows / 4;
   const int lane = threadIdx.x & 31;
   const int lr = lane & 3, lc = lane >> 2;
@@ -176,22 +194,30 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
 #pragma unroll
       for (int j = JLO; j < JHI; ++j) {
         const int cb = j * (j + 1) / 2 - T_LO;
-        // B operands of column tile j: x rows see (a | b), s rows see c
-        double bw0 = 0.0, bc = 0.0;
-        if (T0 > 0 || j == TS) bw0 = vmul(z[j], (j < T0) ? wa : ((j == TS) ? (cls1 ? wb : wa) : wb));
-        if (j >= TB) bc = vmul(z[j], wc);
+        // B operands of column tile j: x rows see (a | b), s rows see c -- formed only when this
+        // warp owns such a tile of the column (the conditions fold at compile time)
+        bool need0 = (HAS_M && j == TS && mine(j, j)), needc = false;
 #pragma unroll
         for (int i = 0; i < T0; ++i)
-          if (i <= j) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bw0);
-        if (HAS_M && j == TS) {
+          if (i <= j && mine(i, j)) need0 = true;
+#pragma unroll
+        for (int i = TB; i < T2; ++i)
+          if (i <= j && mine(i, j)) needc = true;
+        double bw0 = 0.0, bc = 0.0;
+        if (need0) bw0 = vmul(z[j], (j < T0) ? wa : ((j == TS) ? (cls1 ? wb : wa) : wb));
+        if (needc) bc = vmul(z[j], wc);
+#pragma unroll
+        for (int i = 0; i < T0; ++i)
+          if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bw0);
+        if (HAS_M && j == TS && mine(j, j)) {
           dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? 0.0 : z[j], bw0);   // x rows of the tile
           dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? z[j] : 0.0, aw2);   // s rows of the tile
         }
-        if (HAS_M && j > TS)
+        if (HAS_M && j > TS && mine(HAS_M ? TS : 0, j))
           dmma884(acc[cb + (HAS_M ? TS : 0)][0], acc[cb + (HAS_M ? TS : 0)][1], aw2, z[j]);
 #pragma unroll
         for (int i = TB; i < T2; ++i)
-          if (i <= j) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bc);
+          if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bc);
       }
     }
     __syncwarp();            // every lane has read its last operands of this slot
@@ -233,6 +259,25 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
   }
 }
 
+// role r of the team runs the instantiation for its tile range; role 0 is the producer
+template <int T2, int T0, bool HAS_M, int P, int R>
+__device__ __forceinline__ void gram_mid_dispatch(int role, const double* __restrict__ X,
+                                                  const double* __restrict__ Wabc, double* __restrict__ red,
+                                                  int64_t N, int64_t ldw, int K, unsigned ring_u, unsigned full_u,
+                                                  unsigned empty_u, double* ring, int gt, int tt, int warp,
+                                                  int nwarps) {
+  if constexpr (R < P) {
+    if (role == R) {
+      constexpr int LO = gram_mid_bound(T2, T0, HAS_M, P, R), HI = gram_mid_bound(T2, T0, HAS_M, P, R + 1);
+      gram_mid_run<T2, T0, HAS_M, P, LO, HI, R == 0>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt,
+                                                      tt, warp, nwarps);
+    } else {
+      gram_mid_dispatch<T2, T0, HAS_M, P, R + 1>(role, X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt,
+                                                 tt, warp, nwarps);
+    }
+  }
+}
+
 template <int T2, int T0, bool HAS_M, int WARPS, int P>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double* __restrict__ part,
@@ -240,7 +285,6 @@ k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double
   pdl_sync();
   constexpr int NT = T2 * (T2 + 1) / 2;
   constexpr int TEAMS = WARPS / P;
-  constexpr int J0 = gram_mid_split(T2, HAS_M, T0);
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp % TEAMS, role = warp / TEAMS;      // partners sit on the same sub-partition
@@ -260,18 +304,8 @@ k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double
   __syncthreads();
   const int gt = (int)blockIdx.x * TEAMS + team, tt = (int)gridDim.x * TEAMS;
   double* red = sm;          // the rings are reused as the (NT, 64) tile buffer at the end
-  if constexpr (P == 1) {
-    gram_mid_run<T2, T0, HAS_M, 1, 0, T2, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
-                                                 warp, WARPS);
-  } else {
-    if (role == 0) {
-      gram_mid_run<T2, T0, HAS_M, 2, 0, J0, true>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt,
-                                                   warp, WARPS);
-    } else {
-      gram_mid_run<T2, T0, HAS_M, 2, J0, T2, false>(X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt,
-                                                     tt, warp, WARPS);
-    }
-  }
+  gram_mid_dispatch<T2, T0, HAS_M, P, 0>(role, X, Wabc, red, N, ldw, K, ring_u, full_u, empty_u, ring, gt, tt, warp,
+                                         WARPS);
   double* out = part + (size_t)blockIdx.x * NT * 64;
   for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) out[e] = red[e];
 }
@@ -314,6 +348,26 @@ inline bool launch_gram_mid(const double* X, const double* Wabc, double* part, i
   LRVB_GM(12, 5, true)
   LRVB_GM(12, 6, false)
   LRVB_GM(13, 6, true)
+  LRVB_GM(14, 6, true)
+  LRVB_GM(14, 7, false)
+  LRVB_GM(15, 7, true)
+  LRVB_GM(16, 7, true)
+  LRVB_GM(16, 8, false)
+  LRVB_GM(17, 8, true)
+  LRVB_GM(18, 8, true)
+  LRVB_GM(18, 9, false)
+  LRVB_GM(19, 9, true)
+  LRVB_GM(20, 9, true)
+  LRVB_GM(20, 10, false)
+  LRVB_GM(21, 10, true)
+  LRVB_GM(22, 10, true)
+  LRVB_GM(22, 11, false)
+  LRVB_GM(23, 11, true)
+  LRVB_GM(24, 11, true)
+  LRVB_GM(24, 12, false)
+  LRVB_GM(25, 12, true)
+  LRVB_GM(26, 12, true)
+  LRVB_GM(26, 13, false)
 #undef LRVB_GM
   return false;
 }

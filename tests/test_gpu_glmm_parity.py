@@ -51,6 +51,11 @@ CASES = {
     "k52_team": dict(N=1999, K=52, G=20, Q=4, seed=31),
     "k50_team_ring_wrap": dict(N=70003, K=50, G=70, Q=4, seed=32, weights=True),
     "k28_ring_wrap": dict(N=120011, K=28, G=120, Q=4, seed=33),
+    # teams of four (T2 14..18) and eight (T2 19..26) warps with tile-range roles
+    "k56_team4": dict(N=1503, K=56, G=15, Q=4, seed=34),
+    "k72_team4": dict(N=1200, K=72, G=12, Q=4, seed=35, weights=True),
+    "k77_team8": dict(N=1101, K=77, G=11, Q=4, seed=36),
+    "k104_team8_ring_wrap": dict(N=10007, K=104, G=10, Q=4, seed=37),
 }
 
 
