@@ -33,14 +33,15 @@ constexpr int kGmMaxK = 104;      // T2 = ceil(2K / 8) <= 26
 struct GramMidGeom {
   int warps, P;
 };
-// T2 <= 8: 12-16 single-warp teams at <= 168 registers; 9..13: pairs of warps; 14..18: teams of four;
-// 19..26: one team of eight (8 warps x 255 registers from T2 = 11 on)
+// T2 <= 8: 12-16 single-warp teams at <= 168 registers; 9..13: pairs of warps; 14..20: teams of four;
+// 21..26: one team of eight (8 warps x 255 registers from T2 = 11 on).  Fewer, larger roles amortise the
+// operand fetch of a k-step over more DMMAs: as few warps per team as the 255-register budget allows
 __host__ __device__ constexpr GramMidGeom gram_mid_geom(int T2) {
   return T2 <= 6 ? GramMidGeom{16, 1}
        : T2 <= 8 ? GramMidGeom{12, 1}
        : T2 <= 10 ? GramMidGeom{12, 2}
        : T2 <= 13 ? GramMidGeom{8, 2}
-       : T2 <= 18 ? GramMidGeom{8, 4} : GramMidGeom{8, 8};
+       : T2 <= 20 ? GramMidGeom{8, 4} : GramMidGeom{8, 8};
 }
 // Tiles of the packed upper triangle in column-major order: t(i, j) = j (j + 1) / 2 + i, i <= j.  Role r
 // of a P-warp team owns the tiles [bound(r), bound(r + 1)): equal DMMA counts (the diagonal straddle
