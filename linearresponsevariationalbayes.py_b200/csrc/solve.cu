@@ -5,6 +5,7 @@
 // .get_hinv_vec (ConjugateGradient.py:81-85 -> scipy.sparse.linalg.cg) and the dense
 // cho_factor / cho_solve of ModelSensitivity.py:594-602 for the GLMM Hessian
 //      H = [[A, B^T], [B, L]],   A (Dg,Dg) dense, B (G,2,Dg), L = G independent 2x2 blocks.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace lrvb {
@@ -624,6 +625,60 @@ k_spd_inverse(double* __restrict__ S, int n, int* __restrict__ info, int use_sme
   if (tid == 0) *info = bad;
 }
 
+// ---- 128 < n <= 234: symmetric sweeps on the packed lower triangle in shared memory ---------------
+// The full n x n matrix no longer fits in shared memory beyond n = 167, its lower triangle does up
+// to n = 234 (K = 115).  The sweep operator keeps the matrix symmetric at every step:
+//   SWP(k):  A_kk <- -1 / A_kk,   A_ik <- A_ik / A_kk,   A_ij <- A_ij - A_ik A_jk / A_kk   (i, j != k)
+// and after all n sweeps A = -S^-1.  Two barriers per pivot, every element touched once per pivot.
+constexpr int kSpdPackedMax = 234;
+// One SM's shared-memory bandwidth bounds this kernel (every element is read and written once per
+// pivot: ~n^2 / 2 * 24 B at 128 B / clock); rows are striped over groups of 8 lanes so that the pivot
+// column entry of a row is fetched once per row (a flat element-per-thread mapping, perfectly balanced,
+// measured 15 % slower because it fetches two column entries per element).
+__global__ void __launch_bounds__(1024)
+k_spd_inverse_packed(double* __restrict__ S, int n, int* __restrict__ info) {
+  pdl_sync();
+  extern __shared__ double sm[];
+  double* __restrict__ col = sm;            // n   pivot column A_ik (all i)
+  double* __restrict__ A = sm + n;          // n (n + 1) / 2, row-major lower triangle: (i, j <= i) at i (i + 1) / 2 + j
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid >> 3; i < n; i += nt >> 3)
+    for (int j = tid & 7; j <= i; j += 8) A[i * (i + 1) / 2 + j] = S[(size_t)i * n + j];
+  __syncthreads();
+  const int TJ = 8, TI = nt / TJ;
+  const int i0 = tid / TJ, jj = tid - i0 * TJ;
+  int bad = 0;
+  for (int k = 0; k < n; ++k) {
+    const double d = A[k * (k + 1) / 2 + k];
+    if (!(d > 0.0)) {          // uniform: every thread reads the same pivot
+      bad = k + 1;
+      break;
+    }
+    for (int i = tid; i < n; i += nt) col[i] = (i >= k) ? A[i * (i + 1) / 2 + k] : A[k * (k + 1) / 2 + i];
+    __syncthreads();
+    const double pinv = 1.0 / d;
+    for (int i = i0; i < n; i += TI) {
+      double* __restrict__ ai = A + i * (i + 1) / 2;
+      const double ci = col[i] * pinv;
+      if (i == k) {
+        for (int j = jj; j <= i; j += TJ) ai[j] = (j == k) ? -pinv : col[j] * pinv;
+      } else {
+#pragma unroll 4
+        for (int j = jj; j <= i; j += TJ) ai[j] = (j == k) ? ci : fma(-ci, col[j], ai[j]);
+      }
+    }
+    __syncthreads();
+  }
+  if (!bad)
+    for (int i = tid >> 3; i < n; i += nt >> 3)
+      for (int j = tid & 7; j <= i; j += 8) {
+        const double v = -A[i * (i + 1) / 2 + j];
+        S[(size_t)i * n + j] = v;
+        S[(size_t)j * n + i] = v;
+      }
+  if (tid == 0) *info = bad;
+}
+
 // ---- direct solve by block elimination -----------------------------------------------------------
 // rhs_g = [b_g] - sum_g B_g^T L_g^-1 b_l,g     (per right-hand side; per-CTA partials)
 __global__ void __launch_bounds__(256)
@@ -989,6 +1044,10 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
     else LRVB_SPD(16);
 #undef LRVB_SPD
     LRVB_CUDA(le);
+  } else if (n <= kSpdPackedMax && !(getenv("LRVB_SPD_PACKED") && getenv("LRVB_SPD_PACKED")[0] == '0')) {
+    const size_t psm = sizeof(double) * ((size_t)n + (size_t)n * (n + 1) / 2);
+    cudaFuncSetAttribute(k_spd_inverse_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    LRVB_CUDA(launch_pdl(k_spd_inverse_packed, dim3(1), dim3(1024), psm, st, S_dev, (int)n, dinfo));
   } else {
     cudaFuncSetAttribute(k_spd_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LRVB_CUDA(launch_pdl(k_spd_inverse, dim3(1), dim3(1024), smem, st, S_dev, n, dinfo, use_smem));
