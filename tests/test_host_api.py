@@ -210,3 +210,23 @@ def test_json_csr_wire_format_round_trip(vb):
     np.testing.assert_array_equal(back.indices, m.indices)
     np.testing.assert_array_equal(back.data, m.data)
     assert back.indices.dtype == m.indices.dtype
+
+
+def test_point_key_identity_semantics():
+    """Evaluation points are remembered by value for numpy input and by identity + torch's in-place
+    version counter for tensors (no device read-back): an in-place update must invalidate the key."""
+    import torch
+    from lrvb_b200._tensors import PointKey
+    x = np.arange(5.0)
+    k = PointKey(x)
+    assert k.matches(x) and k.matches(x.copy())
+    x[2] = 7.0
+    assert not k.matches(x)              # the key holds its own copy
+    t = torch.arange(5.0, dtype=torch.float64)
+    kt = PointKey(t)
+    assert kt.matches(t) and kt.matches(t.view(5))       # same storage, same version
+    assert not kt.matches(t.clone())                     # equal values, another tensor: evaluated again
+    assert not kt.matches(x)                             # kinds do not mix
+    t.add_(1.0)
+    assert not kt.matches(t)                             # in-place update bumps the version
+    assert not PointKey(x).matches(t)
