@@ -92,6 +92,13 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves separately.  A kernel that calls pdl_wait() BEFORE pdl_launch_dependents() lets its
+// dependent start only once this kernel's own prerequisite has completed: the dependent may then read,
+// ahead of its own wait, everything written by kernels EARLIER than this one (k_finish -> k_global).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t st, Args... args) {

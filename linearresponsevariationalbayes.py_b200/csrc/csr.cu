@@ -142,8 +142,23 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
            int32_t* __restrict__ chunkcnt, const int32_t* __restrict__ chunkoff,
            const int32_t* __restrict__ coltot, int32_t* __restrict__ rowcnt,
            const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data) {
-  pdl_sync();
   const int bid = blockIdx.x;
+  if (!FILL && bid >= nA) {
+    // Counting the border columns and the local rows needs B and L only.  Those are written by
+    // k_finish, and every path to this kernel passes k_global, which signals its dependents after its
+    // own wait: B and L are complete when this CTA starts, so it counts ahead of the wait, behind
+    // k_global (one CTA) which is still finishing A.  The arrays written here (chunkcnt, rowcnt) are
+    // not read by a fill pass that might still be running in front of this kernel.
+    pdl_launch_dependents();
+    if (bid < nA + nB) {
+      csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
+    } else {
+      csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data);
+    }
+    pdl_wait();        // completion of this kernel still implies completion of its prerequisite
+    return;
+  }
+  pdl_sync();
   if (bid < nA) {
     csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data);
   } else if (bid < nA + nB) {

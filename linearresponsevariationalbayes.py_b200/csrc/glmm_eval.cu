@@ -443,7 +443,10 @@ k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const d
          double* __restrict__ locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
          const GbSlot* __restrict__ slots, double* __restrict__ A, int K, int G, int n_loc, int n_bor,
          int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode) {
-  pdl_sync();
+  // wait first: k_global, the dependent, reads the observation pass's partials ahead of its own wait and
+  // may only be scheduled once everything before this kernel has completed
+  pdl_wait();
+  pdl_launch_dependents();
   const int bid = blockIdx.x;
   const int Dg = 4 + 2 * K;
   if (bid < n_loc) {
@@ -470,7 +473,11 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
          const double* __restrict__ gradpart, int n_gp, const double* __restrict__ locpart,
          int n_lp, double* __restrict__ out, int K, int G, lrvb_glmm_prior pr,
          lrvb_glmm_bounds bd, int include_global, int vecmode) {
-  pdl_sync();
+  // Programmatic dependent launch: this CTA is resident while k_finish, its prerequisite, still runs.
+  // k_finish signals its dependents only after its own wait, so every kernel before it -- k_prep (vec)
+  // and the observation pass (klpart, gradpart) -- has completed: the special functions and the
+  // reductions over those partials run here, hidden behind k_finish; only the group-level partials
+  // (locpart) and the global block A need the wait.
   __shared__ double red[32];
   __shared__ double sh[8];
   extern __shared__ double gsum[];  // 2K
@@ -486,6 +493,17 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
   double v = 0.0;
   for (int i = tid; i < n_kl; i += blockDim.x) v += klpart[i];
   const double data_ll = block_sum(v, red);
+  if (ORDER >= 1) {
+    // one warp per column, lanes over the per-CTA partials (fixed order: deterministic)
+    for (int k = tid >> 5; k < 2 * K; k += blockDim.x >> 5) {
+      double s = 0.0;
+      for (int p = tid & 31; p < n_gp; p += 32) s += gradpart[(size_t)k * n_gp + p];
+      s = warp_sum(s);
+      if ((tid & 31) == 0) gsum[k] = s;
+    }
+  }
+  pdl_wait();                       // k_finish has completed: locpart, A
+  pdl_launch_dependents();          // after the wait: the CSR count pass reads B and L ahead of ITS wait
   double d0 = 0, d1 = 0, d2 = 0;
   for (int i = tid; i < n_lp; i += blockDim.x) {
     d0 += locpart[i * 4 + 0];
@@ -496,15 +514,6 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
   d1 = block_sum(d1, red);
   d2 = block_sum(d2, red);
   if (tid == 0) { sh[0] = data_ll; sh[1] = d0; sh[2] = d1; sh[3] = d2; }
-  if (ORDER >= 1) {
-    // one warp per column, lanes over the per-CTA partials (fixed order: deterministic)
-    for (int k = tid >> 5; k < 2 * K; k += blockDim.x >> 5) {
-      double s = 0.0;
-      for (int p = tid & 31; p < n_gp; p += 32) s += gradpart[(size_t)k * n_gp + p];
-      s = warp_sum(s);
-      if ((tid & 31) == 0) gsum[k] = s;
-    }
-  }
   __syncthreads();
   const double ll = sh[0], dsum = sh[1], Ssum = sh[2], logsum = sh[3];
   const double mu_m = vec[0], mu_i = vec[1], a = vec[2], b = vec[3];
