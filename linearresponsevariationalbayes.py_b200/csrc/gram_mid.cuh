@@ -1,21 +1,23 @@
-// Weighted Grams of the beta block for 20 < K <= 52 on the FP64 tensor cores (DMMA.8x8x4), sm_100a.
+// Weighted Grams of the beta block for 16 <= K <= 104 on the FP64 tensor cores (DMMA.8x8x4), sm_100a.
 //
 // Same packed formulation as gram_small.cuh (ONE weighted Gram of z = [x | s], upper triangle of
 // the T2 x T2 tile grid, tile classes pure-x / straddle / pure-s) and the same execution model:
-// EVERY WARP OWNS THE WHOLE TRIANGLE for its rows, streams its own stages through a private
-// shared-memory ring filled by bulk async copies, and all warps of all CTAs do identical work --
-// so the four FP64 pipes of an SM are evenly loaded, which the rectangle jobs of gram_big.cuh
-// never quite achieve (0.52 - 0.63 of the DMMA peak there).  What changes against gram_small is
-// the register budget: up to NT = 91 accumulator tiles (182 registers) per thread at T2 = 13, so
-//   * a CTA has 8 warps (12 for T2 <= 9) at up to 255 registers, one CTA per SM;
-//   * there is no register prefetch of the next k-step: a k-step is 23 - 92 independent DMMAs
-//     (370 - 1470 pipe cycles), the second warp of the sub-partition covers the ~100 cycles in which
-//     the first one fetches its 13 operands;
-//   * the weighted B operands are formed per column tile right before its DMMAs instead of for the
-//     whole k-step up front;
-//   * the per-lane offsets of the packed columns are compile-time constants plus one base;
-//   * the CTA's warps add their accumulators into one shared tile set one after the other (fixed
-//     order) because 8 x 91 tiles do not fit in shared memory at once.
+// the WHOLE TRIANGLE is owned, for a set of rows, by one warp -- or by a TEAM of 2 / 4 / 8 warps when
+// its NT = T2 (T2 + 1) / 2 accumulator tiles do not fit the registers of one (2 registers per tile and
+// thread; 255 registers per thread at 8 warps per SM).  A team streams its own 16-row stages through
+// a private shared-memory ring filled by bulk async copies, and all teams of all CTAs do identical
+// work, so the four FP64 pipes of an SM are evenly loaded -- which the rectangle jobs of gram_big.cuh
+// never quite achieve (0.29 - 0.63 of the DMMA peak on the same sizes, 0.73 - 0.85 here).
+//   * Roles: the tiles in column-major order are cut into P contiguous ranges of equal DMMA count
+//     (gram_mid_bound); role r of a team is a separate instantiation with compile-time tile indices.
+//     The fewer warps per team the better (a k-step's operand fetch is amortised over more DMMAs):
+//     P = 1 up to T2 = 8, 2 up to 13, 4 up to 20, 8 up to 26.
+//   * Ring: full / empty mbarriers per slot; role 0 issues the copies and refills a slot one stage late,
+//     so it may run a stage ahead of its partners instead of meeting them at every stage.
+//   * No register prefetch of the next k-step: a k-step is 16 - 46 independent DMMAs per warp, the other
+//     warps of the sub-partition cover the operand fetch.  B operands are weighted per column tile right
+//     before its DMMAs; the per-lane offsets of the packed columns are compile-time constants plus one base.
+//   * The CTA's warps add their accumulators into one shared tile set one after the other (fixed order).
 // Output layout = gram_small's: part (gridDim.x, NT, 64), tile (i <= j) at slot j (j+1)/2 + i.
 #pragma once
 #include "common.cuh"

@@ -20,7 +20,6 @@
 // waits only for the same element of the peers, which run on OTHER devices, so nothing needs to
 // be co-resident.  A bounded spin turns a missing peer into an error code instead of a hung device.
 #include <new>
-#include <vector>
 #include "common.cuh"
 #include "../../include/lrvb_b200.h"
 
