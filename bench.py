@@ -410,7 +410,7 @@ def run_ours(args, wl):
                         os.path.join(ROOT, "MEASURED_PEAKS.json")) else "B200_PROFILING.md fallback",
                     "kernel_ms": oms, "bytes_per_obs": bytes_per_obs,
                     "note": "the kernel is bound by fp64 instruction throughput (exp / log1p chains of the "
-                            "quadrature: ncu fp64 pipe 42%, issue 56%), not by HBM; see profiles/"}
+                            "quadrature: ncu fp64 pipe 49%, issue 56%, 12 warps / SM at 161 registers), not by HBM; see profiles/"}
         roof_obs["frac"] = roof_obs["achieved"] / hbm
         roofline = dict(roof_obs if oms >= gms else roof_gram)
         roofline["other_kernel"] = roof_gram if oms >= gms else roof_obs
