@@ -105,6 +105,14 @@ def _worker(rank, world, port, out):
         Hinv = np.linalg.inv(Hd)
         Dg = oracle.lay.Dg
         res["cov_g"] = np.abs(lr.get_global_covariance() - Hinv[:Dg, :Dg]).max() / np.abs(Hinv).max()
+        # device Newton over the shards: every rank walks the same iterates (bitwise) to the optimum
+        xo, r = vb.OptimizationUtils.minimize_objective_newton(obj, x, maxiter=30, gtol=1e-7)
+        res["newton_ok"] = bool(r.success)
+        res["newton_grad"] = float(np.abs(oracle.kl_grad(xo)).max())
+        xt = torch.from_numpy(np.ascontiguousarray(xo)).to(dev)
+        xs_all = [torch.empty_like(xt) for _ in range(world)]
+        dist.all_gather(xs_all, xt)
+        res["newton_same"] = all(torch.equal(xs_all[0], t) for t in xs_all)
         res["status2"] = model._peer.status() if model._peer is not None else 0
         out[rank] = res
     finally:
@@ -133,5 +141,7 @@ def test_peer_allreduce_and_sharded_model_all_gpus():
         assert res["cov_g"] < 1e-8
         for key in ("cg_jacobi", "cg_plain", "cg_x0", "cg_torch", "cg_solver"):
             assert res[key] < 1e-8, (rank, key, res[key])
+        assert res["newton_ok"] and res["newton_grad"] < 1e-6, (res["newton_ok"], res["newton_grad"])
+        assert res["newton_same"]
         assert res["cg_x0_fewer"] == 1.0
         assert res["cg_vs_torch_iters"] <= 2, res["cg_vs_torch_iters"]
