@@ -265,7 +265,8 @@ int lrvb_simplex_hess(const double* free_dev, int64_t M, int32_t d, double* hess
  *  connect:  handles = world * lrvb_p2p_handle_bytes() bytes, rank-major; maps the peers;
  *  allreduce_sum: in place on buf_dev (n <= max_elems), enqueued on `stream`; EVERY rank must
  *            issue the same sequence of calls;
- *  status:   0, or 1 + r when rank r did not arrive within ~2 s (syncs the stream). */
+ *  status:   0, or 1 + r when rank r did not arrive within ~5 s; the kernel then aborts (trap), so the
+ *            stream reports a launch failure at its next synchronisation (syncs the stream). */
 typedef struct lrvb_p2p lrvb_p2p;
 int lrvb_p2p_create(lrvb_p2p** out, int32_t rank, int32_t world, int64_t max_elems);
 int lrvb_p2p_handle_bytes(void);

@@ -18,7 +18,7 @@
 // hence its reads -- has completed (stream order).  The kernel runs on the caller's stream behind
 // the producer (programmatic dependent launch like every other kernel of the library).  A thread
 // waits only for the same element of the peers, which run on OTHER devices, so nothing needs to
-// be co-resident.  A bounded spin turns a missing peer into an error code instead of a hung device.
+// be co-resident.  A bounded spin (~5 s) turns a missing peer into a launch failure instead of a hung device.
 #include <new>
 #include "common.cuh"
 #include "../../include/lrvb_b200.h"
@@ -27,7 +27,7 @@ namespace lrvb {
 
 constexpr int kP2pMaxWorld = 16;
 constexpr int kP2pThreads = 256;
-constexpr long long kP2pSpinCycles = 4000000000LL;   // ~2 s at 1.9 GHz
+constexpr long long kP2pSpinCycles = 10000000000LL;  // ~5 s at 1.9 GHz
 
 struct P2pPeers {
   uint4* win[kP2pMaxWorld];                   // window of rank r as mapped in this process
@@ -73,8 +73,11 @@ k_p2p_allreduce(double* __restrict__ buf, int64_t n, P2pPeers peers, int rank, i
         if ((++polls & 1023u) == 0) {
           if (t0 == 0) t0 = clock64();
           else if (clock64() - t0 > kP2pSpinCycles) {
-            atomicExch(status, 1 + r);     // rank r never arrived
-            break;
+            // rank r never arrived: record it and abort the launch -- every later CUDA call of this
+            // process then fails loudly instead of continuing with a partial sum
+            atomicExch(status, 1 + r);
+            __threadfence_system();
+            __trap();
           }
         }
       }
