@@ -1,19 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- logistic-GLMM observations/sec for one fused ELBO + gradient + sparse-Hessian
 evaluation (BASELINE.json metric) on N B200s, plus the end-to-end number through the public
-Objective API, the roofline of the dominant kernel and the CPU baseline.
+Objective API, the rooflines of the dominant kernels, parity against the CPU oracle on the very
+data that is timed, and the CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c1|c2|c3|c4|c5] [--no-target]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A step = one pass of the hot path over one batch of synthetic observations already resident in
-HBM: lrvb_glmm_eval(order 2) [+ NCCL all-reduce of the packed (KL, global gradient, global
-Hessian block) when N > 1] + device CSR assembly of the arrowhead Hessian.  N = 1 workload is
-BASELINE.json configs[1] (N=1M, K=20, G=10k, Q=8); with N > 1 every rank holds a shard of that
-size (weak scaling; groups are rank-private, globals all-reduced).  Prints ONE JSON line.
+HBM: lrvb_glmm_eval(order 2) [+ the all-reduce of the packed (KL, global gradient, global Hessian
+block) over the NVLink peer windows when N > 1] + device CSR assembly of the arrowhead Hessian.
+
+The headline line (`value`) is BASELINE.json configs[1] (C2: N=1M, K=20, G=10k, Q=8) on one GPU;
+with N > 1 every rank holds a C2-sized shard (weak scaling; groups are rank-private, the replicated
+blocks all-reduced).  The same JSON line carries `target_config`: BASELINE.json configs[2] (C3:
+N=10M, K=50, G=100k) -- whole on one GPU at N = 1, and at N > 1 the SAME 10M problem cut into
+group-aligned shards by distributed.partition_groups (strong scaling), timed next to a 1-GPU run of
+the whole problem on rank 0 in the same process so that the speed-up is measured on one box.
+Prints ONE JSON line.
 """
 import argparse
+import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -28,12 +38,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # per-GPU shard: observations, fixed effects, groups, Gauss-Hermite points
+    # observations, fixed effects, groups, Gauss-Hermite points
+    "c1": dict(N=5_000, K=5, G=100, Q=4, name="logistic GLMM N=5k K=5 G=100 Q=4 (BASELINE configs[0])"),
     "c2": dict(N=1_000_000, K=20, G=10_000, Q=8,
                name="logistic GLMM N=1M K=20 G=10k Q=8 per GPU (BASELINE configs[1])"),
     "c3": dict(N=10_000_000, K=50, G=100_000, Q=8,
-               name="logistic GLMM N=10M K=50 G=100k Q=8 per GPU (BASELINE configs[2] shard)"),
-    "c1": dict(N=5_000, K=5, G=100, Q=4, name="logistic GLMM N=5k K=5 G=100 Q=4 (BASELINE configs[0])"),
+               name="logistic GLMM N=10M K=50 G=100k Q=8 (BASELINE configs[2])"),
+    "c4": dict(N=10_000_000, K=200, G=100_000, Q=8,
+               name="logistic GLMM N=10M K=200 G=100k Q=8 (BASELINE configs[3])"),
 }
 METRIC = "GLMM obs/sec for ELBO+grad+sparse Hessian"
 UNIT = "obs/s"
@@ -167,6 +179,18 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+def _hbm_peak_source():
+    return ("MEASURED_PEAKS.json hbm_gbs (burst copy)" if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else "B200_PROFILING.md fallback")
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args, wl):
     """--impl reference: the reference's CPU path for this metric (oracle port -- the reference
@@ -174,15 +198,22 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step = cpu_oracle_step(CPU_SAMPLE, wl["K"], wl["Q"])
+    if args.workload == "c5":
+        import bench_ef
+        return bench_ef.run_reference(args)
+    ns = min(CPU_SAMPLE["N"], wl["N"])
+    sample_cfg = dict(N=ns, G=max(1, wl["G"] * ns // wl["N"]))
+    step = cpu_oracle_step(sample_cfg, wl["K"], wl["Q"])
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     times = [step()[0] for _ in range(args.steps)]
     ms = 1e3 * float(np.mean(times))
-    value = CPU_SAMPLE["N"] / (ms * 1e-3)
+    value = sample_cfg["N"] / (ms * 1e-3)
     cores = blas_threads()
-    sample = "N=%d obs, K=%d, G=%d, Q=%d (1/%d of the per-GPU workload) per step" % (
-        CPU_SAMPLE["N"], wl["K"], CPU_SAMPLE["G"], wl["Q"], wl["N"] // CPU_SAMPLE["N"])
+    sample = ("N=%d obs, K=%d, G=%d, Q=%d per step: a %s sample of the per-GPU workload; obs/s is "
+              "rate-normalised (the work is linear in N at fixed N/G)") % (
+        sample_cfg["N"], wl["K"], sample_cfg["G"], wl["Q"],
+        "1/%d" % (wl["N"] // sample_cfg["N"]) if wl["N"] > sample_cfg["N"] else "full-size")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -198,17 +229,401 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------
+class Ctx(object):
+    pass
+
+
+def _gather_floats(ctx, vals):
+    """(world, len(vals)) array of per-rank values on every rank."""
+    t = ctx.torch.tensor([float(v) for v in vals], dtype=ctx.torch.float64, device=ctx.device)
+    if ctx.world == 1:
+        return t.cpu().numpy()[None, :]
+    out = [ctx.torch.empty_like(t) for _ in range(ctx.world)]
+    ctx.dist.all_gather(out, t)
+    return ctx.torch.stack(out).cpu().numpy()
+
+
+def make_model(ctx, wl, mode):
+    """mode 'single': the whole workload on this GPU.  'weak': this rank's own workload-sized shard.
+    'strong': this rank's group-aligned shard of ONE workload-sized problem (distributed.partition_groups
+    over the balanced synthetic groups)."""
+    torch, vb = ctx.torch, ctx.vb
+    N, K, G, Q = wl["N"], wl["K"], wl["G"], wl["Q"]
+    if mode == "single":
+        X, y, g = synth_shard(torch, N, K, G, seed=1000 * 2, device=ctx.device)
+        model = vb.LogisticGLMM(X, y, g, num_gh_points=Q, num_groups=G)
+        return model, model, N
+    from lrvb_b200 import distributed as vbd
+    if mode == "weak":
+        X, y, g = synth_shard(torch, N, K, G, seed=1000 * 2 + ctx.rank, device=ctx.device)
+        model = vbd.ShardedLogisticGLMM.from_local_shard(X, y, g, num_local_groups=G, num_gh_points=Q)
+        return model, model.local, N
+    # strong: cut the G balanced groups of the N-observation problem exactly as from_full would
+    base, rem = divmod(N, G)
+    counts = np.full(G, base, dtype=np.int64)
+    counts[:rem] += 1
+    bounds = vbd.partition_groups(counts, ctx.world)
+    g0, g1 = int(bounds[ctx.rank]), int(bounds[ctx.rank + 1])
+    Nl = int(counts[g0:g1].sum())
+    X, y, g = synth_shard(torch, Nl, K, g1 - g0, seed=1000 * 3 + ctx.rank, device=ctx.device)
+    model = vbd.ShardedLogisticGLMM.from_local_shard(X, y, g, num_local_groups=g1 - g0, num_gh_points=Q)
+    return model, model.local, Nl
+
+
+def time_workload(ctx, wl, mode, steps, warmup, sampler=None, kernel_steps=30):
+    """Device-timed steps of one workload.  Returns a dict (identical on every rank for the reduced
+    entries).  Timing discipline: garbage collector off and every rank synchronised BEFORE the last
+    barrier; one untimed step after the barrier (the first collective after a barrier pays a
+    re-synchronisation); then straight into the timed loop.  L2 flushed (256 MiB write) before every
+    timed step, outside the events."""
+    torch, dist, lib, nat = ctx.torch, ctx.dist, ctx.lib, ctx.nat
+    sharded = mode in ("weak", "strong")
+    model, local, N_local = make_model(ctx, wl, mode)
+    D = model.D
+    gen = torch.Generator(device=ctx.device)
+    gen.manual_seed(7)
+    x_dev = 0.1 * torch.randn(D, dtype=torch.float64, device=ctx.device, generator=gen)
+    if sharded:
+        dist.broadcast(x_dev, 0)
+    flush = ctx.flush
+    peer = getattr(model, "_peer", None) if sharded else None
+
+    def device_step():
+        model.evaluate(x_dev, 2, force=True)
+        return model.hessian_csr()
+
+    csr = None
+    for _ in range(max(warmup, 3)):
+        flush.zero_()
+        csr = device_step()                 # keep the previous result alive as the timed loop does:
+    torch.cuda.synchronize()                # the allocator then owns both ping-pong result blocks
+    if sampler is not None:
+        sampler.start()
+        for _ in range(3):                  # the sampler thread's first NVML calls happen untimed
+            flush.zero_()
+            csr = device_step()
+    if peer is not None:
+        peer.set_stats(True)
+    gc.collect()
+    gc.disable()                            # no collector pauses from here to the end of the timed loop
+    torch.cuda.synchronize()
+    if sharded:
+        dist.barrier()
+    flush.zero_()
+    csr = device_step()                     # untimed: re-synchronises the ranks on the device
+    torch.cuda.synchronize()
+    if peer is not None:
+        peer.set_stats(True)                # reset: count the timed steps only
+    launches0 = lib.lrvb_launch_count()
+    step_ms = []
+    for _ in range(steps):
+        flush.zero_()                       # L2 flush (126 MB L2 < 256 MiB), outside the timing
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        csr = device_step()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    torch.cuda.synchronize()
+    gc.enable()
+    launches = (lib.lrvb_launch_count() - launches0) // max(1, steps)
+    wait = peer.stats() if peer is not None else None
+    if peer is not None:
+        peer.set_stats(False)
+    if sharded:
+        dist.barrier()
+    clocks = sampler.stop() if sampler is not None else None
+    sm = np.asarray(step_ms)
+    per_rank = _gather_floats(ctx, [sm.mean(), np.median(sm), sm.min(), sm.max(), N_local,
+                                    (wait["wait_us_total"] / max(1, wait["calls"])) if wait else 0.0,
+                                    wait["wait_us_max"] if wait else 0.0]) if sharded else \
+        np.asarray([[sm.mean(), np.median(sm), sm.min(), sm.max(), N_local, 0.0, 0.0]])
+    ms_per_step = float(per_rank[:, 0].max())          # max over ranks of the per-rank mean
+    n_total = int(per_rank[:, 4].sum())
+    res = dict(ms_per_step=ms_per_step, value=n_total / (ms_per_step * 1e-3), n_total=n_total,
+               n_local=N_local, launches=int(launches), nnz=int(csr.nnz), D=int(D), clocks=clocks,
+               median_ms_max_over_ranks=float(per_rank[:, 1].max()),
+               per_rank_ms={"mean": [round(v, 5) for v in per_rank[:, 0]],
+                            "median": [round(v, 5) for v in per_rank[:, 1]],
+                            "max": [round(v, 5) for v in per_rank[:, 3]]},
+               model=model, local=local, x_dev=x_dev, mode=mode)
+    if sharded:
+        res["collective_wait_us"] = {
+            "mean_per_call_max_over_ranks": float(per_rank[:, 5].max()),
+            "mean_per_call_by_rank": [round(v, 2) for v in per_rank[:, 5]],
+            "largest_single_wait_us": float(per_rank[:, 6].max()),
+            "calls_per_step": (wait["calls"] // max(1, steps)) if wait else 0,
+            "how": "inside k_p2p_allreduce: %globaltimer before / after the poll loops, maximum over the "
+                   "elements of a call; the time a rank waited for its slowest peer (inter-rank skew + one "
+                   "NVLink traversal)" if peer is not None else "NCCL path: not measured"}
+    if ctx.rank == 0:
+        s2 = np.sort(sm)
+        worst = np.argsort(step_ms)[-3:][::-1]
+        print("[%s %s] step ms (rank 0): min %.4f median %.4f p90 %.4f max %.4f mean %.4f; slowest %s; "
+              "max-over-ranks mean %.4f" % (
+                  wl["name"][:28], mode, s2[0], s2[len(s2) // 2], s2[int(0.9 * (len(s2) - 1))], s2[-1],
+                  sm.mean(), ", ".join("#%d %.3f" % (i, step_ms[i]) for i in worst), ms_per_step),
+              file=sys.stderr)
+
+    # per-kernel durations for the rooflines: a separate loop, because the CUDA events the library
+    # records between its kernels cut the chain of programmatic dependent launches
+    ms3 = (ctypes.c_float * 3)()
+    eval_ms, obs_ms, gram_ms = [], [], []
+    nat.check(lib.lrvb_glmm_set_timing(local._h, 1))
+    for i in range(min(steps, kernel_steps) + 3):
+        flush.zero_()
+        csr = device_step()
+        torch.cuda.synchronize()
+        if i >= 3:
+            nat.check(lib.lrvb_glmm_last_timing(local._h, ms3))
+            eval_ms.append(ms3[0]); obs_ms.append(ms3[1]); gram_ms.append(ms3[2])
+    nat.check(lib.lrvb_glmm_set_timing(local._h, 0))
+    res.update(eval_ms=float(np.mean(eval_ms)), obs_ms=float(np.mean(obs_ms)), gram_ms=float(np.mean(gram_ms)))
+    del csr
+    return res
+
+
+def rooflines(res, wl, peak_tf, traffic):
+    """Rooflines of the two kernels that carry the step -- the fused per-observation pass (HBM roofline
+    per SURVEY.md 8(d): 8K + 12 algorithmic bytes per observation) and the packed Gram kernel (FP64
+    tensor roofline: 4K^2 + 2K flops per observation) -- and of the whole step.  `roofline` is the
+    kernel with the larger measured duration; the other is reported beside it."""
+    K, Q, N = wl["K"], wl["Q"], res["n_local"]
+    flops_per_obs = 4 * K * K + 2 * K
+    bytes_per_obs = 8 * K + 12
+    step_flops = 4 * K * K + 18 * K + 12 * Q          # SURVEY.md 8(d) total per observation
+    gms, oms = res["gram_ms"], res["obs_ms"]
+    hbm = _hbm_peak()
+    fused = bool(res.get("fused_kernel"))
+    gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
+                   "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
+                   "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
+    roof_gram = {"bound": "tensor", "kernel": gram_kernel,
+                 "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12 if gms > 0 else None, "peak": peak_tf,
+                 "unit": "TFLOP/s", "traffic": traffic.get("k_gram_dram_bytes"),
+                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in "
+                                "MEASURED_PEAKS.json); DMMA.8x8x4 microbenchmark: 37.1 TF",
+                 "kernel_ms": gms, "flops_per_obs": flops_per_obs}
+    roof_gram["frac"] = roof_gram["achieved"] / peak_tf if gms > 0 else None
+    roof_obs = {"bound": "hbm",
+                "kernel": "lrvb::k_obs_fused<2> (quadrature + per-group sums, TMA ring per warp)"
+                if K <= 62 else "lrvb::k_obs<2>",
+                "achieved": N * bytes_per_obs / (oms * 1e-3) / 1e9 if oms > 0 else None, "peak": hbm,
+                "unit": "GB/s", "traffic": traffic.get("k_obs_dram_bytes"),
+                "peak_source": _hbm_peak_source(), "kernel_ms": oms, "bytes_per_obs": bytes_per_obs,
+                "note": "bound by fp64 instruction throughput (exp / log1p chains of the quadrature), not by "
+                        "HBM; see profiles/"}
+    roof_obs["frac"] = roof_obs["achieved"] / hbm if oms > 0 else None
+    roofline = dict(roof_obs if oms >= gms else roof_gram)
+    roofline["other_kernel"] = roof_gram if oms >= gms else roof_obs
+    roofline["eval_ms"] = res["eval_ms"]
+    t = res["ms_per_step"] * 1e-3
+    hbm_s = N * bytes_per_obs / (hbm * 1e9)
+    fl_s = N * step_flops / (peak_tf * 1e12)
+    roofline["step_frac"] = max(hbm_s, fl_s) / t
+    roofline["step_frac_how"] = ("max(N (8K+12) B / HBM peak, N (4K^2+18K+12Q) flop / DGEMM peak) / ms_per_step "
+                                 "= max(%.4f, %.4f) ms / %.4f ms" % (hbm_s * 1e3, fl_s * 1e3, t * 1e3))
+    roofline["traffic_source"] = traffic.get("source")
+    return roofline
+
+
+def cov_entry(ctx, model, K, G_local, peak_tf, ncov=20):
+    """Second half of the metric: wall time of the global-parameter LRVB covariance (H^-1)[:Dg,:Dg] of the
+    cached Hessian by the Schur complement of the local blocks: DMMA Gram over the border matrix
+    [+ all-reduce of S when sharded] + SPD inverse; device timed, max over ranks."""
+    torch, dist = ctx.torch, ctx.dist
+    sharded = hasattr(model, "local")
+    for _ in range(3):
+        if sharded:
+            model._sinv = None
+        model.global_covariance()
+    torch.cuda.synchronize()
+    if sharded:
+        dist.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(ncov):
+        if sharded:
+            model._sinv = None              # the sharded model caches the result: recompute
+        model.global_covariance()
+    c1.record()
+    c1.synchronize()
+    cov_ms = float(_gather_floats(ctx, [c0.elapsed_time(c1) / ncov])[:, 0].max()) if sharded \
+        else c0.elapsed_time(c1) / ncov
+    Dg = 4 + 2 * K
+    world = ctx.world if sharded else 1
+    flops = world * G_local * (2 * Dg * Dg + 8 * Dg) + Dg ** 3
+    tf = flops / (cov_ms * 1e-3) / 1e12
+    return {"ms": cov_ms, "what": "(H^-1)[:Dg,:Dg] of the cached Hessian: Schur complement (DMMA) "
+            "[+ sum over ranks] + SPD inverse, device time, max over ranks", "Dg": Dg,
+            "algorithmic_flops": flops, "achieved_tflops": tf, "peak_tflops": peak_tf,
+            "frac": tf / peak_tf,
+            "bound": "latency (work far below one wave of the tensor pipe)" if Dg < 128 else "tensor / latency"}
+
+
+def e2e_measure(ctx, res, steps, warmup):
+    """The same metric through the public API with HOST buffers: numpy x in, scipy CSR + numpy gradient
+    + float out, every step at a different point; wall clock, max over ranks."""
+    torch, dist, vb = ctx.torch, ctx.dist, ctx.vb
+    model, x_dev, D = res["model"], res["x_dev"], res["D"]
+    sharded = res["mode"] != "single"
+    obj = vb.Objective(model.glmm_par, model) if not sharded else None
+    x0 = x_dev.cpu().numpy()
+    x_host = [x0 + 1e-3 * np.random.default_rng(s).standard_normal(D) for s in range(min(steps + warmup, 8))]
+
+    def step(i):
+        xh = x_host[i % len(x_host)]
+        if sharded:
+            # sharded: every rank brings ITS part of the distributed Hessian / gradient to its host
+            model.evaluate(xh, 2)
+            H = model.hessian_csr().to_scipy()
+            gr = model.grad_local_layout().cpu().numpy()
+            kl = float(model.kl_tensor().item())
+            return H, gr, kl
+        H = obj.fun_free_hessian(xh)     # scipy CSR on the host (order-2 evaluation, cached)
+        gr = obj.fun_free_grad(xh)       # numpy (D,)
+        kl = obj.fun_free(xh)            # float
+        return H, gr, kl
+    for i in range(warmup):
+        step(i)
+    gc.collect()
+    torch.cuda.synchronize()
+    if sharded:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        H, gr, kl = step(warmup + i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt = float(_gather_floats(ctx, [dt])[:, 0].max()) if sharded else dt
+    nnz = int(H.nnz)
+    return {"value": res["n_total"] / (dt / steps), "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
+            "h2d_bytes_per_step": 8 * D,
+            "d2h_bytes_per_step": 8 + 8 * int(gr.size) + 12 * nnz + 4 * (int(H.shape[0]) + 1),
+            "d2h_note": "bytes of the RESULT handed to the caller (data + indices + indptr + gradient + KL); "
+                        "the static pattern (indices, indptr) is transferred again only when it changes",
+            "api": "Objective.fun_free_hessian/fun_free_grad/fun_free with numpy x; "
+                   "scipy CSR + numpy gradient + float returned to the host"}
+
+
+def parity_single(ctx, res, wl):
+    """Untimed check of the very model that was timed (N = 1): KL / gradient / CSR against the CPU oracle
+    on the same data and point (tolerance of the north star: 1e-9 relative)."""
+    from oracle import glmm_oracle as go
+    model, x_dev = res["model"], res["x_dev"]
+    t0 = time.perf_counter()
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(wl["Q"])
+    o = go.GLMMOracle(model.X.cpu().numpy(), model.y.cpu().numpy(), model.g.cpu().numpy().astype(np.int64),
+                      gh_x, gh_w, G=wl["G"])
+    x = x_dev.cpu().numpy()
+    model.evaluate(x_dev, 2, force=True)
+    H = model.hessian_csr().to_scipy()
+    kl = float(model.kl_tensor().item())
+    gr = model.grad_tensor().cpu().numpy()
+    klo, go_, _ = o.kl_blocks(x)
+    He = o.kl_hessian_csr(x)
+    same = bool(np.array_equal(H.indptr, He.indptr) and np.array_equal(H.indices, He.indices))
+    out = {"against": "oracle.GLMMOracle on the timed data (N=%d, K=%d, G=%d) at the timed point" % (
+               wl["N"], wl["K"], wl["G"]),
+           "kl_rel": abs(kl - klo) / abs(klo),
+           "grad_rel": float(np.abs(gr - go_).max() / np.abs(go_).max()),
+           "hess_rel": float(np.abs(H.data - He.data).max() / np.abs(He.data).max()) if same else None,
+           "pattern_equal": same, "nnz": int(H.nnz), "oracle_seconds": round(time.perf_counter() - t0, 2),
+           "tolerance": 1e-9}
+    out["ok"] = bool(same and out["kl_rel"] < 1e-9 and out["grad_rel"] < 1e-9 and out["hess_rel"] < 1e-9)
+    return out
+
+
+def parity_sharded(ctx, res):
+    """Untimed checks at N > 1: (i) the replicated block [KL, grad_g, A] summed by the peer-memory kernel
+    against NCCL's sum of the same per-rank buffers, and bitwise equality of the result across ranks;
+    (ii) on one common 200k-observation data set: N shards == 1 GPU == oracle."""
+    torch, dist, vb = ctx.torch, ctx.dist, ctx.vb
+    from lrvb_b200 import distributed as vbd
+    from oracle import glmm_oracle as go
+    model, local, x_dev = res["model"], res["local"], res["x_dev"]
+    out = {}
+    # (i) same per-rank partial buffers through both collectives
+    local.evaluate(x_dev, 2, force=True)                 # un-reduced partials of this rank
+    part = local._out_global.clone()
+    a = part.clone()
+    dist.all_reduce(a)
+    if model._peer is not None and model._peer.fits(part):
+        b = part.clone()
+        model._peer.all_reduce_(b)
+        gathered = [torch.empty_like(b) for _ in range(ctx.world)]
+        dist.all_gather(gathered, b)
+        out["peer_vs_nccl_rel"] = float(((a - b).abs().max() / a.abs().max()).item())
+        out["peer_bitwise_equal_across_ranks"] = bool(all(torch.equal(gathered[0], t) for t in gathered))
+        out["peer_status"] = model._peer.status()
+    else:
+        out["peer_vs_nccl_rel"] = None
+        out["peer_note"] = "peer windows unavailable or message too large: NCCL path in use"
+    model.invalidate() if hasattr(model, "invalidate") else None
+    model._cache = dict(x=None, order=-1, coords=None)
+    # (ii) N-shard == 1-shard == oracle on a common data set
+    N, K, G, Q = 200_000, 20, 2_000, 8
+    X, y, g = go.make_glmm_data(N, K, G, seed=4242)
+    rng = np.random.default_rng(4243)
+    g = np.sort(rng.integers(0, G, size=N)).astype(np.int64)      # ragged groups
+    x = go.make_free(4 + 2 * K + 2 * G, 4242)
+    sh = vbd.ShardedLogisticGLMM.from_full(X, y, g, G, num_gh_points=Q)
+    obj = vb.Objective(sh.glmm_par, sh)
+    kl_s, gr_s, H_s = obj.fun_free(x), obj.fun_free_grad(x), obj.fun_free_hessian(x)
+    cov_s = sh.global_covariance().cpu().numpy()
+    if ctx.rank == 0:
+        gh_x, gh_w = np.polynomial.hermite.hermgauss(Q)
+        o = go.GLMMOracle(X, y, g, gh_x, gh_w, G=G)
+        klo, gro, _ = o.kl_blocks(x)
+        He = o.kl_hessian_csr(x)
+        one = vb.LogisticGLMM(X, y, g, num_gh_points=Q, num_groups=G)
+        o1 = vb.Objective(one.glmm_par, one)
+        kl_1, gr_1, H_1 = o1.fun_free(x), o1.fun_free_grad(x), o1.fun_free_hessian(x)
+        cov_1 = one.global_covariance().cpu().numpy()
+        cov_o = o.schur_global_cov(x)[0]
+        same = bool(np.array_equal(H_s.indptr, He.indptr) and np.array_equal(H_s.indices, He.indices)
+                    and np.array_equal(H_1.indices, He.indices))
+        rel = lambda p, q: float(np.abs(np.asarray(p) - np.asarray(q)).max() / np.abs(np.asarray(q)).max())  # noqa: E731
+        out["shards_vs_oracle"] = {"case": "N=200k K=20 G=2000 ragged groups, %d shards" % ctx.world,
+                                   "kl_rel": rel(kl_s, klo), "grad_rel": rel(gr_s, gro),
+                                   "hess_rel": rel(H_s.data, He.data) if same else None,
+                                   "cov_rel": rel(cov_s, cov_o), "pattern_equal": same}
+        out["shards_vs_one_gpu"] = {"kl_rel": rel(kl_s, kl_1), "grad_rel": rel(gr_s, gr_1),
+                                    "hess_rel": rel(H_s.data, H_1.data) if same else None,
+                                    "cov_rel": rel(cov_s, cov_1)}
+        so = out["shards_vs_oracle"]
+        out["ok"] = bool(same and so["kl_rel"] < 1e-9 and so["grad_rel"] < 1e-9 and so["hess_rel"] < 1e-9
+                         and so["cov_rel"] < 1e-8 and (out["peer_vs_nccl_rel"] is None or (
+                             out["peer_vs_nccl_rel"] < 1e-13 and out["peer_bitwise_equal_across_ranks"]
+                             and out["peer_status"] == 0)))
+        del one
+    dist.barrier()
+    del sh
+    return out
+
+
+def _load_traffic(key):
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tpath)).get(key, {})
+    except Exception:
+        return {}
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
+    ctx = Ctx()
+    ctx.torch, ctx.dist = torch, dist
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
+    ctx.device = device = torch.device("cuda", local_rank)
     # stdout must carry the one JSON line only, but native libraries write there too (NCCL prints its
     # version banner with printf): point fd 1 at stderr for the whole run and keep the real stdout
     # for the result line
@@ -222,228 +637,115 @@ def run_ours(args, wl):
 
     import lrvb_b200 as vb
     from lrvb_b200 import _native as nat
-    lib = nat.load()
+    ctx.vb, ctx.nat = vb, nat
+    ctx.lib = nat.load()
+    ctx.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
 
-    N, K, G, Q = wl["N"], wl["K"], wl["G"], wl["Q"]
-    X, y, g = synth_shard(torch, N, K, G, seed=1000 * 2 + rank, device=device)
-    if world > 1:
-        from lrvb_b200 import distributed as vbd
-        model = vbd.ShardedLogisticGLMM.from_local_shard(X, y, g, num_local_groups=G,
-                                                         num_gh_points=Q)
-    else:
-        model = vb.LogisticGLMM(X, y, g, num_gh_points=Q, num_groups=G)
-    obj = vb.Objective(model.glmm_par, model)
-    D = model.D
-    gen = torch.Generator(device=device)
-    gen.manual_seed(7)
-    x_dev = 0.1 * torch.randn(D, dtype=torch.float64, device=device, generator=gen)
-    if world > 1:
-        dist.broadcast(x_dev, 0)
-    nsteps_total = args.warmup + args.steps
-    x_host = [x_dev.cpu().numpy() + 1e-3 * np.random.default_rng(s).standard_normal(D)
-              for s in range(min(nsteps_total, 8))]
-    if world > 1:   # every rank must evaluate at the same points
-        for xh in x_host:
-            t = torch.from_numpy(xh).to(device)
-            dist.broadcast(t, 0)
-            xh[:] = t.cpu().numpy()
+    if args.workload == "c5":
+        import bench_ef
+        line = bench_ef.run_ours(ctx, args)
+        if rank == 0:
+            os.write(result_fd, (json.dumps(line) + "\n").encode())
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        os.dup2(result_fd, 1)
+        os.close(result_fd)
+        return
 
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
-    local = model.local if world > 1 else model
-
-    def device_step():
-        model.evaluate(x_dev, 2, force=True)
-        return model.hessian_csr()
-
-    # ---------------- device-resident timing ----------------
-    csr = None
-    for _ in range(args.warmup):
-        csr = device_step()                 # keep the previous result alive as the timed loop does:
-    torch.cuda.synchronize()                # the allocator then owns both ping-pong result blocks
-    if world > 1:
-        dist.barrier()
+    K, G, Q = wl["K"], wl["G"], wl["Q"]
+    mode = "single" if world == 1 else "weak"
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    res = time_workload(ctx, wl, mode, args.steps, args.warmup, sampler=sampler)
+    peak_tf = measure_dgemm_tflops(torch) if rank == 0 else 1.0
+    cov = cov_entry(ctx, res["model"], K, G, peak_tf)
+    e2e = e2e_measure(ctx, res, min(args.steps, 50), min(args.warmup, 5))
+    parity = parity_single(ctx, res, wl) if world == 1 else parity_sharded(ctx, res)
+
+    line = None
     if rank == 0:
-        sampler.start()
-    for _ in range(3):                      # the sampler thread's first NVML calls happen untimed
-        flush.zero_()
-        csr = device_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        flush.zero_()
-        csr = device_step()                 # the first collective after a barrier pays a re-sync: untimed
-        torch.cuda.synchronize()
-    launches0 = lib.lrvb_launch_count()
-    step_ms, gram_ms, obs_ms, eval_ms = [], [], [], []
-    import ctypes
-    ms3 = (ctypes.c_float * 3)()
-    torch.cuda.synchronize()
-    import gc
-    gc.collect()
-    gc.disable()                            # no collector pauses inside the timed steps
-    for _ in range(args.steps):
-        flush.zero_()                       # L2 flush (126 MB L2 < 256 MiB), outside the timing
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        csr = device_step()
-        e1.record()
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-    torch.cuda.synchronize()
-    gc.enable()
-    launches = (lib.lrvb_launch_count() - launches0) // max(1, args.steps)
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    value = world * N / (ms_per_step * 1e-3)
-    if rank == 0:
-        sm = np.sort(np.asarray(step_ms))
-        worst = np.argsort(step_ms)[-3:][::-1]
-        print("step ms: min %.3f median %.3f p90 %.3f max %.3f; slowest steps %s" % (
-            sm[0], sm[len(sm) // 2], sm[int(0.9 * (len(sm) - 1))], sm[-1],
-            ", ".join("#%d %.3f" % (i, step_ms[i]) for i in worst)), file=sys.stderr)
-    nnz = csr.nnz
-
-    # ---------------- per-kernel durations for the roofline (separate, untimed-for-the-metric loop:
-    # the CUDA events the library records between its kernels cut the chain of programmatic
-    # dependent launches, so the metric above is measured without them) ----------------
-    nat.check(lib.lrvb_glmm_set_timing(local._h, 1))
-    for i in range(min(args.steps, 30) + 3):
-        flush.zero_()
-        csr = device_step()
-        torch.cuda.synchronize()
-        if i >= 3:
-            nat.check(lib.lrvb_glmm_last_timing(local._h, ms3))
-            eval_ms.append(ms3[0]); obs_ms.append(ms3[1]); gram_ms.append(ms3[2])
-    nat.check(lib.lrvb_glmm_set_timing(local._h, 0))
-
-    # ---------------- LRVB covariance of the global parameters (second half of the metric) -------
-    # (H^-1)[:Dg,:Dg] by the Schur complement of the local blocks on the cached Hessian: DMMA Gram
-    # over the border matrix [+ all-reduce of S when sharded] + SPD inverse; device timed, max over ranks
-    for _ in range(3):
-        cov = model.global_covariance()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ncov = 20
-    c0.record()
-    for _ in range(ncov):
-        if world > 1:
-            model._sinv = None              # the sharded model caches the result: recompute
-        cov = model.global_covariance()
-    c1.record()
-    c1.synchronize()
-    cov_ms = torch.tensor([c0.elapsed_time(c1) / ncov], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(cov_ms, op=dist.ReduceOp.MAX)
-    cov_ms = float(cov_ms.item())
-
-    # ---------------- end to end through the public API (host buffers) ----------------
-
-    def e2e_step(i):
-        xh = x_host[i % len(x_host)]
-        if world > 1:
-            # sharded: every rank brings ITS part of the distributed Hessian / gradient to its host
-            model.evaluate(xh, 2)
-            H = model.hessian_csr().to_scipy()
-            gr = model.grad_local_layout().cpu().numpy()
-            kl = float(model.kl_tensor().item())
-            return H, gr, kl
-        H = obj.fun_free_hessian(xh)     # scipy CSR on the host (order-2 evaluation, cached)
-        gr = obj.fun_free_grad(xh)       # numpy (D,)
-        kl = obj.fun_free(xh)            # float
-        return H, gr, kl
-    for i in range(args.warmup):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        H, gr, kl = e2e_step(args.warmup + i)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * N / (float(e2e_s.item()) / args.steps)
-    h2d = 8 * D
-    d2h = 8 + 8 * D + 12 * int(H.nnz) + 4 * (D + 1)
-
-    if rank == 0:
-        # rooflines of the two kernels that carry the step: the fused per-observation pass (HBM
-        # roofline per SURVEY.md 8(d): 8K + 12 algorithmic bytes per observation) and the packed
-        # Gram kernel (FP64 tensor roofline: 4K^2 + 2K flops per observation).  `roofline` is the
-        # one with the larger measured duration; the other is reported beside it.
-        peak_tf = measure_dgemm_tflops(torch)
-        flops_per_obs = 4 * K * K + 2 * K
-        bytes_per_obs = 8 * K + 12
-        gms, oms = float(np.mean(gram_ms)), float(np.mean(obs_ms))
-        traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload, {})
-            except Exception:
-                traffic = {}
-        gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
-                       "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
-                       "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
-        roof_gram = {"bound": "tensor", "kernel": gram_kernel,
-                     "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12, "peak": peak_tf,
-                     "unit": "TFLOP/s", "traffic": traffic.get("k_gram_dram_bytes"),
-                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in "
-                                    "MEASURED_PEAKS.json); DMMA.8x8x4 microbenchmark: 37.1 TF",
-                     "kernel_ms": gms, "flops_per_obs": flops_per_obs}
-        roof_gram["frac"] = roof_gram["achieved"] / peak_tf
-        hbm = _hbm_peak()
-        roof_obs = {"bound": "hbm", "kernel": "lrvb::k_obs_fused<2> (quadrature + per-group sums, TMA ring per warp)"
-                    if K <= 62 else "lrvb::k_obs<2>",
-                    "achieved": N * bytes_per_obs / (oms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                    "traffic": traffic.get("k_obs_dram_bytes"),
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if os.path.exists(
-                        os.path.join(ROOT, "MEASURED_PEAKS.json")) else "B200_PROFILING.md fallback",
-                    "kernel_ms": oms, "bytes_per_obs": bytes_per_obs,
-                    "note": "the kernel is bound by fp64 instruction throughput (exp / log1p chains of the "
-                            "quadrature: ncu fp64 pipe 49%, issue 56%, 12 warps / SM at 161 registers), not by HBM; see profiles/"}
-        roof_obs["frac"] = roof_obs["achieved"] / hbm
-        roofline = dict(roof_obs if oms >= gms else roof_gram)
-        roofline["other_kernel"] = roof_gram if oms >= gms else roof_obs
-        roofline["eval_ms"] = float(np.mean(eval_ms))
-        roofline["hbm_frac_of_step"] = (N * bytes_per_obs / (ms_per_step * 1e-3) / 1e9) / hbm
-        cpu = None
-        if world == 1 or True:
-            stepf = cpu_oracle_step(CPU_SAMPLE, K, Q)
-            stepf()
-            ts = [stepf()[0] for _ in range(3)]
-            cores = blas_threads()
-            cpu = {"value": CPU_SAMPLE["N"] / float(np.median(ts)), "unit": UNIT, "cores": cores,
-                   "kind": "port",
-                   "sample": "N=%d obs, K=%d, G=%d, Q=%d (1/%d of the per-GPU workload), median of 3"
-                             % (CPU_SAMPLE["N"], K, CPU_SAMPLE["G"], Q, N // CPU_SAMPLE["N"])}
+        ns = min(CPU_SAMPLE["N"], wl["N"])
+        sample_cfg = dict(N=ns, G=max(1, G * ns // wl["N"]))
+        stepf = cpu_oracle_step(sample_cfg, K, Q)
+        stepf()
+        ts = [stepf()[0] for _ in range(3)]
+        cores = blas_threads()
+        cpu = {"value": sample_cfg["N"] / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "N=%d obs, K=%d, G=%d, Q=%d (1/%d of the per-GPU workload; obs/s is rate-normalised), "
+                         "median of 3" % (sample_cfg["N"], K, sample_cfg["G"], Q, max(1, wl["N"] // sample_cfg["N"]))}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "obs_per_gpu": N, "K": K, "groups_per_gpu": G,
-                       "gh_points": Q, "free_dim": D, "hessian_nnz": int(nnz),
-                       "parallelism": "obs-sharded x%d, NCCL all-reduce of (KL, grad_g, H_gg)" % world
+            "config": {"workload": wl["name"], "obs_per_gpu": wl["N"], "K": K, "groups_per_gpu": G,
+                       "gh_points": Q, "free_dim": res["D"], "hessian_nnz": res["nnz"],
+                       "parallelism": ("obs-sharded x%d (group-aligned shards, groups rank-private); one sum of "
+                                       "[KL, grad_g, H_gg] per step by lrvb::k_p2p_allreduce over NVLink peer "
+                                       "memory (csrc/p2p.cu); NCCL only for init / barriers" % world)
                        if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write); X alone is %d MB"
-                             % (N * K * 8 // 10 ** 6)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "api": "Objective.fun_free_hessian/fun_free_grad/fun_free with numpy x; "
-                           "scipy CSR + numpy gradient + float returned to the host"},
-            "lrvb_covariance": _cov_entry(cov_ms, K, G, world, peak_tf),
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clocks,
+                             % (wl["N"] * K * 8 // 10 ** 6),
+                       "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks; "
+                                 "GC off and ranks synchronised before the last barrier, one untimed step after it"},
+            "e2e": e2e, "lrvb_covariance": cov, "gpu_launches": res["launches"],
+            "roofline": rooflines(res, wl, peak_tf, _load_traffic(args.workload)),
+            "parity": parity, "cpu_baseline": cpu, "clocks": res["clocks"],
+            "median_ms_max_over_ranks": res["median_ms_max_over_ranks"], "per_rank_ms": res["per_rank_ms"],
         }
+        if "collective_wait_us" in res:
+            line["collective_wait_us"] = res["collective_wait_us"]
+    # free the headline workload before the target configuration
+    for k in ("model", "local", "x_dev"):
+        res.pop(k, None)
+    del cov, e2e
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---------------- target configuration: C3 (BASELINE configs[2]) ----------------
+    if not args.no_target and args.workload == "c2":
+        wt = WORKLOADS["c3"]
+        tsteps, twarm = max(5, min(args.steps, 20)), 3
+        tmode = "single" if world == 1 else "strong"
+        rt = time_workload(ctx, wt, tmode, tsteps, twarm, kernel_steps=5)
+        tcov = cov_entry(ctx, rt["model"], wt["K"], rt["local"].G, peak_tf, ncov=5)
+        te2e = e2e_measure(ctx, rt, 3, 1) if world == 1 else None
+        tline = None
+        if rank == 0:
+            tline = {"workload": wt["name"], "n_gpus": world,
+                     "scaling": "strong" if world > 1 else "single GPU",
+                     "value": rt["value"], "unit": UNIT, "ms_per_step": rt["ms_per_step"], "steps": tsteps,
+                     "obs_total": rt["n_total"], "obs_this_rank": rt["n_local"], "hessian_nnz_this_rank": rt["nnz"],
+                     "gpu_launches": rt["launches"], "lrvb_covariance": tcov,
+                     "roofline": rooflines(rt, wt, peak_tf, _load_traffic("c3")),
+                     "per_rank_ms": rt["per_rank_ms"],
+                     "median_ms_max_over_ranks": rt["median_ms_max_over_ranks"]}
+            if te2e is not None:
+                tline["e2e"] = te2e
+            if "collective_wait_us" in rt:
+                tline["collective_wait_us"] = rt["collective_wait_us"]
+                tline["partition"] = "distributed.partition_groups over the 100k balanced groups: %d obs on rank 0" \
+                                     % rt["n_local"]
+        for k in ("model", "local", "x_dev"):
+            rt.pop(k, None)
+        gc.collect()
+        torch.cuda.empty_cache()
+        if world > 1:
+            # the same 10M problem on ONE GPU (rank 0) in the same process: the strong-scaling denominator
+            dist.barrier()
+            if rank == 0:
+                r1 = time_workload(ctx_single(ctx), wt, "single", max(5, tsteps // 2), 3, kernel_steps=3)
+                tline["one_gpu_same_run"] = {"value": r1["value"], "ms_per_step": r1["ms_per_step"],
+                                             "steps": max(5, tsteps // 2)}
+                tline["speedup_vs_one_gpu"] = rt["value"] / r1["value"]
+                for k in ("model", "local", "x_dev"):
+                    r1.pop(k, None)
+                gc.collect()
+                torch.cuda.empty_cache()
+            dist.barrier()
+        if rank == 0:
+            line["target_config"] = tline
+
+    if rank == 0:
         sys.stdout.flush()
         os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -454,25 +756,11 @@ def run_ours(args, wl):
     os.close(result_fd)
 
 
-def _cov_entry(cov_ms, K, G, world, peak_tf):
-    """Second half of the metric: wall time of the global-parameter LRVB covariance and its fraction
-    of the FP64 tensor roofline.  Algorithmic flops: per group B_g^T L_g^-1 B_g on the upper
-    triangle (2 Dg^2 + 8 Dg), plus Dg^3 for the SPD inverse; at Dg = 44 the work is ~40 MFLOP per
-    GPU, i.e. the number is launch / latency bound, not tensor bound."""
-    Dg = 4 + 2 * K
-    flops = world * G * (2 * Dg * Dg + 8 * Dg) + Dg ** 3
-    tf = flops / (cov_ms * 1e-3) / 1e12
-    return {"ms": cov_ms, "what": "(H^-1)[:Dg,:Dg] of the cached Hessian: Schur complement (DMMA) "
-            "[+ sum over ranks] + SPD inverse, device time, max over ranks", "Dg": Dg,
-            "algorithmic_flops": flops, "achieved_tflops": tf, "peak_tflops": peak_tf,
-            "frac": tf / peak_tf, "bound": "latency (work far below one wave of the tensor pipe)"}
-
-
-def _hbm_peak():
-    try:
-        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        return 6650.0   # B200_PROFILING.md fallback
+def ctx_single(ctx):
+    c = Ctx()
+    c.__dict__.update(ctx.__dict__)
+    c.world = 1
+    return c
 
 
 def main():
@@ -481,11 +769,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--no-target", action="store_true",
+                    help="skip the target_config (C3) section of the default run")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rules: W >= 3
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS.get(args.workload)
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -163,6 +163,31 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
                  double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
                  void* stream);
 
+/* The same solve with any preconditioner M (the `M=` argument of scipy.sparse.linalg.cg that
+ * ConjugateGradientSolver.preconditioner feeds, ConjugateGradient.py:84):
+ *   LRVB_PRECOND_NONE / _BLOCK_JACOBI as above;
+ *   LRVB_PRECOND_SCHUR: M = H^-1 applied exactly by block elimination with Sinv_dev = S^-1 (Dg,Dg) from
+ *     lrvb_glmm_schur + lrvb_spd_inverse ("use as preconditioner and as the cross-check");
+ *   LRVB_PRECOND_CSR:   M a (D,D) device CSR matrix (int32 indptr / indices, fp64 data), z = M r by SpMV;
+ *   LRVB_PRECOND_DENSE: M a dense row-major (D,D) device matrix.
+ * M must be symmetric positive definite, as scipy requires. */
+#define LRVB_PRECOND_NONE 0
+#define LRVB_PRECOND_BLOCK_JACOBI 1
+#define LRVB_PRECOND_SCHUR 2
+#define LRVB_PRECOND_CSR 3
+#define LRVB_PRECOND_DENSE 4
+typedef struct {
+  int32_t kind;
+  const double* Sinv_dev;
+  const int32_t* indptr_dev;
+  const int32_t* indices_dev;
+  const double* data_dev;
+  const double* dense_dev;
+} lrvb_cg_precond;
+int lrvb_glmm_cg_m(lrvb_glmm* h, const double* b_dev, const double* x0_dev, const lrvb_cg_precond* M,
+                   double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
+                   void* stream);
+
 /* ---- direct arrowhead solve / LRVB covariance -------------------------------------------
  * Schur complement of the local blocks:
  *   S = [include_A ? A : 0] - sum_g B_g^T L_g^{-1} B_g     (Dg,Dg) row-major, dev.
@@ -265,8 +290,15 @@ int lrvb_simplex_hess(const double* free_dev, int64_t M, int32_t d, double* hess
  *  connect:  handles = world * lrvb_p2p_handle_bytes() bytes, rank-major; maps the peers;
  *  allreduce_sum: in place on buf_dev (n <= max_elems), enqueued on `stream`; EVERY rank must
  *            issue the same sequence of calls;
- *  status:   0, or 1 + r when rank r did not arrive within ~5 s; the kernel then aborts (trap), so the
- *            stream reports a launch failure at its next synchronisation (syncs the stream). */
+ *  status:   0, or 1 + r when rank r did not arrive within the deadline (default 120 s; environment
+ *            LRVB_P2P_TIMEOUT_S at create, or lrvb_p2p_set_timeout).  The word lives in mapped pinned
+ *            HOST memory and is sticky: a timed-out call fills its output with NaN and returns (no
+ *            trap, the CUDA context survives), every later lrvb_p2p_allreduce_sum returns LRVB_ESTATE.
+ *            lrvb_p2p_status syncs the stream first; _nowait just reads the word.
+ *  set_stats / get_stats: when enabled every call measures, inside the kernel (%globaltimer around
+ *            the poll loops, maximum over all elements), how long this rank WAITED for its slowest
+ *            peer; get_stats (syncs) returns out3 = {calls, sum of the per-call waits (us), largest
+ *            per-call wait (us)} since set_stats -- bench.py's collective_wait_us. */
 typedef struct lrvb_p2p lrvb_p2p;
 int lrvb_p2p_create(lrvb_p2p** out, int32_t rank, int32_t world, int64_t max_elems);
 int lrvb_p2p_handle_bytes(void);
@@ -274,6 +306,10 @@ int lrvb_p2p_export(lrvb_p2p* h, void* handle_out);
 int lrvb_p2p_connect(lrvb_p2p* h, const void* handles);
 int lrvb_p2p_allreduce_sum(lrvb_p2p* h, double* buf_dev, int64_t n, void* stream);
 int lrvb_p2p_status(lrvb_p2p* h, int32_t* status_out, void* stream);
+int lrvb_p2p_status_nowait(lrvb_p2p* h, int32_t* status_out);
+int lrvb_p2p_set_timeout(lrvb_p2p* h, double seconds);
+int lrvb_p2p_set_stats(lrvb_p2p* h, int32_t enable, void* stream);
+int lrvb_p2p_get_stats(lrvb_p2p* h, double* out3_host, void* stream);
 int lrvb_p2p_destroy(lrvb_p2p* h);
 /* ConjugateGradientSolver.get_hinv_vec (ConjugateGradient.py:81-85) over the shards of one job:
  * lrvb_glmm_cg on vectors in the shard's local layout [globals | u.mean | u.info of the shard's

@@ -10,9 +10,11 @@ test_objectives.py:541) is recognised when the callable is a bound method of a d
 ``Objective``: the Hessian blocks are evaluated once at ``x0`` and the whole CG loop (HVP, dots,
 axpys, convergence test; csrc/solve.cu) runs on the GPU with scipy's stopping rule
 ``||r|| < tol * ||b||``.  ``tol`` keeps the reference attribute name; scipy >= 1.14 spells it
-``rtol`` (SURVEY.md 8b "CG API drift").  ``preconditioner`` may be None, the string
-``"block_jacobi"`` (device block-Jacobi) -- or, for a generic Python HVP callable (host control
-path, exactly the reference's scipy call), anything scipy's ``M=`` accepts.
+``rtol`` (SURVEY.md 8b "CG API drift").  ``preconditioner`` is scipy's ``M=`` (:84): None, a
+scipy sparse matrix or a dense array (applied on the device by SpMV / GEMV), or the strings
+``"block_jacobi"`` (inverse of the block diagonal of H) and ``"schur"`` (H^-1 itself through the
+Schur complement of the local blocks); for a generic Python HVP callable (host
+control path, exactly the reference's scipy call) anything scipy accepts.
 """
 import time
 
@@ -107,12 +109,10 @@ class ConjugateGradientSolver(object):
 
     def _device_solve(self, vec, x0):
         model = self._objective.model
-        if self.preconditioner is None:
-            precond = 0
-        elif isinstance(self.preconditioner, str) and self.preconditioner == "block_jacobi":
-            precond = 1
-        else:
-            raise ValueError("device CG supports preconditioner None or 'block_jacobi'")
+        # None, "block_jacobi", "schur", or any matrix scipy's M= accepts (sparse / dense): the model
+        # turns it into a device operator (GLMM.make_preconditioner); a sharded model takes the
+        # first two
+        precond = 0 if self.preconditioner is None else self.preconditioner
         model.evaluate(self.x0, 2, self._coords)  # cached after the first solve
         n = vec.numel() if is_torch(vec) else np.asarray(vec).size
         if n != self.dim:

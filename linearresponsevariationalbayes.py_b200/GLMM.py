@@ -416,14 +416,56 @@ class LogisticGLMM(object):
         rhs = self.solve_reduce_rhs(b_dev, include_bg=True)
         return self.solve_finish(Sinv, rhs, b_dev)
 
+    def make_preconditioner(self, M):
+        """The `M=` of scipy.sparse.linalg.cg (ConjugateGradient.py:84) as a device descriptor.
+        M: None / 0; 'block_jacobi' / 1; 'schur' (M = H^-1 applied exactly through the Schur
+        complement of the local blocks); a scipy sparse matrix, a (D, D) numpy array or a torch
+        tensor (M r by device SpMV / GEMV).  Returns (nat.CGPrecond, keep-alive tuple)."""
+        import scipy.sparse
+        torch = nat.require_cuda()
+        d = nat.CGPrecond()
+        keep = ()
+        if M is None or (isinstance(M, int) and M == 0):
+            d.kind = nat.PRECOND_NONE
+        elif (isinstance(M, str) and M == "block_jacobi") or (isinstance(M, int) and M == 1):
+            d.kind = nat.PRECOND_BLOCK_JACOBI
+        elif isinstance(M, str) and M == "schur":
+            sinv = self.global_covariance()
+            d.kind, d.Sinv_dev, keep = nat.PRECOND_SCHUR, sinv.data_ptr(), (sinv,)
+        elif scipy.sparse.issparse(M):
+            m = scipy.sparse.csr_matrix(M)
+            if m.shape != (self.D, self.D):
+                raise ValueError("Wrong shape for the preconditioner.  Expected {}, got {}".format(
+                    (self.D, self.D), m.shape))
+            m.sort_indices()
+            ip = to_device(m.indptr.astype(np.int32), torch.int32)
+            ix = to_device(m.indices.astype(np.int32), torch.int32)
+            dv = to_device(m.data.astype(np.float64))
+            d.kind, d.indptr_dev, d.indices_dev, d.data_dev = (nat.PRECOND_CSR, ip.data_ptr(),
+                                                               ix.data_ptr(), dv.data_ptr())
+            keep = (ip, ix, dv)
+        elif is_torch(M) or isinstance(M, np.ndarray):
+            m = to_device(M)
+            if tuple(m.shape) != (self.D, self.D):
+                raise ValueError("Wrong shape for the preconditioner.  Expected {}, got {}".format(
+                    (self.D, self.D), tuple(m.shape)))
+            d.kind, d.dense_dev, keep = nat.PRECOND_DENSE, m.data_ptr(), (m,)
+        else:
+            raise ValueError("device CG takes preconditioner None, 'block_jacobi', 'schur', a scipy sparse "
+                             "matrix, a numpy array or a torch tensor; got %r (a Python operator cannot run "
+                             "inside the device iteration)" % (M,))
+        return d, keep
+
     def cg_cached(self, b_dev, x0_dev=None, precond=0, rtol=1e-8, maxiter=0):
         """scipy-cg-compatible solve with the cached Hessian -> (x_dev, info, iters)."""
         torch = nat.require_cuda()
         x = torch.empty(self.D, dtype=torch.float64, device=self.device)
         info, iters = ctypes.c_int32(), ctypes.c_int32()
-        nat.check(self._lib.lrvb_glmm_cg(self._h, nat.ptr(b_dev), nat.ptr(x0_dev), int(precond),
-                                         float(rtol), int(maxiter), nat.ptr(x), ctypes.byref(info),
-                                         ctypes.byref(iters), nat.stream_ptr()))
+        desc, keep = self.make_preconditioner(precond)
+        nat.check(self._lib.lrvb_glmm_cg_m(self._h, nat.ptr(b_dev), nat.ptr(x0_dev), ctypes.byref(desc),
+                                           float(rtol), int(maxiter), nat.ptr(x), ctypes.byref(info),
+                                           ctypes.byref(iters), nat.stream_ptr()))
+        del keep
         return x, info.value, iters.value
 
     def schur_cached(self, include_A=True):

@@ -56,11 +56,32 @@ class LinearResponseCovariances(object):
         return self.objective.fun_free_hessian(self._opt0)
 
     def get_global_covariance(self):
-        """(H^{-1})[:Dg,:Dg]: LRVB covariance of the global free parameters (Dg,Dg)."""
+        """(H^{-1})[:Dg,:Dg]: LRVB covariance of the global free parameters (Dg,Dg).  method
+        'schur': one Schur complement + SPD inverse; method 'cg': Dg conjugate-gradient solves with
+        device Hessian-vector products (ConjugateGradient.py:81-105; BASELINE configs[3]), their
+        ``info`` / iteration counts appended to ``cg_infos`` / ``cg_iterations``."""
+        import torch
         self._ensure_point()
+        if self.method == "cg":
+            Dg, D = self.model.Dg, self.model.D
+            cov = torch.empty(Dg, Dg, dtype=torch.float64, device=self.model.device)
+            e = torch.zeros(D, dtype=torch.float64, device=self.model.device)
+            for i in range(Dg):
+                e.zero_()
+                e[i] = 1.0
+                x, info, iters = self.model.cg(e, None, precond=self._cg_precond(), rtol=self.cg_tol)
+                self.cg_infos.append(info)
+                self.cg_iterations.append(iters)
+                cov[i] = x[:Dg]
+            cov = 0.5 * (cov + cov.t())
+            return cov if is_torch(self._opt0) else cov.cpu().numpy()
         if self._sinv is None:
             self._sinv = self.model.global_covariance()
         return self._sinv if is_torch(self._opt0) else self._sinv.cpu().numpy()
+
+    def _cg_precond(self):
+        p = self.cg_preconditioner
+        return 0 if p is None else p
 
     def get_local_covariances(self):
         """Per-group LRVB covariance of (u.mean_g, u.info_g) free parameters, (G,3)=(mm,mi,ii)."""
@@ -82,9 +103,7 @@ class LinearResponseCovariances(object):
         rows = rhs.reshape(-1, self.model.D)
         out = []
         for row in rows:
-            x, info, iters = self.model.cg(
-                row, None, precond=1 if self.cg_preconditioner == "block_jacobi" else 0,
-                rtol=self.cg_tol)
+            x, info, iters = self.model.cg(row, None, precond=self._cg_precond(), rtol=self.cg_tol)
             self.cg_infos.append(info)
             self.cg_iterations.append(iters)
             out.append(x)

@@ -26,6 +26,14 @@ class Bounds(ctypes.Structure):
     _fields_ = [(n, c_double) for n in ("mu_info", "tau_shape", "tau_rate", "beta_info", "u_info")]
 
 
+class CGPrecond(ctypes.Structure):
+    """lrvb_cg_precond: the `M=` of scipy.sparse.linalg.cg (ConjugateGradient.py:84) for the device CG."""
+    _fields_ = [("kind", c_int32), ("Sinv_dev", c_void_p), ("indptr_dev", c_void_p),
+                ("indices_dev", c_void_p), ("data_dev", c_void_p), ("dense_dev", c_void_p)]
+
+
+PRECOND_NONE, PRECOND_BLOCK_JACOBI, PRECOND_SCHUR, PRECOND_CSR, PRECOND_DENSE = 0, 1, 2, 3, 4
+
 # name -> (restype, argtypes); must list every symbol of include/lrvb_b200.h
 _P = c_void_p
 SIGNATURES = {
@@ -53,6 +61,8 @@ SIGNATURES = {
     "lrvb_glmm_hvp": (c_int32, [_P, _P, _P, c_int32, _P]),
     "lrvb_glmm_cg": (c_int32, [_P, _P, _P, c_int32, c_double, c_int32, _P, POINTER(c_int32),
                                POINTER(c_int32), _P]),
+    "lrvb_glmm_cg_m": (c_int32, [_P, _P, _P, POINTER(CGPrecond), c_double, c_int32, _P, POINTER(c_int32),
+                                 POINTER(c_int32), _P]),
     "lrvb_glmm_schur": (c_int32, [_P, _P, c_int32, _P]),
     "lrvb_spd_inverse": (c_int32, [_P, c_int32, POINTER(c_int32), _P]),
     "lrvb_glmm_solve_reduce_rhs": (c_int32, [_P, _P, c_int32, _P, c_int32, _P]),
@@ -84,6 +94,10 @@ SIGNATURES = {
     "lrvb_p2p_connect": (c_int32, [_P, _P]),
     "lrvb_p2p_allreduce_sum": (c_int32, [_P, _P, c_int64, _P]),
     "lrvb_p2p_status": (c_int32, [_P, POINTER(c_int32), _P]),
+    "lrvb_p2p_status_nowait": (c_int32, [_P, POINTER(c_int32)]),
+    "lrvb_p2p_set_timeout": (c_int32, [_P, c_double]),
+    "lrvb_p2p_set_stats": (c_int32, [_P, c_int32, _P]),
+    "lrvb_p2p_get_stats": (c_int32, [_P, POINTER(c_double), _P]),
     "lrvb_p2p_destroy": (c_int32, [_P]),
     "lrvb_glmm_cg_sharded": (c_int32, [_P, _P, _P, _P, c_int32, c_double, c_int32, c_int32, _P,
                                        POINTER(c_int32), POINTER(c_int32), _P]),

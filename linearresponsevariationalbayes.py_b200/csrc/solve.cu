@@ -186,6 +186,7 @@ k_cg_precond(const double* __restrict__ r, double* __restrict__ z, const double*
     double zi;
     const double ri = r[i];
     if (!precond) zi = ri;
+    else if (precond == 2) zi = z[i];        // z = M r was formed by the caller's operator
     else if (i < Dg) zi = ri / A[(size_t)i * Dg + i];
     else if (i < Dg + G) {
       const int64_t gi = i - Dg;
@@ -194,13 +195,43 @@ k_cg_precond(const double* __restrict__ r, double* __restrict__ z, const double*
       const int64_t gi = i - Dg - G;
       zi = Linv[gi * 3 + 1] * r[i - G] + Linv[gi * 3 + 2] * ri;
     }
-    z[i] = zi;
+    if (precond != 2) z[i] = zi;
     s = fma(ri, zi, s);
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) {
     rzpart[blockIdx.x * 2] = s;
     rzpart[blockIdx.x * 2 + 1] = 0.0;
+  }
+}
+
+// z = M r for a caller-supplied preconditioner matrix: CSR (one warp per row) or dense row-major
+__global__ void __launch_bounds__(256)
+k_cg_m_csr(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+           const double* __restrict__ data, const double* __restrict__ r, double* __restrict__ z, int64_t D,
+           const int* __restrict__ flags) {
+  pdl_sync();
+  if (flags[0]) return;
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < D; row += (int64_t)gridDim.x * 8) {
+    double s = 0.0;
+    for (int32_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) s = fma(data[e], r[indices[e]], s);
+    s = warp_sum(s);
+    if (lane == 0) z[row] = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_cg_m_dense(const double* __restrict__ M, const double* __restrict__ r, double* __restrict__ z, int64_t D,
+             const int* __restrict__ flags) {
+  pdl_sync();
+  if (flags[0]) return;
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < D; row += (int64_t)gridDim.x * 8) {
+    const double* m = M + (size_t)row * D;
+    double s = 0.0;
+    for (int64_t c = lane; c < D; c += 32) s = fma(m[c], r[c], s);
+    s = warp_sum(s);
+    if (lane == 0) z[row] = s;
   }
 }
 
@@ -833,12 +864,17 @@ int lrvb_glmm_hvp(lrvb_glmm* h, const double* v_dev, double* out_dev, int32_t in
   return launch_hvp(h, v_dev, out_dev, include_A, nullptr, (cudaStream_t)stream);
 }
 
-int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_t precond,
-                 double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
-                 void* stream) {
+static int cg_run(lrvb_glmm* h, const double* b_dev, const double* x0_dev, const lrvb_cg_precond* M,
+                  double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters, void* stream) {
   LRVB_TRY(require_hess(h, "lrvb_glmm_cg"));
   LRVB_REQUIRE(b_dev && x_dev && info, "lrvb_glmm_cg: NULL argument");
-  LRVB_REQUIRE(precond == 0 || precond == 1, "lrvb_glmm_cg: precond = %d not in {0,1}", precond);
+  const int kind = M ? M->kind : 0;
+  LRVB_REQUIRE(kind >= 0 && kind <= 4, "lrvb_glmm_cg: preconditioner kind = %d not in 0..4", kind);
+  LRVB_REQUIRE(kind != LRVB_PRECOND_SCHUR || M->Sinv_dev, "lrvb_glmm_cg: Schur preconditioner needs Sinv_dev");
+  LRVB_REQUIRE(kind != LRVB_PRECOND_CSR || (M->indptr_dev && M->indices_dev && M->data_dev),
+               "lrvb_glmm_cg: CSR preconditioner needs indptr / indices / data");
+  LRVB_REQUIRE(kind != LRVB_PRECOND_DENSE || M->dense_dev, "lrvb_glmm_cg: dense preconditioner needs dense_dev");
+  const int precond = kind >= 2 ? 2 : kind;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t D = h->D;
   const int Dg = h->Dg, G = h->G;
@@ -854,7 +890,8 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   int* flags = h->flags;
   const int vgrid = h->dot_grid;
   LRVB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
-  if (precond) LRVB_TRY(prepare_linv(h, st));
+  if (kind == LRVB_PRECOND_BLOCK_JACOBI || kind == LRVB_PRECOND_SCHUR) LRVB_TRY(prepare_linv(h, st));
+  double* rhs_g = h->cgbuf + 4 * D;        // Dg doubles of scratch (Schur preconditioner)
   // ||b||, x, r
   LRVB_CUDA(launch_pdl(k_dot, dim3(vgrid), dim3(256), 0, st, b_dev, b_dev, nullptr, nullptr, D, pqpart, nullptr));
   LRVB_CHECK_LAUNCH();
@@ -878,6 +915,28 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   while (it < maxiter) {
     const int end = (it + batch < maxiter) ? it + batch : maxiter;
     for (; it < end; ++it) {
+      if (kind == LRVB_PRECOND_SCHUR) {
+        // z = H^-1 r by block elimination with the caller's S^-1: M is the exact inverse
+        LRVB_CUDA(launch_pdl(k_solve_reduce, dim3(h->hvp_grid), dim3(256), sizeof(double) * 8 * (size_t)Dg, st, h->B,
+                             h->Linv, (const double*)r, h->hvppart, Dg, G));
+        LRVB_CUDA(launch_pdl(k_solve_reduce_finish, dim3(cdiv(Dg, 8)), dim3(256), 0, st, h->hvppart, h->hvp_grid,
+                             (const double*)r, rhs_g, Dg, 1));
+        LRVB_CUDA(launch_pdl(k_solve_global, dim3(cdiv(Dg, 8)), dim3(256), 0, st, M->Sinv_dev, (const double*)rhs_g, z, Dg));
+        g_launches += 3;
+        if (G > 0) {
+          LRVB_CUDA(launch_pdl(k_solve_local, dim3(h->hvp_grid), dim3(256), sizeof(double) * (size_t)Dg, st, h->B, h->Linv,
+                               (const double*)r, z, Dg, G));
+          ++g_launches;
+        }
+      } else if (kind == LRVB_PRECOND_CSR) {
+        LRVB_CUDA(launch_pdl(k_cg_m_csr, dim3(vgrid), dim3(256), 0, st, M->indptr_dev, M->indices_dev, M->data_dev,
+                             (const double*)r, z, D, (const int*)flags));
+        ++g_launches;
+      } else if (kind == LRVB_PRECOND_DENSE) {
+        LRVB_CUDA(launch_pdl(k_cg_m_dense, dim3(vgrid), dim3(256), 0, st, M->dense_dev, (const double*)r, z, D,
+                             (const int*)flags));
+        ++g_launches;
+      }
       LRVB_CUDA(launch_pdl(k_cg_precond, dim3(vgrid), dim3(256), 0, st, r, z, h->A, h->Linv, rrpart, vgrid, rzpart, h->scal, flags,
                                           Dg, G, precond));
       LRVB_CUDA(launch_pdl(k_cg_latch, dim3(1), dim3(1), 0, st, flags));
@@ -901,6 +960,21 @@ int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_
   }
   if (iters) *iters = hflags[1];
   return LRVB_OK;
+}
+
+int lrvb_glmm_cg(lrvb_glmm* h, const double* b_dev, const double* x0_dev, int32_t precond,
+                 double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
+                 void* stream) {
+  LRVB_REQUIRE(precond == 0 || precond == 1, "lrvb_glmm_cg: precond = %d not in {0,1}", precond);
+  lrvb_cg_precond M = {};
+  M.kind = precond;
+  return cg_run(h, b_dev, x0_dev, &M, rtol, maxiter, x_dev, info, iters, stream);
+}
+
+int lrvb_glmm_cg_m(lrvb_glmm* h, const double* b_dev, const double* x0_dev, const lrvb_cg_precond* M,
+                   double rtol, int32_t maxiter, double* x_dev, int32_t* info, int32_t* iters,
+                   void* stream) {
+  return cg_run(h, b_dev, x0_dev, M, rtol, maxiter, x_dev, info, iters, stream);
 }
 
 // ---- conjugate gradient over the shards of one job ------------------------------------------------

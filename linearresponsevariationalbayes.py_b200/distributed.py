@@ -120,12 +120,35 @@ class PeerAllReduce(object):
         nat.check(self._lib.lrvb_p2p_allreduce_sum(self._h, nat.ptr(t), t.numel(), nat.stream_ptr()))
         return t
 
-    def status(self):
+    def status(self, wait=True):
+        """0, or 1 + r when rank r missed the deadline (sticky; the results since are NaN and
+        ``all_reduce_`` raises RuntimeError).  ``wait=False`` reads the host word without
+        synchronising the stream."""
         import ctypes
         from . import _native as nat
         s = ctypes.c_int32()
-        nat.check(self._lib.lrvb_p2p_status(self._h, ctypes.byref(s), nat.stream_ptr()))
+        if wait:
+            nat.check(self._lib.lrvb_p2p_status(self._h, ctypes.byref(s), nat.stream_ptr()))
+        else:
+            nat.check(self._lib.lrvb_p2p_status_nowait(self._h, ctypes.byref(s)))
         return s.value
+
+    def set_timeout(self, seconds):
+        from . import _native as nat
+        nat.check(self._lib.lrvb_p2p_set_timeout(self._h, float(seconds)))
+
+    def set_stats(self, enable=True):
+        """Start (and reset) / stop the in-kernel accounting of the time spent waiting for peers."""
+        from . import _native as nat
+        nat.check(self._lib.lrvb_p2p_set_stats(self._h, 1 if enable else 0, nat.stream_ptr()))
+
+    def stats(self):
+        """dict(calls, wait_us_total, wait_us_max) since ``set_stats`` (synchronises)."""
+        import ctypes
+        from . import _native as nat
+        out = (ctypes.c_double * 3)()
+        nat.check(self._lib.lrvb_p2p_get_stats(self._h, out, nat.stream_ptr()))
+        return dict(calls=int(out[0]), wait_us_total=float(out[1]), wait_us_max=float(out[2]))
 
     def close(self):
         if self._h is not None and self._h.value:
@@ -353,6 +376,15 @@ class ShardedLogisticGLMM(object):
     def cg_local_layout(self, b, x0=None, precond=0, rtol=1e-8, maxiter=0):
         """scipy.sparse.linalg.cg's iteration (ConjugateGradient.py:81-85) on sharded vectors."""
         import torch
+        if isinstance(precond, str):
+            if precond != "block_jacobi":
+                raise ValueError("the sharded CG takes preconditioner None or 'block_jacobi'; got %r "
+                                 "(use LinearResponseCovariances(method='schur') for the exact solve)" % precond)
+            precond = 1
+        elif precond is None:
+            precond = 0
+        elif not isinstance(precond, int):
+            raise ValueError("the sharded CG takes preconditioner None or 'block_jacobi'")
         if maxiter <= 0:
             maxiter = 10 * self.D
         if self._peer is not None and self.Dg + 1 <= self._peer.max_elems:

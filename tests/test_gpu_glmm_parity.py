@@ -173,6 +173,36 @@ def test_cg_and_direct_solve(setup, vb):
     assert_close(cov_m, ref, rtol=1e-8, scale=np.abs(ref).max() * 1e-3, what="moment covariance")
 
 
+def test_cg_general_preconditioner(vb):
+    """scipy's M= (ConjugateGradient.py:84) on the device path: a sparse matrix, a dense array, the
+    block-Jacobi and Schur strings must all reach the dense solution; the exact inverse converges at once."""
+    import scipy.sparse
+    case = make_case(N=3000, K=4, G=25, Q=8, seed=77, bounds=0.05)
+    oracle, model = make_oracle(case), make_model(vb, case)
+    obj = vb.Objective(model.glmm_par, model)
+    xo, res = vb.OptimizationUtils.minimize_objective_newton(obj, case["free"], maxiter=50, gtol=1e-8)
+    assert res.success
+    Hd = oracle.kl_hessian_dense(xo)
+    b = np.random.default_rng(3).standard_normal(model.D)
+    xe = np.linalg.solve(Hd, b)
+    solver = vb.ConjugateGradientSolver(obj.fun_free_hvp, xo)
+    solver.tol = 1e-11
+    iters = {}
+    diag = scipy.sparse.diags(1.0 / np.diag(Hd)).tocsr()
+    for name, M in (("none", None), ("diag_csr", diag), ("dense_inv", np.linalg.inv(Hd)),
+                    ("block_jacobi", "block_jacobi"), ("schur", "schur")):
+        solver.preconditioner = M
+        xs, info = solver.get_hinv_vec(b)
+        assert info == 0, name
+        assert np.max(np.abs(xs - xe)) < 1e-8 * max(1.0, np.abs(xe).max()), name
+        iters[name] = solver.last_iterations
+    assert iters["schur"] <= 3 and iters["dense_inv"] <= 3, iters
+    assert iters["diag_csr"] < iters["none"], iters
+    solver.preconditioner = lambda v: v
+    with pytest.raises(ValueError):
+        solver.get_hinv_vec(b)
+
+
 def test_no_observations(vb):
     """N = 0 (a rank that owns no group in a sharded job, or priors only): the data kernels are
     skipped, the non-data terms and the Hessian pattern must still match the oracle."""

@@ -145,3 +145,56 @@ def test_peer_allreduce_and_sharded_model_all_gpus():
         assert res["newton_same"]
         assert res["cg_x0_fewer"] == 1.0
         assert res["cg_vs_torch_iters"] <= 2, res["cg_vs_torch_iters"]
+
+
+def _missing_peer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from lrvb_b200.distributed import PeerAllReduce
+        peer = PeerAllReduce.create(4096)
+        res = {"created": peer is not None}
+        if peer is None:
+            out[rank] = res
+            return
+        peer.set_timeout(0.5)
+        t = torch.full((100,), float(rank + 1), dtype=torch.float64, device=dev)
+        peer.all_reduce_(t)                       # a healthy call first
+        res["first_ok"] = bool((t == sum(range(1, world + 1))).all().item()) and peer.status() == 0
+        dist.barrier()
+        if rank != world - 1:
+            # the last rank never issues this call: the others must come back with a STATUS, not a trap
+            t2 = torch.ones(100, dtype=torch.float64, device=dev)
+            peer.all_reduce_(t2)
+            res["status"] = peer.status()          # syncs; 1 + (world - 1) = the missing rank
+            res["nan"] = bool(torch.isnan(t2).all().item())
+            # the CUDA context is alive: ordinary work still runs
+            res["context_alive"] = float((torch.ones(8, device=dev) * 2).sum().item()) == 16.0
+            try:
+                peer.all_reduce_(t2)
+                res["raises"] = False
+            except RuntimeError as exc:
+                res["raises"] = "did not arrive" in str(exc)
+        dist.barrier()
+        peer.close()
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_missing_peer_is_a_status_not_a_trap():
+    """a peer that never arrives within the deadline must not destroy the CUDA
+    context; the status word (mapped pinned host memory) names the missing rank, the output is NaN and
+    the communicator refuses further use."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_missing_peer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    assert out[0]["created"] and out[0]["first_ok"] and out[1]["first_ok"]
+    assert out[0]["status"] == world, out[0]
+    assert out[0]["nan"] and out[0]["context_alive"] and out[0]["raises"] is True, dict(out[0])
