@@ -477,7 +477,7 @@ def e2e_measure(ctx, res, steps, warmup):
         if sharded:
             # sharded: every rank brings ITS part of the distributed Hessian / gradient to its host
             model.evaluate(xh, 2)
-            H = model.hessian_csr().to_scipy()
+            H = model.local.hessian_scipy()
             gr = model.grad_local_layout().cpu().numpy()
             kl = float(model.kl_tensor().item())
             return H, gr, kl

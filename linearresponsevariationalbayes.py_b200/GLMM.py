@@ -83,12 +83,31 @@ class DeviceCSR(object):
     def values(self):
         return self._val[:self.nnz]
 
-    def to_scipy(self):
-        """Host copy as ``scipy.sparse.csr_matrix``.  The three arrays land in pinned host blocks
-        from torch's caching host allocator by asynchronous copies on the current stream (one
-        synchronisation); the scipy matrix keeps those blocks alive, no second host copy."""
+    def to_scipy(self, cache=None):
+        """Host copy as ``scipy.sparse.csr_matrix``.  The arrays land in pinned host blocks from
+        torch's caching host allocator by asynchronous copies on the current stream; the scipy
+        matrix keeps those blocks alive, no second host copy.
+
+        ``cache`` (a dict owned by the model): the sparsity pattern of an arrowhead Hessian is
+        static between evaluations unless an entry becomes exactly zero, so the host keeps the
+        last pattern (``indptr`` / ``indices``, read-only arrays shared by the matrices handed out)
+        next to its device copy; when the device comparison says the new pattern is identical only
+        ``data`` crosses PCIe (2/3 of the bytes) and the matrix is assembled without scipy's
+        O(nnz) validation pass."""
         import scipy.sparse
         torch = nat.require_cuda()
+        if cache is not None and cache.get("crow") is not None and cache["shape"] == self.shape \
+                and torch.equal(self.crow_indices, cache["crow"]):          # sync 1: (D+1) int32 compare
+            nnz = cache["nnz"]
+            same = (self._col[:nnz] == cache["col"]).all()
+            hv = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
+            hv.copy_(self._val[:nnz], non_blocking=True)
+            if bool(same.item()):                                            # sync 2: data has landed too
+                self._nnz = nnz
+                m = scipy.sparse.csr_matrix.__new__(scipy.sparse.csr_matrix)
+                m.__dict__.update(cache["template"])
+                m.data = hv.numpy()
+                return m
         host = []
         for t in (self.values, self.col_indices, self.crow_indices):
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -97,6 +116,13 @@ class DeviceCSR(object):
         torch.cuda.current_stream().synchronize()
         m = scipy.sparse.csr_matrix(tuple(h.numpy() for h in host), shape=self.shape, copy=False)
         m.has_sorted_indices = True
+        if cache is not None:
+            m.indices.flags.writeable = False     # shared with later matrices of the same pattern
+            m.indptr.flags.writeable = False
+            tmpl = dict(m.__dict__)
+            tmpl.pop("data", None)
+            cache.update(crow=self.crow_indices.clone(), col=self.col_indices.clone(), nnz=self.nnz,
+                         shape=self.shape, template=tmpl)
         return m
 
     def toarray(self):
@@ -206,6 +232,7 @@ class LogisticGLMM(object):
         self._x_event = None
         self._g_pin = None
         self._cache = dict(x=None, order=-1, coords=None)
+        self._pattern_cache = {}          # host + device copy of the last exported CSR pattern
         self._D_in = self.D
         self._coords = "free"
         self.device = dev
@@ -333,6 +360,23 @@ class LogisticGLMM(object):
         nat.check(self._lib.lrvb_glmm_obs_weights(self._h, ctypes.byref(w), ctypes.byref(ld)))
         return _view(w.value, (5, ld.value), self)[:, :self.N]
 
+    def max_abs_diagonal(self):
+        """Largest |H_ii| of the cached Hessian (one small device reduction)."""
+        A, _, L = self.blocks()
+        m = A.diagonal().abs().max()
+        if self.G > 0:
+            m = max(m, L[:, 0].abs().max(), L[:, 2].abs().max())
+        return float(m)
+
+    def add_diagonal_(self, lam):
+        """H <- H + lam I on the CACHED blocks (Levenberg damping of the device Newton iteration);
+        the next evaluation overwrites them."""
+        A, _, L = self.blocks()
+        A.diagonal().add_(float(lam))
+        if self.G > 0:
+            L[:, 0].add_(float(lam))
+            L[:, 2].add_(float(lam))
+
     def set_global_block(self, A):
         nat.check(self._lib.lrvb_glmm_set_global_block(self._h, nat.ptr(A), nat.stream_ptr()))
 
@@ -348,6 +392,11 @@ class LogisticGLMM(object):
         nat.check(self._lib.lrvb_glmm_hessian_csr(self._h, nat.ptr(crow), nat.ptr(col), nat.ptr(val),
                                                   cap.value, nat.ptr(nnz), nat.stream_ptr()))
         return DeviceCSR(crow, col, val, (self.D, self.D), nnz_dev=nnz)
+
+    def hessian_scipy(self):
+        """Host ``scipy.sparse.csr_matrix`` of the cached Hessian (what ``Objective.fun_free_hessian``
+        returns for numpy input, SparseObjectives.py:156-158); re-uses the cached pattern."""
+        return self.hessian_csr().to_scipy(cache=self._pattern_cache)
 
     def hvp_cached(self, v_dev, out=None, include_A=True):
         """H v with the cached Hessian; v_dev a CUDA fp64 tensor (D,)."""

@@ -95,8 +95,10 @@ def minimize_objective_newton(objective, init_x, maxiter=50, gtol=1e-8, disp=Fal
 
     Each iteration: one order-2 evaluation (KL, gradient, Hessian blocks), ``step = -H^{-1} g`` by
     the Schur-complement solve of the cached Hessian, Armijo backtracking with order-0
-    evaluations.  Where the Hessian is not positive definite (step not a descent direction, or
-    not finite) the iteration falls back to a normalised gradient step.  Returns
+    evaluations.  Where the Hessian is not positive definite (the Schur complement has a
+    non-positive pivot, or the step is not a finite descent direction) the step is recomputed with
+    Levenberg damping ``(H + lambda I)^{-1} g``, lambda growing tenfold from 1e-3 of the largest
+    diagonal entry until the damped matrix is positive definite (``model.add_diagonal_``).  Returns
     ``(opt_x, scipy.optimize.OptimizeResult)`` like the scipy-driven optimisers above; ``opt_x`` is
     numpy for numpy input, a CUDA tensor for tensor input.
     """
@@ -124,11 +126,23 @@ def minimize_objective_newton(objective, init_x, maxiter=50, gtol=1e-8, disp=Fal
             break
         if it == maxiter:
             break
-        step = -model.solve(g).reshape(-1)
-        slope = float(torch.dot(g, step).item())
-        if not np.isfinite(slope) or slope >= 0.0:
-            step = -g / max(1.0, float(g.norm().item()))     # not positive definite here
-            slope = float(torch.dot(g, step).item())
+        step, slope, lam, lam_total = None, 0.0, 0.0, 0.0
+        for _try in range(24):
+            try:
+                step = -model.solve(g).reshape(-1)
+                slope = float(torch.dot(g, step).item())
+            except np.linalg.LinAlgError:
+                slope = float("nan")
+            if np.isfinite(slope) and slope < 0.0:
+                break
+            # not positive definite here: damp the cached blocks (the next iteration re-evaluates them)
+            lam = 1e-3 * model.max_abs_diagonal() if lam == 0.0 else 10.0 * lam
+            model.add_diagonal_(lam - lam_total)
+            lam_total = lam
+            step = None
+        if step is None:
+            message = "no descent direction found"
+            break
         t, accepted = 1.0, False
         for _ in range(max_backtracks):
             xn = x + t * step

@@ -150,6 +150,8 @@ class Objective(object):
             return self.model.hessian_csr()      # device CSR (a sharded model: this rank's part)
         if hasattr(self.model, "hessian_csr_global"):
             return self.model.hessian_csr_global()   # sharded model: gather the full matrix
+        if hasattr(self.model, "hessian_scipy"):
+            return self.model.hessian_scipy()
         return self.model.hessian_csr().to_scipy()
 
     def _hvp(self, x, vec, coords):

@@ -9,6 +9,7 @@
 #include "obs_fused.cuh"
 #include "gram_mid.cuh"
 #include "gram_big.cuh"
+#include "fused.cuh"
 
 namespace lrvb {
 
@@ -174,9 +175,25 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     const int64_t tw = grid * h->of_warps;
     h->of_rows_per_warp = ((nst + tw - 1) / tw) * kOfRows;
     h->of_smem = obs_fused_smem(K, Q, h->of_warps);
-    CREATE_TRY(dev_alloc(&h->bval, (size_t)tw * 2 * (5 + 4 * (size_t)K)));
+    int64_t nrec = tw;
+    {
+      // order 2 in one pass (fused.cuh): teams of one quadrature warp + P DMMA warps, one CTA per SM
+      const char* fe = getenv("LRVB_FUSED");
+      const FusedGeom fg = fused_geom((2 * K + 7) / 8);
+      int64_t fgrid = (nst + fg.teams - 1) / fg.teams;
+      if (fgrid > kNumSMs) fgrid = kNumSMs;
+      if (fgrid < 1) fgrid = 1;
+      const int64_t tt = fgrid * fg.teams;
+      h->fused2 = !(fe && fe[0] == '0');
+      h->fu_grid = (int)fgrid;
+      h->fu_teams = fg.teams;
+      h->fu_rows_per_team = ((nst + tt - 1) / tt) * kFuRows;
+      if (tt > nrec) nrec = tt;
+    }
+    CREATE_TRY(dev_alloc(&h->bval, (size_t)nrec * 2 * (5 + 4 * (size_t)K)));
     configure_obs_fused(h->of_smem);
     if (h->obs_grid < h->of_grid) h->obs_grid = h->of_grid;
+    if (h->obs_grid < h->fu_grid) h->obs_grid = h->fu_grid;     // klpart / gradpart are sized by obs_grid
   }
   CREATE_TRY(dev_alloc(&h->klpart, (size_t)h->obs_grid));
   CREATE_TRY(dev_alloc(&h->gradpart, (size_t)h->obs_grid * 2 * K));
@@ -271,7 +288,8 @@ int lrvb_glmm_last_timing(lrvb_glmm* h, float* ms3) {
   LRVB_CUDA(cudaEventElapsedTime(&ms3[0], h->ev[4], h->ev[5]));
   if (h->N > 0) {
     LRVB_CUDA(cudaEventElapsedTime(&ms3[1], h->ev[0], h->ev[1]));
-    if (h->ev_order >= 2) LRVB_CUDA(cudaEventElapsedTime(&ms3[2], h->ev[2], h->ev[3]));
+    // with the one-pass kernel (fused.cuh) there is no separate Gram launch: ms3[2] stays 0
+    if (h->ev_order >= 2 && h->ev_gram) LRVB_CUDA(cudaEventElapsedTime(&ms3[2], h->ev[2], h->ev[3]));
   }
   return LRVB_OK;
 }

@@ -20,6 +20,7 @@
 #include "gram_mid.cuh"
 #define LRVB_GRAM_BIG_KERNELS
 #include "gram_big.cuh"
+#include "fused.cuh"
 
 namespace lrvb {
 
@@ -623,7 +624,29 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   LRVB_CHECK_LAUNCH();
 
   int n_obs_cta = 0;
-  if (h->obs_fused) {
+  const bool one_pass = h->fused2 && order >= 2 && N > 0;
+  h->ev_gram = 0;
+  if (one_pass) {
+    // order 2, K <= 62: quadrature, per-group sums and the packed Gram in ONE pass over X (fused.cuh)
+    if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
+    FusedArgs fa;
+    fa.X = h->X; fa.y = h->y; fa.g = h->g; fa.w = h->w; fa.vec = h->vec; fa.gh = h->gh; fa.gptr = h->gptr;
+    fa.W = h->W; fa.ldw = h->ldw; fa.klpart = h->klpart; fa.gradpart = h->gradpart; fa.gsc = h->gsc; fa.BR = h->BR;
+    fa.bval = h->bval; fa.grampart = h->grampart; fa.N = N; fa.K = K; fa.G = G; fa.Q = Q;
+    fa.rows_per_team = h->fu_rows_per_team;
+    if (!launch_fused_eval(fa, h->fu_grid, Q, st)) {
+      set_error("launch_eval: one-pass kernel rejected K = %d / alignment", K);
+      return LRVB_ESTATE;
+    }
+    LRVB_CHECK_LAUNCH();
+    if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
+    n_obs_cta = h->fu_grid;
+    if (G > 0) {
+      LRVB_CUDA(launch_pdl(k_obs_fixup<2>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G,
+                           h->fu_rows_per_team));
+      LRVB_CHECK_LAUNCH();
+    }
+  } else if (h->obs_fused) {
     // K <= 62: observation pass and per-group sums in one kernel (obs_fused.cuh)
     if (N > 0) {
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
@@ -676,8 +699,9 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     LRVB_CHECK_LAUNCH();
   }
   }
-  if (order >= 2) {
+  if (order >= 2 && !one_pass) {
     if (N > 0) {
+      h->ev_gram = 1;
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[2], st));
       if (h->gram_small) {
         if (!launch_gram_small(h->X, h->W + 2 * h->ldw, h->grampart, N, h->ldw, K, h->gram_grid_x, st)) {
@@ -702,20 +726,22 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   {
     const int n_loc = h->loc_grid;
     int n_bor = 0, n_gf = 0, NT = 0;
+    const int packed_gram = (h->gram_small || h->gram_mid || one_pass) ? 1 : 0;   // partial layout (n_cta, NT, 64)
+    const int packed_ctas = one_pass ? h->fu_grid : h->gram_grid_x;
     if (order >= 2) {
       if (G > 0) n_bor = cdiv((int64_t)G * Dg, 256);
       if (N > 0) {
-        if (h->gram_small || h->gram_mid) { NT = gram_small_shape(K).NT; n_gf = NT; }
+        if (packed_gram) { NT = gram_small_shape(K).NT; n_gf = NT; }
         else n_gf = h->gram_jobs * 16;
       }
     }
     const int grid = n_loc + n_bor + n_gf;
-    const int packed_gram = (h->gram_small || h->gram_mid) ? 1 : 0;   // partial layout (n_cta, NT, 64)
+
 #define LRVB_FIN(O)                                                                              \
   LRVB_CUDA(launch_pdl(k_finish<O>, dim3(grid), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
                        h->locpart, h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,   \
                        outp + 1 + Dg, K, G, n_loc, n_bor, packed_gram, NT, h->gram_grid_y,         \
-                       packed_gram ? h->gram_grid_x : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
+                       packed_gram ? packed_ctas : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
                        h->bounds, h->vecmode))
     if (order == 0) LRVB_FIN(0);
     else if (order == 1) LRVB_FIN(1);

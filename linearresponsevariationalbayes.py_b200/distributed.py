@@ -434,6 +434,18 @@ class ShardedLogisticGLMM(object):
         x, info, iters = self.cg_local_layout(b, x0, precond, rtol, maxiter)
         return self.from_local(x), info, iters
 
+    def max_abs_diagonal(self):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([self.local.max_abs_diagonal()], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.pg)
+        return float(t.item())
+
+    def add_diagonal_(self, lam):
+        # A is a replica on every rank (only rank 0's copy enters the Schur complement and the HVP)
+        self.local.add_diagonal_(lam)
+        self._sinv = None
+
     def global_covariance(self):
         """(H^-1)_gg: all-reduce of the per-rank Schur pieces, then the small SPD inverse."""
         if self._sinv is None:
