@@ -203,8 +203,8 @@ struct lrvb_glmm {
   size_t of_smem = 0;
   int64_t of_rows_per_warp = 0;
   double* bval = nullptr;     // (of_grid * of_warps, 2, 5 + 4K) head / tail pieces of straddling groups
-  // order-2 evaluation in one pass (fused.cuh): quadrature warps + DMMA warps on the same stage of X
-  int fused2 = 0, fu_grid = 0, fu_teams = 0;
+  // order-2 evaluation in one pass (team.cuh): teams of warps do quadrature, group sums and Gram per stage
+  int fused2 = 0, fu_grid = 0, fu_teams = 0, fu_warps = 0;
   int64_t fu_rows_per_team = 0;
   int ev_gram = 0;            // the last timed evaluation ran a separate Gram kernel
   // group pass

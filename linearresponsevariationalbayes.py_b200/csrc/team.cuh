@@ -32,6 +32,10 @@ namespace lrvb {
 
 constexpr int kTeRows = 32;
 constexpr int kTeSlots = 2;
+#ifndef LRVB_TEAM_MAXWARPS
+#define LRVB_TEAM_MAXWARPS 12
+#endif
+constexpr int kTeMaxWarps = LRVB_TEAM_MAXWARPS;      // 12 warps x 168 registers: no spills (see TeamQC)
 #ifndef LRVB_TEAM_UNROLL
 #define LRVB_TEAM_UNROLL 4
 #endif
@@ -50,10 +54,10 @@ inline size_t team_smem(int K, int Q, int T2, int warps) {
   return body + sizeof(double) * (2 * (size_t)K + 2 * Q + (size_t)teams * 2 * K + teams) +
          sizeof(unsigned long long) * (size_t)teams * kTeSlots;
 }
-// the largest warp count (multiple of P, <= 16) whose shared memory fits
+// the largest warp count (multiple of P, <= kTeMaxWarps) whose shared memory fits
 inline int team_max_warps(int K, int Q, int T2) {
   const int P = team_P(T2);
-  int w = 16 / P * P;
+  int w = kTeMaxWarps / P * P;
   while (w > P && team_smem(K, Q, T2, w) > 225 * 1024) w -= P;
   return w;
 }
@@ -68,6 +72,303 @@ __device__ __forceinline__ void team_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Per-warp state of the quadrature / group-sum phases (scalar-replaced into registers: everything is
+// inlined).  Nothing here may live in local memory: with ~215 KB of the SM's 256 KB SRAM carved out as
+// shared memory the L1 that would back spills or an ABI call's register saves is a few KB for 384 threads,
+// and a first version that called the Q / C phases as a non-inlined function (accumulators saved around
+// the call once per stage) ran 1.5 - 2.4x SLOWER than the two separate kernels for exactly that reason
+// (profiles/r02_onepass_attempts.md).  Hence 12 warps x 168 registers rather than 16 x 128.
+template <int NCHW>
+struct TeamQC {
+  const double *bm, *bv, *ghc, *ghw;
+  double *ring, *wq, *part, *gred_row, *kred_slot;
+  unsigned ring_u, full_u;
+  int64_t gw, rs, re;
+  int nst, R, team, skew, chunk0, cur_g;
+  bool c_warp;
+  double klacc;
+  double gm[NCHW], gv[NCHW], q0[NCHW], q1[NCHW], q2[NCHW], q3[NCHW], q4[NCHW], q5[NCHW];
+};
+
+template <int P, int NCHW>
+__device__ __forceinline__ void team_issue(const FusedArgs& a, const TeamQC<NCHW>& c, int st, int slot) {
+  const int lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int64_t n0 = c.rs + (int64_t)st * kTeRows;
+  const unsigned nops = a.w ? 4u : 3u;
+  if (st < c.nst && n0 + kTeRows <= a.N && lane < (int)nops) {
+    const unsigned xbytes = (unsigned)(kTeRows * K * sizeof(double));
+    const unsigned vbytes = (unsigned)(kTeRows * sizeof(double));
+    const unsigned gbytes = (unsigned)(kTeRows * sizeof(int32_t));
+    const unsigned bar = c.full_u + 8 * slot;
+    const unsigned dst = c.ring_u + (unsigned)(slot * team_slot_elems(K) * sizeof(double));
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, xbytes + (a.w ? 2 : 1) * vbytes + gbytes);
+      bulk_g2s(dst, a.X + n0 * K, xbytes, bar);
+    } else if (lane == 1) {
+      bulk_g2s(dst + xbytes, a.y + n0, vbytes, bar);
+    } else if (lane == 2) {
+      bulk_g2s(dst + xbytes + 2 * vbytes, a.g + n0, gbytes, bar);
+    } else {
+      bulk_g2s(dst + xbytes + vbytes, a.w + n0, vbytes, bar);
+    }
+  }
+}
+
+template <int NCHW>
+__device__ __forceinline__ void team_flush(const FusedArgs& a, TeamQC<NCHW>& c) {
+  if (c.cur_g < 0) return;
+  const int lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int nb = 5 + 4 * K;
+  const int64_t gb = a.gptr[c.cur_g], ge = a.gptr[c.cur_g + 1];
+  double* dbr;
+  double* dsc;
+  if (gb >= c.rs && ge <= c.re) {          // the whole group lies inside the team's range
+    dbr = a.BR + (size_t)c.cur_g * 4 * K;
+    dsc = a.gsc + (size_t)c.cur_g * 5;
+  } else {                                 // head (starts before the range) or tail piece
+    double* rec = a.bval + ((size_t)c.gw * 2 + (gb < c.rs ? 0 : 1)) * nb;
+    dsc = rec;
+    dbr = rec + 5;
+  }
+#pragma unroll
+  for (int i = 0; i < NCHW; ++i) {
+    const int k = lane + 32 * (c.chunk0 + i);
+    if (k < K) {
+      dbr[k] = c.q2[i];
+      dbr[K + k] = c.q3[i];
+      dbr[2 * K + k] = c.q4[i];
+      dbr[3 * K + k] = c.q5[i];
+      c.gm[i] += c.q0[i];
+      c.gv[i] += c.q1[i];
+    } else if (k == K) {                   // ones column: sum l_m, l_v, a, b, c
+      dsc[0] = c.q0[i];
+      dsc[1] = c.q1[i];
+      dsc[2] = c.q2[i];
+      dsc[3] = c.q3[i];
+      dsc[4] = c.q5[i];
+    }
+    c.q0[i] = c.q1[i] = c.q2[i] = c.q3[i] = c.q4[i] = c.q5[i] = 0.0;
+  }
+}
+
+// Phases Q and C of stage `st` (slot `slot`, full-barrier parity `phase`) for one warp.
+template <int P, int NCHW>
+__device__ __forceinline__ void team_qc_stage(const FusedArgs& a, TeamQC<NCHW>& c, int st, int slot, unsigned phase) {
+  constexpr int UNR = LRVB_TEAM_UNROLL;
+  const int lane = threadIdx.x & 31;
+  const int K = a.K, G = a.G, Q = a.Q;
+  const int64_t N = a.N, ldw = a.ldw;
+  const double* __restrict__ vec = a.vec;
+  const double* __restrict__ w = a.w;
+  const double* __restrict__ bm = c.bm;
+  const double* __restrict__ bv = c.bv;
+  const double* __restrict__ ghc = c.ghc;
+  const double* __restrict__ ghw = c.ghw;
+  double* __restrict__ W = a.W;
+  const int R = c.R;
+  const int slot_elems = team_slot_elems(K);
+  const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
+  const int64_t n0 = c.rs + (int64_t)st * kTeRows;
+  double* xs = c.ring + (size_t)slot * slot_elems;
+  double* ys = xs + kTeRows * K;
+  const int32_t* gs = reinterpret_cast<const int32_t*>(ys + 2 * kTeRows);
+  double* wq = c.wq;
+  const int rows = (int)((c.re - n0 < kTeRows) ? (c.re - n0) : kTeRows);
+  if (R == 0 && n0 + kTeRows > N) {
+    // ragged last stage of the data set: filled by warp 0 itself (zero rows beyond N); every warp of
+    // the team has passed the barrier of stage st - 1, so the slot's previous use (st - 2) is over
+    const int vr = (int)(N - n0);
+    for (int e = lane; e < kTeRows * K; e += 32) xs[e] = (e < vr * K) ? a.X[n0 * K + e] : 0.0;
+    ys[lane] = (lane < vr) ? a.y[n0 + lane] : 0.0;
+    ys[kTeRows + lane] = (lane < vr && w) ? w[n0 + lane] : 0.0;
+    reinterpret_cast<int32_t*>(ys + 2 * kTeRows)[lane] = (lane < vr) ? a.g[n0 + lane] : -1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.full_u + 8 * slot);
+  }
+  mbar_wait(c.full_u + 8 * slot, phase);
+
+  // ---- Q: lane = observation ----
+  unsigned segmask = 0;
+  {
+    const int64_t n = n0 + lane;
+    const bool valid = lane < rows;
+    const int gi = valid ? gs[lane] : 0;
+    if (c.c_warp) {
+      const int gprev = __shfl_up_sync(0xffffffffu, gi, 1);
+      segmask = __ballot_sync(0xffffffffu, valid && (lane == 0 ? gi != c.cur_g : gi != gprev));
+    }
+    double zm = vec[um0 + gi];
+    double zv = 1.0 / vec[ui0 + gi];
+    const double* xr = xs + (size_t)lane * K;
+    const int skew = c.skew;
+    for (int k = skew; k < K; ++k) {
+      const double x = xr[k];
+      zm = fma(x, bm[k], zm);
+      zv = fma(x * x, bv[k], zv);
+    }
+    for (int k = 0; k < skew; ++k) {
+      const double x = xr[k];
+      zm = fma(x, bm[k], zm);
+      zv = fma(x * x, bv[k], zv);
+    }
+    const double zs = sqrt(zv);
+    GHSumsF s = {0, 0, 0, 0, 0, 0};
+    GHSumsF s2 = {0, 0, 0, 0, 0, 0};
+    int q = R;
+    for (; q + (UNR - 1) * P < Q; q += UNR * P) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const double cq = ghc[q + u * P];
+        gh_node_f<2>(fma(zs, cq, zm), cq, ghw[q + u * P], (u & 1) ? s2 : s);
+      }
+    }
+    for (; q + P < Q; q += 2 * P) {      // two nodes in flight for the remainder (and when Q / P < UNR)
+      const double c0 = ghc[q], c1 = ghc[q + P];
+      gh_node_f<2>(fma(zs, c0, zm), c0, ghw[q], s);
+      gh_node_f<2>(fma(zs, c1, zm), c1, ghw[q + P], s2);
+    }
+    for (; q < Q; q += P) {
+      const double c0 = ghc[q];
+      gh_node_f<2>(fma(zs, c0, zm), c0, ghw[q], s);
+    }
+    s.A += s2.A; s.Am += s2.Am; s.As += s2.As; s.Amm += s2.Amm; s.Ams += s2.Ams; s.Ass += s2.Ass;
+    if (P > 1) {
+      // exchange the partial node sums: per warp [parity][6][32], summed in warp order
+      constexpr int PW = 3 * 6 * kTeRows;          // per-warp block: wq | partials (parity 0) | partials (parity 1)
+      double* mp = c.part + (size_t)(st & 1) * 6 * kTeRows;
+      mp[lane] = s.A; mp[32 + lane] = s.Am; mp[64 + lane] = s.As;
+      mp[96 + lane] = s.Amm; mp[128 + lane] = s.Ams; mp[160 + lane] = s.Ass;
+      team_bar(1 + c.team, 32 * P);
+      // every warp of the team is past stage st - 1: its slot is free for stage st + 1
+      if (R == 0 && st >= 1) team_issue<P, NCHW>(a, c, st + 1, slot ^ 1);
+      const double* tp = mp - (size_t)R * PW;      // warp 0's block of this parity
+      s.A = s.Am = s.As = s.Amm = s.Ams = s.Ass = 0.0;
+#pragma unroll
+      for (int r2 = 0; r2 < P; ++r2) {
+        const double* op = tp + (size_t)r2 * PW;
+        s.A += op[lane]; s.Am += op[32 + lane]; s.As += op[64 + lane];
+        s.Amm += op[96 + lane]; s.Ams += op[128 + lane]; s.Ass += op[160 + lane];
+      }
+    }
+    const double wn = valid ? (w ? ys[kTeRows + lane] : 1.0) : 0.0;
+    const double yn = ys[lane];
+    const double h = 0.5 / zs;
+    const double lm = wn * (yn - s.Am);
+    const double lv = -wn * s.As * h;
+    const double wa = -wn * s.Amm;
+    const double wb = -wn * s.Ams * h;
+    const double wc = -wn * (s.Ass - s.As / zs) / (4.0 * zv);     // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
+    double2* wrow = reinterpret_cast<double2*>(wq + 6 * lane);
+    wrow[0] = make_double2(lm, lv);
+    wrow[1] = make_double2(wa, wb);
+    wrow[2] = make_double2(wc, 0.0);
+    if (R == 0) {
+      c.klacc += wn * (yn * zm - s.A);
+      if (valid && W) {
+        W[n] = lm;
+        W[ldw + n] = lv;
+        W[2 * ldw + n] = wa;
+        W[3 * ldw + n] = wb;
+        W[4 * ldw + n] = wc;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- C: lane = column; per-group running sums of this warp's chunk(s) ----
+  if (c.c_warp) {
+    const double2* w2 = reinterpret_cast<const double2*>(wq);
+    int koff[NCHW];
+    bool isone[NCHW];
+    double q0[NCHW], q1[NCHW], q2[NCHW], q3[NCHW], q4[NCHW], q5[NCHW];
+#pragma unroll
+    for (int i = 0; i < NCHW; ++i) {
+      const int k = lane + 32 * (c.chunk0 + i);
+      koff[i] = (k < K) ? k : 0;
+      isone[i] = (k == K);
+      q0[i] = c.q0[i]; q1[i] = c.q1[i]; q2[i] = c.q2[i]; q3[i] = c.q3[i]; q4[i] = c.q4[i]; q5[i] = c.q5[i];
+    }
+    auto rows_acc = [&](int r, auto nrow) {
+      constexpr int NR = decltype(nrow)::value;
+      double2 wl[NR], wab[NR], wc2[NR];
+      double x[NR][NCHW];
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        wl[u] = w2[3 * (r + u)];
+        wab[u] = w2[3 * (r + u) + 1];
+        wc2[u] = w2[3 * (r + u) + 2];
+#pragma unroll
+        for (int i = 0; i < NCHW; ++i) {
+          const double v = xs[(size_t)(r + u) * K + koff[i]];
+          x[u][i] = isone[i] ? 1.0 : v;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCHW; ++i) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+          const double xv = x[u][i], xx = xv * xv;
+          t0 = fma(wl[u].x, xv, t0);
+          t1 = fma(wl[u].y, xx, t1);
+          t2 = fma(wab[u].x, xv, t2);
+          t3 = fma(wab[u].y, xv, t3);
+          t4 = fma(wab[u].y, xx, t4);
+          t5 = fma(wc2[u].x, xx, t5);
+        }
+        q0[i] += t0; q1[i] += t1; q2[i] += t2; q3[i] += t3; q4[i] += t4; q5[i] += t5;
+      }
+    };
+    int r = 0;
+    const unsigned m = segmask;
+    while (r < rows) {
+      if ((m >> r) & 1u) {            // row r opens a new group
+#pragma unroll
+        for (int i = 0; i < NCHW; ++i) {
+          c.q0[i] = q0[i]; c.q1[i] = q1[i]; c.q2[i] = q2[i]; c.q3[i] = q3[i]; c.q4[i] = q4[i]; c.q5[i] = q5[i];
+        }
+        team_flush<NCHW>(a, c);
+#pragma unroll
+        for (int i = 0; i < NCHW; ++i) q0[i] = q1[i] = q2[i] = q3[i] = q4[i] = q5[i] = 0.0;
+        c.cur_g = gs[r];
+      }
+      const unsigned rest = (r + 1 < 32) ? (m >> (r + 1)) : 0u;
+      const int nxt = rest ? (r + 1 + __ffs((int)rest) - 1) : rows;
+      const int r1 = nxt < rows ? nxt : rows;
+      for (; r + 4 <= r1; r += 4) rows_acc(r, std::integral_constant<int, 4>());
+      for (; r < r1; ++r) rows_acc(r, std::integral_constant<int, 1>());
+    }
+#pragma unroll
+    for (int i = 0; i < NCHW; ++i) {
+      c.q0[i] = q0[i]; c.q1[i] = q1[i]; c.q2[i] = q2[i]; c.q3[i] = q3[i]; c.q4[i] = q4[i]; c.q5[i] = q5[i];
+    }
+  }
+}
+
+// last flush + the warp's KL / global-gradient partials
+template <int NCHW>
+__device__ __forceinline__ void team_qc_finish(const FusedArgs& a, TeamQC<NCHW>& c) {
+  const int lane = threadIdx.x & 31;
+  const int K = a.K;
+  if (c.c_warp) team_flush<NCHW>(a, c);
+  if (c.R == 0) {
+    const double kl = warp_sum(c.klacc);
+    if (lane == 0) *c.kred_slot = kl;
+  }
+  if (c.c_warp) {
+#pragma unroll
+    for (int i = 0; i < NCHW; ++i) {
+      const int k = lane + 32 * (c.chunk0 + i);
+      if (k < K) {
+        c.gred_row[k] = c.gm[i];
+        c.gred_row[K + k] = c.gv[i];
+      }
+    }
+  }
+}
+
 // One warp of a team: role R of P, tile range [TLO, THI).  NCHW = column chunks this warp may own.
 template <int T2, int T0, bool HAS_M, int P, int R, int TLO, int THI, int NCHW>
 __device__ __forceinline__ void team_run(const FusedArgs& a, double* ring, unsigned ring_u, unsigned full_u,
@@ -79,29 +380,36 @@ __device__ __forceinline__ void team_run(const FusedArgs& a, double* ring, unsig
   constexpr int JLO = gram_mid_col(TLO), JHI = gram_mid_col(THI - 1) + 1;
   constexpr int NTL = THI - TLO;
   constexpr int KSTEPS = kTeRows / 4;
-  constexpr int UNR = LRVB_TEAM_UNROLL;
   auto mine = [](int i, int j) constexpr { return j * (j + 1) / 2 + i >= TLO && j * (j + 1) / 2 + i < THI; };
   const int lane = threadIdx.x & 31;
   const int lr = lane & 3, lc = lane >> 2;
-  const int K = a.K, G = a.G, Q = a.Q;
-  const int64_t N = a.N, ldw = a.ldw;
-  const double* __restrict__ X = a.X;
-  const double* __restrict__ y = a.y;
-  const int32_t* __restrict__ g = a.g;
-  const double* __restrict__ w = a.w;
-  const double* __restrict__ vec = a.vec;
-  const int32_t* __restrict__ gptr = a.gptr;
-  double* __restrict__ W = a.W;
+  const int K = a.K;
   const int slot_elems = team_slot_elems(K);
-  const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
-  const int64_t rs = gw * a.rows_per_team;
-  const int64_t re = (rs + a.rows_per_team < N) ? rs + a.rows_per_team : N;
-  const int nst = (rs < re) ? (int)((re - rs + kTeRows - 1) / kTeRows) : 0;
-  const unsigned xbytes = (unsigned)(kTeRows * K * sizeof(double));
-  const unsigned vbytes = (unsigned)(kTeRows * sizeof(double));
-  const unsigned gbytes = (unsigned)(kTeRows * sizeof(int32_t));
-  const unsigned nops = w ? 4u : 3u;
   const unsigned wq_u = smem_u32(wq);
+
+  TeamQC<NCHW> c;
+  c.bm = bm; c.bv = bv; c.ghc = ghc; c.ghw = ghw;
+  c.ring = ring; c.wq = wq; c.part = part; c.gred_row = gred_row; c.kred_slot = kred_slot;
+  c.ring_u = ring_u; c.full_u = full_u;
+  c.gw = gw;
+  c.rs = gw * a.rows_per_team;
+  c.re = (c.rs + a.rows_per_team < a.N) ? c.rs + a.rows_per_team : a.N;
+  c.nst = (c.rs < c.re) ? (int)((c.re - c.rs + kTeRows - 1) / kTeRows) : 0;
+  c.R = R; c.team = team;
+  {
+    int gcd16 = 1;
+    while (gcd16 < 16 && (K % (gcd16 * 2)) == 0) gcd16 *= 2;
+    int skew = ((lane & 15) * gcd16) >> 4;      // bank-conflict skew of the row-per-lane reads
+    c.skew = skew >= K ? 0 : skew;
+  }
+  const int nch_total = (K + 1 + 31) / 32;
+  c.c_warp = (P == 1) || (R < nch_total);
+  c.chunk0 = (P == 1) ? 0 : R;
+  c.cur_g = -1;
+  c.klacc = 0.0;
+#pragma unroll
+  for (int i = 0; i < NCHW; ++i) c.gm[i] = c.gv[i] = c.q0[i] = c.q1[i] = c.q2[i] = c.q3[i] = c.q4[i] = c.q5[i] = 0.0;
+  const int nst = c.nst;
 
   // ---- D operands: per-lane offsets of the packed columns inside a staged row ----
   const int base = lr * K + lc;
@@ -122,237 +430,16 @@ __device__ __forceinline__ void team_run(const FusedArgs& a, double* ring, unsig
 #pragma unroll
   for (int t = 0; t < NTL; ++t) acc[t][0] = acc[t][1] = 0.0;
 
-  // ---- C state: column chunk(s) of this warp ----
-  const int nch_total = (K + 1 + 31) / 32;
-  const bool c_warp = (P == 1) || (R < nch_total);
-  const int chunk0 = (P == 1) ? 0 : R;
-  double gm[NCHW], gv[NCHW];
-  double q0[NCHW], q1[NCHW], q2[NCHW], q3[NCHW], q4[NCHW], q5[NCHW];
-#pragma unroll
-  for (int c = 0; c < NCHW; ++c) gm[c] = gv[c] = q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = q5[c] = 0.0;
-  int cur_g = -1;
-  double klacc = 0.0;
-  const int nb = 5 + 4 * K;
-
-  auto issue = [&](int st, int slot) {      // warp 0 of the team only
-    const int64_t n0 = rs + (int64_t)st * kTeRows;
-    if (st < nst && n0 + kTeRows <= N && lane < (int)nops) {
-      const unsigned bar = full_u + 8 * slot;
-      const unsigned dst = ring_u + (unsigned)(slot * slot_elems * sizeof(double));
-      if (lane == 0) {
-        mbar_arrive_expect_tx(bar, xbytes + (w ? 2 : 1) * vbytes + gbytes);
-        bulk_g2s(dst, X + n0 * K, xbytes, bar);
-      } else if (lane == 1) {
-        bulk_g2s(dst + xbytes, y + n0, vbytes, bar);
-      } else if (lane == 2) {
-        bulk_g2s(dst + xbytes + 2 * vbytes, g + n0, gbytes, bar);
-      } else {
-        bulk_g2s(dst + xbytes + vbytes, w + n0, vbytes, bar);
-      }
-    }
-  };
-  auto flush = [&]() {
-    if (cur_g < 0) return;
-    const int64_t gb = gptr[cur_g], ge = gptr[cur_g + 1];
-    double* dbr;
-    double* dsc;
-    if (gb >= rs && ge <= re) {
-      dbr = a.BR + (size_t)cur_g * 4 * K;
-      dsc = a.gsc + (size_t)cur_g * 5;
-    } else {
-      double* rec = a.bval + ((size_t)gw * 2 + (gb < rs ? 0 : 1)) * nb;
-      dsc = rec;
-      dbr = rec + 5;
-    }
-#pragma unroll
-    for (int c = 0; c < NCHW; ++c) {
-      const int k = lane + 32 * (chunk0 + c);
-      if (k < K) {
-        dbr[k] = q2[c];
-        dbr[K + k] = q3[c];
-        dbr[2 * K + k] = q4[c];
-        dbr[3 * K + k] = q5[c];
-        gm[c] += q0[c];
-        gv[c] += q1[c];
-      } else if (k == K) {
-        dsc[0] = q0[c];
-        dsc[1] = q1[c];
-        dsc[2] = q2[c];
-        dsc[3] = q3[c];
-        dsc[4] = q5[c];
-      }
-      q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = q5[c] = 0.0;
-    }
-  };
-
-  int gcd16 = 1;
-  while (gcd16 < 16 && (K % (gcd16 * 2)) == 0) gcd16 *= 2;
-  int skew = ((lane & 15) * gcd16) >> 4;
-  if (skew >= K) skew = 0;
-
   if (R == 0) {
 #pragma unroll
-    for (int p = 0; p < kTeSlots; ++p) issue(p, p);
+    for (int p = 0; p < kTeSlots; ++p) team_issue<P, NCHW>(a, c, p, p);
   }
 
   int slot = 0;
   unsigned phase = 0;
+#pragma unroll 1
   for (int st = 0; st < nst; ++st) {
-    const int64_t n0 = rs + (int64_t)st * kTeRows;
-    double* xs = ring + (size_t)slot * slot_elems;
-    double* ys = xs + kTeRows * K;
-    const int32_t* gs = reinterpret_cast<const int32_t*>(ys + 2 * kTeRows);
-    const int rows = (int)((re - n0 < kTeRows) ? (re - n0) : kTeRows);
-    if (R == 0 && n0 + kTeRows > N) {
-      // ragged last stage of the data set: filled by warp 0 itself (zero rows beyond N); every warp of
-      // the team has passed the barrier of stage st - 1, so the slot's previous use (st - 2) is over
-      const int vr = (int)(N - n0);
-      for (int e = lane; e < kTeRows * K; e += 32) xs[e] = (e < vr * K) ? X[n0 * K + e] : 0.0;
-      ys[lane] = (lane < vr) ? y[n0 + lane] : 0.0;
-      ys[kTeRows + lane] = (lane < vr && w) ? w[n0 + lane] : 0.0;
-      reinterpret_cast<int32_t*>(ys + 2 * kTeRows)[lane] = (lane < vr) ? g[n0 + lane] : -1;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_u + 8 * slot);
-    }
-    mbar_wait(full_u + 8 * slot, phase);
-
-    // ---- Q: lane = observation ----
-    unsigned segmask;
-    {
-      const int64_t n = n0 + lane;
-      const bool valid = lane < rows;
-      const int gi = valid ? gs[lane] : 0;
-      if (c_warp) {
-        const int gprev = __shfl_up_sync(0xffffffffu, gi, 1);
-        segmask = __ballot_sync(0xffffffffu, valid && (lane == 0 ? gi != cur_g : gi != gprev));
-      }
-      double zm = vec[um0 + gi];
-      double zv = 1.0 / vec[ui0 + gi];
-      const double* xr = xs + (size_t)lane * K;
-      for (int k = skew; k < K; ++k) {
-        const double x = xr[k];
-        zm = fma(x, bm[k], zm);
-        zv = fma(x * x, bv[k], zv);
-      }
-      for (int k = 0; k < skew; ++k) {
-        const double x = xr[k];
-        zm = fma(x, bm[k], zm);
-        zv = fma(x * x, bv[k], zv);
-      }
-      const double zs = sqrt(zv);
-      GHSumsF s = {0, 0, 0, 0, 0, 0};
-      GHSumsF s2 = {0, 0, 0, 0, 0, 0};
-      int q = R;
-      for (; q + (UNR - 1) * P < Q; q += UNR * P) {
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const double cq = ghc[q + u * P];
-          gh_node_f<2>(fma(zs, cq, zm), cq, ghw[q + u * P], (u & 1) ? s2 : s);
-        }
-      }
-      for (; q < Q; q += P) {
-        const double c0 = ghc[q];
-        gh_node_f<2>(fma(zs, c0, zm), c0, ghw[q], s);
-      }
-      s.A += s2.A; s.Am += s2.Am; s.As += s2.As; s.Amm += s2.Amm; s.Ams += s2.Ams; s.Ass += s2.Ass;
-      if (P > 1) {
-        // exchange the partial node sums: part[parity][warp of team][6][32], summed in warp order
-        double* mp = part + (size_t)(st & 1) * 6 * kTeRows;
-        mp[lane] = s.A; mp[32 + lane] = s.Am; mp[64 + lane] = s.As;
-        mp[96 + lane] = s.Amm; mp[128 + lane] = s.Ams; mp[160 + lane] = s.Ass;
-        team_bar(1 + team, 32 * P);
-        // every warp of the team is past stage st - 1: its slot is free for stage st + 1
-        if (R == 0 && st >= 1) issue(st + 1, slot ^ 1);
-        const double* tp = part - (size_t)R * 3 * 6 * kTeRows + (size_t)(st & 1) * 6 * kTeRows;   // warp 0's block
-        s.A = s.Am = s.As = s.Amm = s.Ams = s.Ass = 0.0;
-#pragma unroll
-        for (int r2 = 0; r2 < P; ++r2) {
-          const double* op = tp + (size_t)r2 * 3 * 6 * kTeRows;
-          s.A += op[lane]; s.Am += op[32 + lane]; s.As += op[64 + lane];
-          s.Amm += op[96 + lane]; s.Ams += op[128 + lane]; s.Ass += op[160 + lane];
-        }
-      }
-      const double wn = valid ? (w ? ys[kTeRows + lane] : 1.0) : 0.0;
-      const double yn = ys[lane];
-      const double h = 0.5 / zs;
-      const double lm = wn * (yn - s.Am);
-      const double lv = -wn * s.As * h;
-      const double wa = -wn * s.Amm;
-      const double wb = -wn * s.Ams * h;
-      const double wc = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
-      double2* wrow = reinterpret_cast<double2*>(wq + 6 * lane);
-      wrow[0] = make_double2(lm, lv);
-      wrow[1] = make_double2(wa, wb);
-      wrow[2] = make_double2(wc, 0.0);
-      if (R == 0) {
-        klacc += wn * (yn * zm - s.A);
-        if (valid && W) {
-          W[n] = lm;
-          W[ldw + n] = lv;
-          W[2 * ldw + n] = wa;
-          W[3 * ldw + n] = wb;
-          W[4 * ldw + n] = wc;
-        }
-      }
-    }
-    __syncwarp();
-
-    // ---- C: lane = column; per-group running sums of this warp's chunk(s) ----
-    if (c_warp) {
-      const double2* w2 = reinterpret_cast<const double2*>(wq);
-      int koff[NCHW];
-      bool isone[NCHW];
-#pragma unroll
-      for (int c = 0; c < NCHW; ++c) {
-        const int k = lane + 32 * (chunk0 + c);
-        koff[c] = (k < K) ? k : 0;
-        isone[c] = (k == K);
-      }
-      auto rows_acc = [&](int r, auto nrow) {
-        constexpr int NR = decltype(nrow)::value;
-        double2 wl[NR], wab[NR], wc2[NR];
-        double x[NR][NCHW];
-#pragma unroll
-        for (int u = 0; u < NR; ++u) {
-          wl[u] = w2[3 * (r + u)];
-          wab[u] = w2[3 * (r + u) + 1];
-          wc2[u] = w2[3 * (r + u) + 2];
-#pragma unroll
-          for (int c = 0; c < NCHW; ++c) {
-            const double v = xs[(size_t)(r + u) * K + koff[c]];
-            x[u][c] = isone[c] ? 1.0 : v;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < NCHW; ++c) {
-          double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
-#pragma unroll
-          for (int u = 0; u < NR; ++u) {
-            const double xv = x[u][c], xx = xv * xv;
-            t0 = fma(wl[u].x, xv, t0);
-            t1 = fma(wl[u].y, xx, t1);
-            t2 = fma(wab[u].x, xv, t2);
-            t3 = fma(wab[u].y, xv, t3);
-            t4 = fma(wab[u].y, xx, t4);
-            t5 = fma(wc2[u].x, xx, t5);
-          }
-          q0[c] += t0; q1[c] += t1; q2[c] += t2; q3[c] += t3; q4[c] += t4; q5[c] += t5;
-        }
-      };
-      int r = 0;
-      const unsigned m = segmask;
-      while (r < rows) {
-        if ((m >> r) & 1u) {
-          flush();
-          cur_g = gs[r];
-        }
-        const unsigned rest = (r + 1 < 32) ? (m >> (r + 1)) : 0u;
-        const int nxt = rest ? (r + 1 + __ffs((int)rest) - 1) : rows;
-        const int r1 = nxt < rows ? nxt : rows;
-        for (; r + 4 <= r1; r += 4) rows_acc(r, std::integral_constant<int, 4>());
-        for (; r < r1; ++r) rows_acc(r, std::integral_constant<int, 1>());
-      }
-    }
+    team_qc_stage<P, NCHW>(a, c, st, slot, phase);
 
     // ---- D: this warp's tiles of the packed triangle over the 8 k-steps of the stage ----
     {
@@ -416,27 +503,12 @@ __device__ __forceinline__ void team_run(const FusedArgs& a, double* ring, unsig
       }
     }
     __syncwarp();     // every lane is done with the slot and with wq
-    if (P == 1) issue(st + kTeSlots, slot);
+    if (P == 1) team_issue<P, NCHW>(a, c, st + kTeSlots, slot);
     slot ^= 1;
     if (slot == 0) phase ^= 1u;
   }
-  if (c_warp) flush();
+  team_qc_finish<NCHW>(a, c);
 
-  // ---- per-team partials: KL (warp 0), global gradient (the chunk warps) ----
-  if (R == 0) {
-    klacc = warp_sum(klacc);
-    if (lane == 0) *kred_slot = klacc;
-  }
-  if (c_warp) {
-#pragma unroll
-    for (int c = 0; c < NCHW; ++c) {
-      const int k = lane + 32 * (chunk0 + c);
-      if (k < K) {
-        gred_row[k] = gm[c];
-        gred_row[K + k] = gv[c];
-      }
-    }
-  }
   // ---- the rings become the (NT, 64) tile buffer; warps add their accumulators in warp order ----
   __syncthreads();
   for (int e = threadIdx.x; e < (T2 * (T2 + 1) / 2) * 64; e += blockDim.x) red[e] = 0.0;
@@ -475,7 +547,7 @@ __device__ __forceinline__ void team_dispatch(int role, const FusedArgs& a, doub
 
 // blockDim.x = 32 * warps, warps a multiple of P; warps [P t, P t + P) are team t
 template <int T2, int T0, bool HAS_M, int P, int NCHW>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(32 * kTeMaxWarps, 1)
 k_team_eval(const FusedArgs a) {
   pdl_sync();
   constexpr int NT = T2 * (T2 + 1) / 2;
