@@ -9,7 +9,7 @@
 #include "obs_fused.cuh"
 #include "gram_mid.cuh"
 #include "gram_big.cuh"
-#include "team.cuh"
+#include "fused.cuh"
 
 namespace lrvb {
 
@@ -177,35 +177,24 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     h->of_smem = obs_fused_smem(K, Q, h->of_warps);
     int64_t nrec = tw;
     {
-      // order 2 in one pass (team.cuh): homogeneous teams of P warps, one CTA per SM.  Warps per CTA: the
-      // count in [12, 16] (multiple of P, shared memory permitting) with the smallest makespan
-      // ceil(stages / (SMs * teams)) * warps -- at N = 1M, K = 20 that is 12 (18 stages per warp, 2 %
-      // quantisation loss) rather than 16 (14 stages, 6 %).  LRVB_TEAM_WARPS overrides.
+      // order 2 in one pass (fused.cuh): teams of NQ quadrature warps + P DMMA warps, one CTA per SM; every
+      // Q warp owns a contiguous multiple-of-32 range of rows
       const char* fe = getenv("LRVB_FUSED");
-      const int T2f = (2 * K + 7) / 8, Pf = team_P(T2f);
-      const int wmax = team_max_warps(K, Q, T2f);
-      int best = wmax;
-      int64_t best_cost = -1;
-      for (int wv = wmax; wv >= Pf && wv >= 10; wv -= Pf) {
-        const int64_t teams_sm = wv / Pf;
-        const int64_t per = (nst + kNumSMs * teams_sm - 1) / (kNumSMs * teams_sm);
-        const int64_t cost = per * wv;
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = wv; }
-      }
-      if (const char* we = getenv("LRVB_TEAM_WARPS")) {
-        const int wv = atoi(we);
-        if (wv >= Pf && wv <= wmax && wv % Pf == 0) best = wv;
-      }
-      const int teams_cta = best / Pf;
-      int64_t fgrid = (nst + teams_cta - 1) / teams_cta;
+      const FusedGeom fg = fused_geom((2 * K + 7) / 8);
+      const int nqw = fg.teams * fg.NQ;
+      int64_t fgrid = (nst + nqw - 1) / nqw;
       if (fgrid > kNumSMs) fgrid = kNumSMs;
       if (fgrid < 1) fgrid = 1;
-      const int64_t tt = fgrid * teams_cta;
-      h->fused2 = !(fe && fe[0] == '0');
+      const int64_t tt = fgrid * nqw;
+      // default: K <= 24, where quadrature and Gram need about the same pipe time and the one-pass kernel
+      // is ~10 % faster than the two kernels; for larger K the Gram dominates, the D warps of the one-pass
+      // kernel (128 registers, 4 warps per triangle) are slower than gram_mid's (255 registers, 2 warps) and
+      // the two-kernel path wins (profiles/r02_onepass_attempts.md).  LRVB_FUSED=1 / 0 forces / disables it.
+      h->fused2 = fe ? (fe[0] != '0') : ((2 * K + 7) / 8 <= 6);
       h->fu_grid = (int)fgrid;
-      h->fu_teams = teams_cta;
-      h->fu_warps = best;
-      h->fu_rows_per_team = ((nst + tt - 1) / tt) * kTeRows;
+      h->fu_teams = nqw;
+      h->fu_warps = fg.warps;
+      h->fu_rows_per_team = ((nst + tt - 1) / tt) * kFuRows;
       if (tt > nrec) nrec = tt;
     }
     CREATE_TRY(dev_alloc(&h->bval, (size_t)nrec * 2 * (5 + 4 * (size_t)K)));

@@ -1,21 +1,32 @@
 // Order-2 evaluation in ONE pass over X: the per-observation quadrature + per-group sums of obs_fused.cuh
 // and the packed weighted Gram of gram_mid.cuh as one persistent, warp-specialised kernel (K <= 62), sm_100a.
 //
-// Why: run back to back, the observation pass keeps the FP64 pipe ~50 % busy (latency-bound exp / log1p
-// chains, 12 warps per SM) and the Gram kernel ~80 % (DMMA), and each reads X from HBM.  Here a CTA is a
-// set of TEAMS; a team is one Q warp (quadrature, lane = observation; then the per-group sums, lane =
-// column -- the code of k_obs_fused) and P D warps (the packed [x|s] triangle on DMMA.8x8x4 -- the code of
-// k_gram_mid), and both work on the SAME 32-row stage of X in shared memory:
+// Why: run back to back, the observation pass keeps the FP64 pipe ~50 % busy and the Gram kernel ~80 %
+// (DMMA), and each reads X from HBM.  What limits the observation pass is the DEPENDENT-issue latency of
+// FP64 on this chip: the measurements of this round fit ~24 cycles per dependent DFMA (DMMA: 26), so a
+// sub-partition needs ~12 independent FP64 chains in flight to fill its pipe (one DFMA per 2 cycles), and
+// the 161-register observation kernel reaches 3 warps x ~2 chains.  A DMMA warp needs no such help (16+
+// independent accumulator tiles).  So: put quadrature warps and DMMA warps on the same sub-partition and let
+// the tensor instructions fill the cycles the quadrature chains leave empty.
+//
+// A CTA is a set of TEAMS; a team is NQ Q warps (quadrature, lane = observation, 4 nodes in flight; then the
+// per-group sums, lane = column -- the code of k_obs_fused) and P D warps (the packed [x|s] triangle on
+// DMMA.8x8x4 -- the code of k_gram_mid).  Every Q warp owns a contiguous multiple-of-32 range of rows and
+// its own ring of 32-row stages; the team's D warps consume the stages of its Q warps round-robin:
 //
 //   TMA (Q lane 0) --full--> Q warp: weights l_m,l_v,a,b,c of the 32 rows into the slot --ready--> D warps:
 //   8 k-steps of the packed Gram with those weights --empty (Q + P arrivals)--> refill of the slot
 //
-// so X is read from HBM once (8K + 12 B per observation + the 40 B W store), the weights a, b, c never
-// leave the SM on their way to the tensor pipe, and the scheduler of every SM sub-partition always has
-// independent DMMAs to issue while a quadrature chain waits on its latency.  A team owns a contiguous
-// multiple-of-32 range of rows (as a warp does in k_obs_fused): groups inside the range are written
-// directly, head / tail pieces of straddling groups go to bval and k_obs_fixup adds them in row order.
-// No atomics, fixed summation orders: results are bitwise reproducible for a given launch geometry.
+// X is read from HBM once (8K + 12 B per observation + the 40 B W store), the weights a, b, c never leave
+// the SM on their way to the tensor pipe.  Groups inside a Q warp's range are written directly, head / tail
+// pieces of straddling groups go to bval and k_obs_fixup adds them in row order.  No atomics, fixed
+// summation orders: results are bitwise reproducible for a given launch geometry.
+//
+// Two earlier versions are kept in the history with their measurements (profiles/r02_onepass_attempts.md):
+// one Q warp (2 nodes in flight) per D warp -- Q-bound, exactly as slow as the two kernels; and homogeneous
+// teams in which every warp did quadrature, group sums and its share of the Gram -- no faster either (the
+// accumulators leave too few registers for enough chains), and 2x slower when the Q/C code was a real call
+// (local-memory traffic with the L1 carved down to a few KB).
 //
 // Slot (doubles): X 32 x K | y 32 | w 32 | g (int32 x 32) | wq 32 x 6 = (l_m, l_v, a, b, c, -) per row.
 // Barriers per slot: full (1 arrival + tx bytes), ready (1: the Q warp), empty (1 + P).
@@ -28,44 +39,48 @@
 namespace lrvb {
 
 constexpr int kFuRows = 32;          // rows per stage (= lanes of the Q warp = 8 k-steps)
-constexpr int kFuStages = 3;         // slots per team
-constexpr int kFuUnroll = 2;         // quadrature nodes in flight per lane (the D warps cover the latency)
+#ifndef LRVB_FUSED_UNROLL
+#define LRVB_FUSED_UNROLL 4
+#endif
+constexpr int kFuUnroll = LRVB_FUSED_UNROLL;   // quadrature nodes in flight per lane
 
 struct FusedGeom {
-  int teams, P, warps;               // warps = CTA size / 32 (teams * (1 + P) rounded up to a multiple of 4)
+  int teams, NQ, P, warps, slots;    // warps = CTA size / 32; slots = ring depth per Q warp
 };
-// T2 <= 6 (K <= 24): 8 teams of (Q + 1 D) = 16 warps at <= 128 registers, two teams per SM sub-partition.
-// T2 7..8 (K 25..32; 28 - 36 accumulator tiles do not fit one 128-register warp, and 8 teams x 3 slots
-// would not fit the shared memory from K = 29): 4 teams of (Q + 2 D) = 12 warps, one team per sub-partition.
-// T2 9..13 (K <= 52): 3 teams of (Q + 4 D) = 15 (+1 idle) warps, three D warps per sub-partition.
-// T2 14..16 (K <= 62): 2 teams of (Q + 7 D) = 16 warps (17 - 20 tiles per D warp).
+// T2 <= 6 (K <= 24; quadrature and Gram need about the same pipe time): 4 teams -- one per SM
+//   sub-partition -- of 3 Q warps + 1 D warp (15 / 21 accumulator tiles), 2-slot rings.
+// T2 7..8 (K 25..32): 4 teams of 1 Q + 3 D warps (10 - 12 tiles each).
+// T2 9..13 (K <= 52): 3 teams of 1 Q + 4 D = 15 (+1 idle) warps, three D warps per sub-partition.
+// T2 14..16 (K <= 62): 2 teams of 1 Q + 7 D = 16 warps (17 - 20 tiles per D warp).
 __host__ __device__ constexpr FusedGeom fused_geom(int T2) {
-  return T2 <= 6 ? FusedGeom{8, 1, 16} : T2 <= 8 ? FusedGeom{4, 2, 12}
-       : T2 <= 13 ? FusedGeom{3, 4, 16} : FusedGeom{2, 7, 16};
+  return T2 <= 6 ? FusedGeom{4, 3, 1, 16, 2} : T2 <= 8 ? FusedGeom{4, 1, 3, 16, 3}
+       : T2 <= 13 ? FusedGeom{2, 3, 4, 16, 2} : FusedGeom{2, 1, 7, 16, 3};
 }
 __host__ __device__ inline int fused_slot_elems(int K) { return kFuRows * K + 2 * kFuRows + kFuRows / 2 + 6 * kFuRows; }
 inline size_t fused_smem(int K, int Q, int T2) {
   const FusedGeom g = fused_geom(T2);
-  const size_t ring = sizeof(double) * (size_t)g.teams * kFuStages * fused_slot_elems(K);
+  const int nq = g.teams * g.NQ;
+  const size_t ring = sizeof(double) * (size_t)nq * g.slots * fused_slot_elems(K);
   const size_t red = sizeof(double) * (size_t)(T2 * (T2 + 1) / 2) * 64;
   const size_t body = ring > red ? ring : red;
-  // + beta mean / var (2K), GH nodes (2Q), gradient partials (teams x 2K), KL partials (teams), barriers
-  return body + sizeof(double) * (2 * (size_t)K + 2 * Q + (size_t)g.teams * 2 * K + g.teams) +
-         sizeof(unsigned long long) * (size_t)g.teams * kFuStages * 3;
+  // + beta mean / var (2K), GH nodes (2Q), gradient partials (Q warps x 2K), KL partials (Q warps), barriers
+  return body + sizeof(double) * (2 * (size_t)K + 2 * Q + (size_t)nq * 2 * K + nq) +
+         sizeof(unsigned long long) * (size_t)nq * g.slots * 3;
 }
 
 struct FusedArgs {
   const double* X; const double* y; const int32_t* g; const double* w; const double* vec; const double* gh;
   const int32_t* gptr; double* W; int64_t ldw; double* klpart; double* gradpart; double* gsc; double* BR;
-  double* bval; double* grampart; int64_t N; int K, G, Q; int64_t rows_per_team;
+  double* bval; double* grampart; int64_t N; int K, G, Q; int64_t rows_per_q;   // rows per Q warp (multiple of 32)
 };
 
 // ---- the Q warp: k_obs_fused's stage loop on the team's ring ------------------------------------------
-template <int NCH>
+template <int NCH, int SLOTS>
 __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, unsigned ring_u, unsigned full_u,
                                             unsigned ready_u, unsigned empty_u, const double* bm, const double* bv,
                                             const double* ghc, const double* ghw, double* gred_row, double* kred_slot,
-                                            int64_t gw, int P) {
+                                            int64_t gw) {
+  constexpr int kFuStages = SLOTS;
   const int lane = threadIdx.x & 31;
   const int K = a.K, G = a.G, Q = a.Q;
   const int64_t N = a.N, ldw = a.ldw;
@@ -78,8 +93,8 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
   double* __restrict__ W = a.W;
   const int slot_elems = fused_slot_elems(K);
   const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
-  const int64_t rs = gw * a.rows_per_team;
-  const int64_t re = (rs + a.rows_per_team < N) ? rs + a.rows_per_team : N;
+  const int64_t rs = gw * a.rows_per_q;
+  const int64_t re = (rs + a.rows_per_q < N) ? rs + a.rows_per_q : N;
   const int nst = (rs < re) ? (int)((re - rs + kFuRows - 1) / kFuRows) : 0;
   const unsigned xbytes = (unsigned)(kFuRows * K * sizeof(double));
   const unsigned vbytes = (unsigned)(kFuRows * sizeof(double));
@@ -204,20 +219,7 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
       }
       const double zs = sqrt(zv);
       GHSumsF s = {0, 0, 0, 0, 0, 0};
-      GHSumsF s2 = {0, 0, 0, 0, 0, 0};
-      int q = 0;
-      for (; q + kFuUnroll <= Q; q += kFuUnroll) {
-#pragma unroll
-        for (int u = 0; u < kFuUnroll; ++u) {
-          const double cq = ghc[q + u];
-          gh_node_f<2>(fma(zs, cq, zm), cq, ghw[q + u], (u & 1) ? s2 : s);
-        }
-      }
-      for (; q < Q; ++q) {
-        const double c0 = ghc[q];
-        gh_node_f<2>(fma(zs, c0, zm), c0, ghw[q], s);
-      }
-      s.A += s2.A; s.Am += s2.Am; s.As += s2.As; s.Amm += s2.Amm; s.Ams += s2.Ams; s.Ass += s2.Ass;
+      gh_all_nodes_f<2, kFuUnroll>(zm, zs, ghc, ghw, Q, s);
       const double wn = valid ? (w ? ys[kFuRows + lane] : 1.0) : 0.0;
       const double yn = ys[lane];
       klacc += wn * (yn * zm - s.A);
@@ -241,6 +243,13 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(ready_u + 8 * slot);     // release: the D warps may consume the stage
+    // the slot of the previous stage: refill it as soon as the D warps have released it (polled here,
+    // waited for at the end of the stage) so that the copy overlaps the group sums
+    bool refill = (st > 0) && (st - 1 + kFuStages < nst);
+    if (refill && mbar_test(empty_u + 8 * pslot, pphase)) {
+      issue(st - 1 + kFuStages, pslot);
+      refill = false;
+    }
 
     // ---- phase C: lane = column; per-group running sums ----
     {
@@ -302,11 +311,9 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
     if (lane == 0) mbar_arrive(empty_u + 8 * slot);     // the Q warp's share of the slot's release
     // refill the slot of the PREVIOUS stage once the D warps have released it too: the Q warp may run
     // a stage ahead of its D warps instead of meeting them at every stage
-    if (st > 0) {
-      if (st - 1 + kFuStages < nst) {
-        mbar_wait(empty_u + 8 * pslot, pphase);
-        issue(st - 1 + kFuStages, pslot);
-      }
+    if (refill) {
+      mbar_wait(empty_u + 8 * pslot, pphase);
+      issue(st - 1 + kFuStages, pslot);
     }
     pslot = slot;
     pphase = phase;
@@ -326,10 +333,10 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
   }
 }
 
-// ---- a D warp: k_gram_mid's k-step on the team's 32-row stages -----------------------------------------
-template <int T2, int T0, bool HAS_M, int P, int TLO, int THI>
-__device__ __forceinline__ void fused_d_run(const FusedArgs& a, unsigned ring_u, unsigned full_u, unsigned ready_u,
-                                            unsigned empty_u, int64_t gw, double (&acc)[THI - TLO][2]) {
+// ---- a D warp: k_gram_mid's k-step on the 32-row stages of the team's NQ rings, round-robin ----------------
+template <int T2, int T0, bool HAS_M, int P, int TLO, int THI, int NQ, int SLOTS, int TEAMS>
+__device__ __forceinline__ void fused_d_run(const FusedArgs& a, unsigned sm_u, unsigned bars_u, int team,
+                                            double (&acc)[THI - TLO][2]) {
   constexpr int TS = HAS_M ? T0 : -1;
   constexpr int TB = HAS_M ? T0 + 1 : T0;
   constexpr int JLO = gram_mid_col(TLO), JHI = gram_mid_col(THI - 1) + 1;
@@ -356,90 +363,104 @@ __device__ __forceinline__ void fused_d_run(const FusedArgs& a, unsigned ring_u,
     off_last = lr * K + (valid_last ? col - K : 0);
   }
 
-  const int64_t rs = gw * a.rows_per_team;
-  const int64_t re = (rs + a.rows_per_team < a.N) ? rs + a.rows_per_team : a.N;
-  const int nst = (rs < re) ? (int)((re - rs + kFuRows - 1) / kFuRows) : 0;
+  // Q warp qi of this team is CTA-local Q warp qi * TEAMS + team; its rows: [gq * rows_per_q, ...)
+  int nst_q[NQ];
+  int max_nst = 0;
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    const int64_t gq = (int64_t)blockIdx.x * (TEAMS * NQ) + qi * TEAMS + team;
+    const int64_t rs = gq * a.rows_per_q;
+    const int64_t re = (rs + a.rows_per_q < a.N) ? rs + a.rows_per_q : a.N;
+    nst_q[qi] = (rs < re) ? (int)((re - rs + kFuRows - 1) / kFuRows) : 0;
+    max_nst = nst_q[qi] > max_nst ? nst_q[qi] : max_nst;
+  }
 
   int slot = 0;
   unsigned phase = 0;
-  for (int st = 0; st < nst; ++st) {
-    mbar_wait(ready_u + 8 * slot, phase);      // weights written (the Q warp saw the TMA data first)
-    mbar_wait(full_u + 8 * slot, phase);       // and this warp observes the bulk copies itself
-    const unsigned xs_u = ring_u + (unsigned)(slot * slot_elems * sizeof(double));
-    const unsigned wq_u = xs_u + 8u * (unsigned)(kFuRows * K + 2 * kFuRows + kFuRows / 2 + 6 * lr);
+  for (int st = 0; st < max_nst; ++st) {
 #pragma unroll 1
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      const unsigned row_u = xs_u + 8u * (unsigned)(4 * ks * K);
-      double z[JHI];
+    for (int qi = 0; qi < NQ; ++qi) {
+      if (st >= nst_q[qi]) continue;
+      const int ql = qi * TEAMS + team;
+      const unsigned full_u = bars_u + 8u * (unsigned)(ql * SLOTS * 3);
+      const unsigned ready_u = full_u + 8 * SLOTS, empty_u = full_u + 16 * SLOTS;
+      mbar_wait(ready_u + 8 * slot, phase);      // weights written (the Q warp saw the TMA data first)
+      mbar_wait(full_u + 8 * slot, phase);       // and this warp observes the bulk copies itself
+      const unsigned xs_u = sm_u + 8u * (unsigned)((ql * SLOTS + slot) * slot_elems);
+      const unsigned wq_u = xs_u + 8u * (unsigned)(kFuRows * K + 2 * kFuRows + kFuRows / 2 + 6 * lr);
+#pragma unroll 1
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const unsigned row_u = xs_u + 8u * (unsigned)(4 * ks * K);
+        double z[JHI];
 #pragma unroll
-      for (int t = 0; t < JHI; ++t) {
-        int o;
-        if (t == TS) o = off_m;
-        else if (t == T2 - 1 && t >= TB) o = off_last;
-        else o = base + ((t < T0) ? 8 * t : 8 * t - K);
-        z[t] = lds_f64(row_u + 8u * (unsigned)o);
-      }
-      const unsigned wrow_u = wq_u + 8u * (unsigned)(24 * ks);     // row 4 ks + lr, 6 doubles per row
-      const double wa = lds_f64(wrow_u + 16u);
-      const double wb = lds_f64(wrow_u + 24u);
-      const double wc = lds_f64(wrow_u + 32u);
+        for (int t = 0; t < JHI; ++t) {
+          int o;
+          if (t == TS) o = off_m;
+          else if (t == T2 - 1 && t >= TB) o = off_last;
+          else o = base + ((t < T0) ? 8 * t : 8 * t - K);
+          z[t] = lds_f64(row_u + 8u * (unsigned)o);
+        }
+        const unsigned wrow_u = wq_u + 8u * (unsigned)(24 * ks);     // row 4 ks + lr, 6 doubles per row
+        const double wa = lds_f64(wrow_u + 16u);
+        const double wb = lds_f64(wrow_u + 24u);
+        const double wc = lds_f64(wrow_u + 32u);
 #pragma unroll
-      for (int t = 0; t < JHI; ++t) {
-        if (t == TS) {
-          const double xx = vmul(z[t], z[t]);
-          z[t] = cls1 ? xx : z[t];
-          if (!valid_m) z[t] = 0.0;
-        } else if (t >= TB) {
-          z[t] = vmul(z[t], z[t]);
-          if (t == T2 - 1 && !valid_last) z[t] = 0.0;
+        for (int t = 0; t < JHI; ++t) {
+          if (t == TS) {
+            const double xx = vmul(z[t], z[t]);
+            z[t] = cls1 ? xx : z[t];
+            if (!valid_m) z[t] = 0.0;
+          } else if (t >= TB) {
+            z[t] = vmul(z[t], z[t]);
+            if (t == T2 - 1 && !valid_last) z[t] = 0.0;
+          }
+        }
+        double aw2 = 0.0;
+        if (HAS_M && JHI > TS) aw2 = vmul(z[(HAS_M && JHI > TS) ? TS : 0], cls1 ? wc : wb);
+#pragma unroll
+        for (int j = JLO; j < JHI; ++j) {
+          const int cb = j * (j + 1) / 2 - T_LO;
+          bool need0 = (HAS_M && j == TS && mine(j, j)), needc = false;
+#pragma unroll
+          for (int i = 0; i < T0; ++i)
+            if (i <= j && mine(i, j)) need0 = true;
+#pragma unroll
+          for (int i = TB; i < T2; ++i)
+            if (i <= j && mine(i, j)) needc = true;
+          double bw0 = 0.0, bc = 0.0;
+          if (need0) bw0 = vmul(z[j], (j < T0) ? wa : ((j == TS) ? (cls1 ? wb : wa) : wb));
+          if (needc) bc = vmul(z[j], wc);
+#pragma unroll
+          for (int i = 0; i < T0; ++i)
+            if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bw0);
+          if (HAS_M && j == TS && mine(j, j)) {
+            dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? 0.0 : z[j], bw0);
+            dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? z[j] : 0.0, aw2);
+          }
+          if (HAS_M && j > TS && mine(HAS_M ? TS : 0, j))
+            dmma884(acc[cb + (HAS_M ? TS : 0)][0], acc[cb + (HAS_M ? TS : 0)][1], aw2, z[j]);
+#pragma unroll
+          for (int i = TB; i < T2; ++i)
+            if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bc);
         }
       }
-      double aw2 = 0.0;
-      if (HAS_M && JHI > TS) aw2 = vmul(z[(HAS_M && JHI > TS) ? TS : 0], cls1 ? wc : wb);
-#pragma unroll
-      for (int j = JLO; j < JHI; ++j) {
-        const int cb = j * (j + 1) / 2 - T_LO;
-        bool need0 = (HAS_M && j == TS && mine(j, j)), needc = false;
-#pragma unroll
-        for (int i = 0; i < T0; ++i)
-          if (i <= j && mine(i, j)) need0 = true;
-#pragma unroll
-        for (int i = TB; i < T2; ++i)
-          if (i <= j && mine(i, j)) needc = true;
-        double bw0 = 0.0, bc = 0.0;
-        if (need0) bw0 = vmul(z[j], (j < T0) ? wa : ((j == TS) ? (cls1 ? wb : wa) : wb));
-        if (needc) bc = vmul(z[j], wc);
-#pragma unroll
-        for (int i = 0; i < T0; ++i)
-          if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bw0);
-        if (HAS_M && j == TS && mine(j, j)) {
-          dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? 0.0 : z[j], bw0);
-          dmma884(acc[cb + j][0], acc[cb + j][1], cls1 ? z[j] : 0.0, aw2);
-        }
-        if (HAS_M && j > TS && mine(HAS_M ? TS : 0, j))
-          dmma884(acc[cb + (HAS_M ? TS : 0)][0], acc[cb + (HAS_M ? TS : 0)][1], aw2, z[j]);
-#pragma unroll
-        for (int i = TB; i < T2; ++i)
-          if (i <= j && mine(i, j)) dmma884(acc[cb + i][0], acc[cb + i][1], z[i], bc);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_u + 8 * slot);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_u + 8 * slot);
-    if (++slot == kFuStages) { slot = 0; phase ^= 1u; }
+    if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
   }
 }
 
-template <int T2, int T0, bool HAS_M, int P, int R>
-__device__ __forceinline__ void fused_d_dispatch(int role, const FusedArgs& a, unsigned ring_u, unsigned full_u,
-                                                 unsigned ready_u, unsigned empty_u, int64_t gw, double* red,
-                                                 int warp, int nwarps) {
+template <int T2, int T0, bool HAS_M, int P, int R, int NQ, int SLOTS, int TEAMS>
+__device__ __forceinline__ void fused_d_dispatch(int role, const FusedArgs& a, unsigned sm_u, unsigned bars_u, int team,
+                                                 double* red, int warp, int nwarps) {
   if constexpr (R < P) {
     if (role == R) {
       constexpr int LO = gram_mid_bound(T2, T0, HAS_M, P, R), HI = gram_mid_bound(T2, T0, HAS_M, P, R + 1);
       double acc[HI - LO][2];
 #pragma unroll
       for (int t = 0; t < HI - LO; ++t) acc[t][0] = acc[t][1] = 0.0;
-      fused_d_run<T2, T0, HAS_M, P, LO, HI>(a, ring_u, full_u, ready_u, empty_u, gw, acc);
+      fused_d_run<T2, T0, HAS_M, P, LO, HI, NQ, SLOTS, TEAMS>(a, sm_u, bars_u, team, acc);
       // every warp of the CTA is done with the rings: they become the (NT, 64) tile buffer; the D warps
       // add their accumulators one after the other (fixed order)
       __syncthreads();
@@ -460,41 +481,40 @@ __device__ __forceinline__ void fused_d_dispatch(int role, const FusedArgs& a, u
         __syncthreads();
       }
     } else {
-      fused_d_dispatch<T2, T0, HAS_M, P, R + 1>(role, a, ring_u, full_u, ready_u, empty_u, gw, red, warp, nwarps);
+      fused_d_dispatch<T2, T0, HAS_M, P, R + 1, NQ, SLOTS, TEAMS>(role, a, sm_u, bars_u, team, red, warp, nwarps);
     }
   }
 }
 
-template <int T2, int T0, bool HAS_M, int NCH, int TEAMS, int P, int WARPS>
+// warps [0, TEAMS * NQ): Q warp ql = qi * TEAMS + team;  then D warp dw = warp - TEAMS * NQ: team dw % TEAMS,
+// role dw / TEAMS (with TEAMS = 4 a team's warps share one SM sub-partition)
+template <int T2, int T0, bool HAS_M, int NCH, int TEAMS, int NQ, int P, int WARPS, int SLOTS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_fused_eval(const FusedArgs a) {
   pdl_sync();
   constexpr int NT = T2 * (T2 + 1) / 2;
+  constexpr int NQW = TEAMS * NQ;
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = a.K, Q = a.Q;
   const int slot_elems = fused_slot_elems(K);
-  const size_t ring_elems = (size_t)TEAMS * kFuStages * slot_elems;
+  const size_t ring_elems = (size_t)NQW * SLOTS * slot_elems;
   const size_t red_elems = (size_t)NT * 64;
   double* tail = sm + (ring_elems > red_elems ? ring_elems : red_elems);
   double* bm = tail;                              // K   E[beta]
   double* bv = bm + K;                            // K   Var[beta]
   double* ghc = bv + K;                           // Q
   double* ghw = ghc + Q;                          // Q
-  double* gred = ghw + Q;                         // TEAMS x 2K
-  double* kred = gred + (size_t)TEAMS * 2 * K;    // TEAMS
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(kred + TEAMS);
+  double* gred = ghw + Q;                         // NQW x 2K
+  double* kred = gred + (size_t)NQW * 2 * K;      // NQW
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(kred + NQW);
+  const unsigned sm_u = smem_u32(sm), bars_u = smem_u32(bars);
 
-  // roles: warps [0, TEAMS) are the Q warps; D warp w' = warp - TEAMS serves team w' % TEAMS as role w' / TEAMS
-  const bool is_q = warp < TEAMS;
-  const int dw = warp - TEAMS;
-  const int team = is_q ? warp : dw % TEAMS;
+  const bool is_q = warp < NQW;
+  const int dw = warp - NQW;
+  const int team = is_q ? warp % TEAMS : dw % TEAMS;
   const int role = is_q ? -1 : dw / TEAMS;
   const bool active = is_q || role < P;
-  double* ring = sm + (size_t)team * kFuStages * slot_elems;
-  const unsigned ring_u = smem_u32(ring);
-  const unsigned full_u = smem_u32(bars + (size_t)team * kFuStages * 3);
-  const unsigned ready_u = full_u + 8 * kFuStages, empty_u = full_u + 16 * kFuStages;
 
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     bm[k] = a.vec[4 + k];
@@ -505,21 +525,24 @@ k_fused_eval(const FusedArgs a) {
     ghw[q] = a.gh[Q + q];
   }
   if (is_q && lane == 0) {
+    const unsigned full_u = bars_u + 8u * (unsigned)(warp * SLOTS * 3);
 #pragma unroll
-    for (int p = 0; p < kFuStages; ++p) {
+    for (int p = 0; p < SLOTS; ++p) {
       mbar_init(full_u + 8 * p, 1);
-      mbar_init(ready_u + 8 * p, 1);
-      mbar_init(empty_u + 8 * p, 1 + P);
+      mbar_init(full_u + 8 * SLOTS + 8 * p, 1);
+      mbar_init(full_u + 16 * SLOTS + 8 * p, 1 + P);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
-  const int64_t gw = (int64_t)blockIdx.x * TEAMS + team;
   double* red = sm;
   if (is_q) {
-    fused_q_run<NCH>(a, ring, ring_u, full_u, ready_u, empty_u, bm, bv, ghc, ghw, gred + (size_t)team * 2 * K,
-                     kred + team, gw, P);
+    double* ring = sm + (size_t)warp * SLOTS * slot_elems;
+    const unsigned full_u = bars_u + 8u * (unsigned)(warp * SLOTS * 3);
+    const int64_t gq = (int64_t)blockIdx.x * NQW + warp;
+    fused_q_run<NCH, SLOTS>(a, ring, smem_u32(ring), full_u, full_u + 8 * SLOTS, full_u + 16 * SLOTS, bm, bv, ghc, ghw,
+                            gred + (size_t)warp * 2 * K, kred + warp, gq);
     // meet the D warps at the barriers of their reduction (the same number on every path)
     __syncthreads();
     for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) red[e] = 0.0;
@@ -527,7 +550,7 @@ k_fused_eval(const FusedArgs a) {
 #pragma unroll 1
     for (int w = 0; w < WARPS; ++w) __syncthreads();
   } else if (active) {
-    fused_d_dispatch<T2, T0, HAS_M, P, 0>(role, a, ring_u, full_u, ready_u, empty_u, gw, red, warp, WARPS);
+    fused_d_dispatch<T2, T0, HAS_M, P, 0, NQ, SLOTS, TEAMS>(role, a, sm_u, bars_u, team, red, warp, WARPS);
   } else {
     __syncthreads();
     for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) red[e] = 0.0;
@@ -540,12 +563,12 @@ k_fused_eval(const FusedArgs a) {
   for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) out[e] = red[e];
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < TEAMS; ++i) s += kred[i];
+    for (int i = 0; i < NQW; ++i) s += kred[i];
     a.klpart[blockIdx.x] = s;
   }
   for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) {
     double s = 0.0;
-    for (int i = 0; i < TEAMS; ++i) s += gred[(size_t)i * 2 * K + k];
+    for (int i = 0; i < NQW; ++i) s += gred[(size_t)i * 2 * K + k];
     a.gradpart[(size_t)k * gridDim.x + blockIdx.x] = s;
   }
 }
@@ -563,11 +586,11 @@ inline bool launch_fused_eval(const FusedArgs& a, int grid, int Q, cudaStream_t 
     constexpr FusedGeom g = fused_geom(T2_);                                                         \
     static size_t configured = 48 * 1024;                                                            \
     if (smem > configured) {                                                                         \
-      cudaFuncSetAttribute(k_fused_eval<T2_, T0_, M_, NCH_, g.teams, g.P, g.warps>,                  \
+      cudaFuncSetAttribute(k_fused_eval<T2_, T0_, M_, NCH_, g.teams, g.NQ, g.P, g.warps, g.slots>,   \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
       configured = smem;                                                                             \
     }                                                                                                \
-    return launch_pdl(k_fused_eval<T2_, T0_, M_, NCH_, g.teams, g.P, g.warps>, dim3(grid),           \
+    return launch_pdl(k_fused_eval<T2_, T0_, M_, NCH_, g.teams, g.NQ, g.P, g.warps, g.slots>, dim3(grid), \
                       dim3(32 * g.warps), smem, st, a) == cudaSuccess;                               \
   }
   LRVB_FU(1, 0, true, 1)

@@ -20,7 +20,7 @@
 #include "gram_mid.cuh"
 #define LRVB_GRAM_BIG_KERNELS
 #include "gram_big.cuh"
-#include "team.cuh"
+#include "fused.cuh"
 
 namespace lrvb {
 
@@ -627,14 +627,14 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   const bool one_pass = h->fused2 && order >= 2 && N > 0;
   h->ev_gram = 0;
   if (one_pass) {
-    // order 2, K <= 62: quadrature, per-group sums and the packed Gram in ONE pass over X (team.cuh)
+    // order 2, K <= 62: quadrature, per-group sums and the packed Gram in ONE pass over X (fused.cuh)
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
     FusedArgs fa;
     fa.X = h->X; fa.y = h->y; fa.g = h->g; fa.w = h->w; fa.vec = h->vec; fa.gh = h->gh; fa.gptr = h->gptr;
     fa.W = h->W; fa.ldw = h->ldw; fa.klpart = h->klpart; fa.gradpart = h->gradpart; fa.gsc = h->gsc; fa.BR = h->BR;
     fa.bval = h->bval; fa.grampart = h->grampart; fa.N = N; fa.K = K; fa.G = G; fa.Q = Q;
-    fa.rows_per_team = h->fu_rows_per_team;
-    if (!launch_team_eval(fa, h->fu_grid, h->fu_warps, Q, st)) {
+    fa.rows_per_q = h->fu_rows_per_team;
+    if (!launch_fused_eval(fa, h->fu_grid, Q, st)) {
       set_error("launch_eval: one-pass kernel rejected K = %d / alignment", K);
       return LRVB_ESTATE;
     }

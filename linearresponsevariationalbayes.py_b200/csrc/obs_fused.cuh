@@ -138,6 +138,118 @@ __device__ __forceinline__ void gh_node_f(double t, double c, double wq, GHSumsF
   }
 }
 
+// U Gauss-Hermite nodes at once, written step by step ACROSS the nodes: a dependent FP64 instruction
+// issues ~24 cycles after its producer on this chip, and with gh_node_f called U times the compiler
+// overlaps the chains only in pairs (SASS of round 1: the four reciprocal seeds of an "unroll 4" loop were
+// ~50, ~220 and ~80 instructions apart).  Here every step of the exp / reciprocal / atanh chains is a loop
+// over the U nodes, so U independent instructions sit next to each other in program order.
+// Adds the nodes ghc[0..U), ghw[0..U) to s in increasing node order.
+template <int ORDER, int U>
+__device__ __forceinline__ void gh_nodes_f(double zm, double zs, const double* __restrict__ ghc,
+                                           const double* __restrict__ ghw, GHSumsF& s) {
+  const double magic = 6755399441055744.0;
+  double t[U], c[U], x[U], nd[U], f[U], p[U], e[U];
+  int n[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    c[u] = ghc[u];
+    t[u] = fma(zs, c[u], zm);
+    x[u] = fmax(-fabs(t[u]), -708.0);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) nd[u] = fma(x[u], 1.4426950408889634, magic);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    n[u] = __double2loint(nd[u]);
+    nd[u] -= magic;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) f[u] = fma(nd[u], -6.93147180369123816490e-01, x[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) f[u] = fma(nd[u], -1.90821492927058770002e-10, f[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 10; ++i) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], f[u], kExpC[i]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], f[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], f[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) e[u] = p[u] * __hiloint2double((n[u] + 1023) << 20, 0);
+  // r = 1 / (1 + e), L = log1p(e) = 2 atanh(e / (2 + e)) from one reciprocal of (1 + e)(2 + e)
+  double a1[U], b2[U], ab[U], y[U], tt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    a1[u] = 1.0 + e[u];
+    b2[u] = 2.0 + e[u];
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) ab[u] = a1[u] * b2[u];
+#pragma unroll
+  for (int u = 0; u < U; ++u) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[u]) : "d"(ab[u]));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) tt[u] = fma(-ab[u], y[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) y[u] = fma(y[u], tt[u], y[u]);
+  }
+  double r[U], uu[U], v[U], pl[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    r[u] = y[u] * b2[u];
+    uu[u] = e[u] * (y[u] * a1[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    v[u] = uu[u] * uu[u];
+    pl[u] = kAtanhC[0];
+  }
+#pragma unroll
+  for (int i = 1; i < 10; ++i) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) pl[u] = fma(pl[u], v[u], kAtanhC[i]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) pl[u] = fma(pl[u], v[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double L = (uu[u] + uu[u]) * pl[u];
+    const double wq = ghw[u];
+    const double sp = fmax(t[u], 0.0) + L;
+    s.A = fma(wq, sp, s.A);
+    if (ORDER >= 1) {
+      const double er = e[u] * r[u];
+      const double sg = (t[u] >= 0.0) ? r[u] : er;
+      const double wsg = wq * sg;
+      s.Am += wsg;
+      s.As = fma(wsg, c[u], s.As);
+      if (ORDER >= 2) {
+        const double wd = wq * (er * r[u]);
+        const double wdc = wd * c[u];
+        s.Amm += wd;
+        s.Ams += wdc;
+        s.Ass = fma(wdc, c[u], s.Ass);
+      }
+    }
+  }
+}
+
+// All Q nodes of one observation, U at a time (then 2, then 1).
+template <int ORDER, int U>
+__device__ __forceinline__ void gh_all_nodes_f(double zm, double zs, const double* __restrict__ ghc,
+                                               const double* __restrict__ ghw, int Q, GHSumsF& s) {
+  int q = 0;
+  for (; q + U <= Q; q += U) gh_nodes_f<ORDER, U>(zm, zs, ghc + q, ghw + q, s);
+  if (U > 2)
+    for (; q + 2 <= Q; q += 2) gh_nodes_f<ORDER, 2>(zm, zs, ghc + q, ghw + q, s);
+  for (; q < Q; ++q) gh_nodes_f<ORDER, 1>(zm, zs, ghc + q, ghw + q, s);
+}
+
 // bval: (total_warps, 2, 5 + 4K) head / tail partials of groups that straddle a range boundary.
 template <int ORDER, int NCH>
 __global__ void __launch_bounds__(32 * kOfMaxWarps, 1)
@@ -310,22 +422,8 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
       }
       const double zs = sqrt(zv);
       GHSumsF s = {0, 0, 0, 0, 0, 0};
-      // kOfUnroll independent nodes per iteration: the exp / log1p chains of one node are serial,
-      // interleaving several hides the FP64 latency
-      GHSumsF s2 = {0, 0, 0, 0, 0, 0};
-      int q = 0;
-      for (; q + kOfUnroll <= Q; q += kOfUnroll) {
-#pragma unroll
-        for (int u = 0; u < kOfUnroll; ++u) {
-          const double cq = ghc[q + u];
-          gh_node_f<ORDER>(fma(zs, cq, zm), cq, ghw[q + u], (u & 1) ? s2 : s);
-        }
-      }
-      for (; q < Q; ++q) {
-        const double c0 = ghc[q];
-        gh_node_f<ORDER>(fma(zs, c0, zm), c0, ghw[q], s);
-      }
-      s.A += s2.A; s.Am += s2.Am; s.As += s2.As; s.Amm += s2.Amm; s.Ams += s2.Ams; s.Ass += s2.Ass;
+      // kOfUnroll independent nodes at a time, interleaved step by step (gh_nodes_f)
+      gh_all_nodes_f<ORDER, kOfUnroll>(zm, zs, ghc, ghw, Q, s);
       const double wn = valid ? (w ? ys[kOfRows + lane] : 1.0) : 0.0;
       const double yn = ys[lane];
       klacc += wn * (yn * zm - s.A);
