@@ -395,28 +395,44 @@ def rooflines(res, wl, peak_tf, traffic):
     step_flops = 4 * K * K + 18 * K + 12 * Q          # SURVEY.md 8(d) total per observation
     gms, oms = res["gram_ms"], res["obs_ms"]
     hbm = _hbm_peak()
-    fused = bool(res.get("fused_kernel"))
-    gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
-                   "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
-                   "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
-    roof_gram = {"bound": "tensor", "kernel": gram_kernel,
-                 "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12 if gms > 0 else None, "peak": peak_tf,
-                 "unit": "TFLOP/s", "traffic": traffic.get("k_gram_dram_bytes"),
-                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in "
-                                "MEASURED_PEAKS.json); DMMA.8x8x4 microbenchmark: 37.1 TF",
-                 "kernel_ms": gms, "flops_per_obs": flops_per_obs}
-    roof_gram["frac"] = roof_gram["achieved"] / peak_tf if gms > 0 else None
-    roof_obs = {"bound": "hbm",
-                "kernel": "lrvb::k_obs_fused<2> (quadrature + per-group sums, TMA ring per warp)"
-                if K <= 62 else "lrvb::k_obs<2>",
-                "achieved": N * bytes_per_obs / (oms * 1e-3) / 1e9 if oms > 0 else None, "peak": hbm,
-                "unit": "GB/s", "traffic": traffic.get("k_obs_dram_bytes"),
-                "peak_source": _hbm_peak_source(), "kernel_ms": oms, "bytes_per_obs": bytes_per_obs,
-                "note": "bound by fp64 instruction throughput (exp / log1p chains of the quadrature), not by "
-                        "HBM; see profiles/"}
-    roof_obs["frac"] = roof_obs["achieved"] / hbm if oms > 0 else None
-    roofline = dict(roof_obs if oms >= gms else roof_gram)
-    roofline["other_kernel"] = roof_gram if oms >= gms else roof_obs
+    if gms == 0.0 and oms > 0.0:
+        # one-pass kernel (csrc/fused.cuh): quadrature, group sums and the packed Gram in one launch; it is
+        # bound by the FP64 pipe (DFMA + DMMA share it), so its roofline is the FP64 tensor peak against ALL
+        # algorithmic flops of an observation (4K^2 + 18K + 12Q)
+        roofline = {"bound": "tensor",
+                    "kernel": "lrvb::k_fused_eval (one pass over X: quadrature warps + DMMA.8x8x4 warps per SM "
+                              "sub-partition, TMA rings)",
+                    "achieved": N * step_flops / (oms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                    "traffic": traffic.get("k_fused_dram_bytes"),
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in MEASURED_PEAKS.json); "
+                                   "DMMA.8x8x4 microbenchmark: 37.1 TF",
+                    "kernel_ms": oms, "flops_per_obs": step_flops,
+                    "hbm": {"achieved": N * bytes_per_obs / (oms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                            "bytes_per_obs": bytes_per_obs, "peak_source": _hbm_peak_source(),
+                            "frac": N * bytes_per_obs / (oms * 1e-3) / 1e9 / hbm}}
+        roofline["frac"] = roofline["achieved"] / peak_tf
+    else:
+        gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
+                       "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
+                       "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
+        roof_gram = {"bound": "tensor", "kernel": gram_kernel,
+                     "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12 if gms > 0 else None, "peak": peak_tf,
+                     "unit": "TFLOP/s", "traffic": traffic.get("k_gram_dram_bytes"),
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in "
+                                    "MEASURED_PEAKS.json); DMMA.8x8x4 microbenchmark: 37.1 TF",
+                     "kernel_ms": gms, "flops_per_obs": flops_per_obs}
+        roof_gram["frac"] = roof_gram["achieved"] / peak_tf if gms > 0 else None
+        roof_obs = {"bound": "hbm",
+                    "kernel": "lrvb::k_obs_fused<2> (quadrature + per-group sums, TMA ring per warp)"
+                    if K <= 62 else "lrvb::k_obs<2>",
+                    "achieved": N * bytes_per_obs / (oms * 1e-3) / 1e9 if oms > 0 else None, "peak": hbm,
+                    "unit": "GB/s", "traffic": traffic.get("k_obs_dram_bytes"),
+                    "peak_source": _hbm_peak_source(), "kernel_ms": oms, "bytes_per_obs": bytes_per_obs,
+                    "note": "bound by fp64 instruction throughput (exp / log1p chains of the quadrature), not by "
+                            "HBM; see profiles/"}
+        roof_obs["frac"] = roof_obs["achieved"] / hbm if oms > 0 else None
+        roofline = dict(roof_obs if oms >= gms else roof_gram)
+        roofline["other_kernel"] = roof_gram if oms >= gms else roof_obs
     roofline["eval_ms"] = res["eval_ms"]
     t = res["ms_per_step"] * 1e-3
     hbm_s = N * bytes_per_obs / (hbm * 1e9)

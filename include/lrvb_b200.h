@@ -146,6 +146,20 @@ int lrvb_glmm_hessian_csr_capacity(const lrvb_glmm* h, int64_t* capacity);
 int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
                           double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream);
 
+/* The pattern of an arrowhead Hessian is static between evaluations unless an entry becomes (or stops
+ * being) exactly zero.  After one full export on this handle, lrvb_glmm_hessian_csr_refill rewrites `data`
+ * ALONE (one pass, offsets cached in the handle) for the pattern `indptr_dev` of that export and compares the
+ * zero mask of the new values with the recorded one: *mismatch_dev (int32, caller zeroes it) becomes 1 when
+ * the pattern changed, in which case `data` is unusable and a full export is needed.  mismatch_host_mapped
+ * (nullable) is a device-accessible pointer to pinned HOST memory that receives the same flag, so the host
+ * can read it once the kernel has completed without queueing a copy on the stream.
+ * lrvb_glmm_hessian_csr_if is that full export made conditional ON THE DEVICE: every kernel is a no-op unless
+ * *run_if_dev != 0, so "refill, then csr_if(mismatch)" never synchronises with the host and is always right. */
+int lrvb_glmm_hessian_csr_refill(lrvb_glmm* h, const int32_t* indptr_dev, double* data_dev,
+                                 int32_t* mismatch_dev, int32_t* mismatch_host_mapped, void* stream);
+int lrvb_glmm_hessian_csr_if(lrvb_glmm* h, const int32_t* run_if_dev, int32_t* indptr_dev, int32_t* indices_dev,
+                             double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream);
+
 /* ---- Hessian-vector product -------------------------------------------------------------
  * Replaces Objective.fun_free_hvp (SparseObjectives.py:183-187) at the point of the last
  * order-2 eval.  v_dev, out_dev (D,).  include_A = 0 leaves the A v_g term out of out[0:Dg]

@@ -14,6 +14,7 @@ accepts it in place of ``fun``.
                   + entropies(mu, beta, u, tau) + priors(mu, beta, tau) )
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -56,73 +57,115 @@ def _view(ptr, shape, owner):
     return t
 
 
-class DeviceCSR(object):
-    """CSR Hessian resident on the device: ``crow_indices`` (D+1) int32, ``col_indices`` (nnz)
-    int32 sorted within each row, ``values`` (nnz) float64 -- the canonical form scipy produces
-    from get_sparse_sub_hessian triplets (SparseObjectives.py:591-619)."""
+class _Pattern(object):
+    """One exported sparsity pattern: device ``crow`` (D+1) / ``col`` (capacity) int32, the nnz (device
+    scalar, read once when first needed) and, once some caller has asked for a host matrix, the host
+    copies of the index arrays (read-only, shared by the scipy matrices handed out)."""
+    __slots__ = ("crow", "col", "nnz_dev", "_nnz", "shape", "host_template")
 
-    def __init__(self, crow, col, val, shape, nnz_dev=None):
-        # col / val may be over-allocated to the structural capacity; the actual nnz sits in a
-        # device scalar and is read (one sync) only when a size is needed
-        self.crow_indices, self.shape = crow, tuple(shape)
-        self._col, self._val, self._nnz_dev, self._nnz = col, val, nnz_dev, None
-        if nnz_dev is None:
-            self._nnz = int(val.numel())
+    def __init__(self, crow, col, nnz_dev, shape):
+        self.crow, self.col, self.nnz_dev, self._nnz, self.shape = crow, col, nnz_dev, None, tuple(shape)
+        self.host_template = None
 
     @property
     def nnz(self):
         if self._nnz is None:
-            self._nnz = int(self._nnz_dev.item())
+            self._nnz = int(self.nnz_dev.item())
         return self._nnz
+
+
+class _PendingRefill(object):
+    """A refill whose pattern check has not been read yet: the kernel's flag lands in mapped pinned
+    host memory, ``event`` marks the kernel's completion, ``fallback`` is the conditional full export
+    that ran on the device if (and only if) the flag was raised."""
+    __slots__ = ("event", "flag_pin", "slot", "fallback", "resolved", "mismatch")
+
+    def __init__(self, event, flag_pin, slot, fallback):
+        self.event, self.flag_pin, self.slot, self.fallback = event, flag_pin, slot, fallback
+        self.resolved, self.mismatch = False, False
+
+    def resolve(self):
+        if not self.resolved:
+            self.event.synchronize()
+            self.mismatch = bool(int(self.flag_pin[self.slot]) != 0)
+            self.resolved = True
+            if not self.mismatch:
+                self.fallback = None
+        return self.mismatch
+
+
+class DeviceCSR(object):
+    """CSR Hessian resident on the device: ``crow_indices`` (D+1) int32, ``col_indices`` (nnz)
+    int32 sorted within each row, ``values`` (nnz) float64 -- the canonical form scipy produces
+    from get_sparse_sub_hessian triplets (SparseObjectives.py:591-619).
+
+    The index arrays belong to a ``_Pattern`` that is shared between the matrices of successive
+    evaluations as long as the set of exact zeros does not change (csrc/csr.cu: refill + zero-mask
+    check); they must be treated as read-only.  Accessors resolve a pending pattern check first (one
+    event wait, no copy on the compute stream)."""
+
+    def __init__(self, pattern, val, pending=None):
+        self._pattern, self._val, self._pending = pattern, val, pending
+        self.shape = pattern.shape
+
+    def _resolve(self):
+        pend = self._pending
+        if pend is not None:
+            self._pending = None
+            if pend.resolve():
+                # the zero pattern changed at this evaluation: the conditional full export holds the result
+                self._pattern, self._val = pend.fallback
+        return self._pattern
+
+    @property
+    def nnz(self):
+        return self._resolve().nnz
+
+    @property
+    def crow_indices(self):
+        return self._resolve().crow
 
     @property
     def col_indices(self):
-        return self._col[:self.nnz]
+        pat = self._resolve()
+        return pat.col[:pat.nnz]
 
     @property
     def values(self):
-        return self._val[:self.nnz]
+        pat = self._resolve()
+        return self._val[:pat.nnz]
 
     def to_scipy(self, cache=None):
-        """Host copy as ``scipy.sparse.csr_matrix``.  The arrays land in pinned host blocks from
-        torch's caching host allocator by asynchronous copies on the current stream; the scipy
-        matrix keeps those blocks alive, no second host copy.
-
-        ``cache`` (a dict owned by the model): the sparsity pattern of an arrowhead Hessian is
-        static between evaluations unless an entry becomes exactly zero, so the host keeps the
-        last pattern (``indptr`` / ``indices``, read-only arrays shared by the matrices handed out)
-        next to its device copy; when the device comparison says the new pattern is identical only
-        ``data`` crosses PCIe (2/3 of the bytes) and the matrix is assembled without scipy's
-        O(nnz) validation pass."""
+        """Host copy as ``scipy.sparse.csr_matrix``.  ``data`` lands in a pinned host block from
+        torch's caching host allocator by an asynchronous copy on the current stream (the scipy matrix
+        keeps the block alive, no second host copy).  The index arrays are downloaded once per PATTERN:
+        later matrices of the same pattern share the host copies (made read-only) and are assembled
+        without scipy's O(nnz) validation pass, so only ``data`` -- 2/3 of the bytes -- crosses PCIe.
+        (``cache`` is accepted for compatibility; the cache lives in the pattern.)"""
         import scipy.sparse
         torch = nat.require_cuda()
-        if cache is not None and cache.get("crow") is not None and cache["shape"] == self.shape \
-                and torch.equal(self.crow_indices, cache["crow"]):          # sync 1: (D+1) int32 compare
-            nnz = cache["nnz"]
-            same = (self._col[:nnz] == cache["col"]).all()
-            hv = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
-            hv.copy_(self._val[:nnz], non_blocking=True)
-            if bool(same.item()):                                            # sync 2: data has landed too
-                self._nnz = nnz
-                m = scipy.sparse.csr_matrix.__new__(scipy.sparse.csr_matrix)
-                m.__dict__.update(cache["template"])
-                m.data = hv.numpy()
-                return m
-        host = []
-        for t in (self.values, self.col_indices, self.crow_indices):
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            host.append(h)
-        torch.cuda.current_stream().synchronize()
-        m = scipy.sparse.csr_matrix(tuple(h.numpy() for h in host), shape=self.shape, copy=False)
-        m.has_sorted_indices = True
-        if cache is not None:
+        pat = self._resolve()
+        nnz = pat.nnz
+        hv = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
+        hv.copy_(self._val[:nnz], non_blocking=True)
+        if pat.host_template is None:
+            hc = torch.empty(nnz, dtype=torch.int32, pin_memory=True)
+            hr = torch.empty(pat.crow.numel(), dtype=torch.int32, pin_memory=True)
+            hc.copy_(pat.col[:nnz], non_blocking=True)
+            hr.copy_(pat.crow, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            m = scipy.sparse.csr_matrix((hv.numpy(), hc.numpy(), hr.numpy()), shape=self.shape, copy=False)
+            m.has_sorted_indices = True
             m.indices.flags.writeable = False     # shared with later matrices of the same pattern
             m.indptr.flags.writeable = False
             tmpl = dict(m.__dict__)
             tmpl.pop("data", None)
-            cache.update(crow=self.crow_indices.clone(), col=self.col_indices.clone(), nnz=self.nnz,
-                         shape=self.shape, template=tmpl)
+            pat.host_template = tmpl
+            return m
+        torch.cuda.current_stream().synchronize()
+        m = scipy.sparse.csr_matrix.__new__(scipy.sparse.csr_matrix)
+        m.__dict__.update(pat.host_template)
+        m.data = hv.numpy()
         return m
 
     def toarray(self):
@@ -232,7 +275,9 @@ class LogisticGLMM(object):
         self._x_event = None
         self._g_pin = None
         self._cache = dict(x=None, order=-1, coords=None)
-        self._pattern_cache = {}          # host + device copy of the last exported CSR pattern
+        self._csr_pattern = None          # _Pattern of the last full export (shared by refilled matrices)
+        self._csr_pending = None          # refill whose pattern check has not been read yet
+        self._csr_flag_pin, self._csr_slot = None, 0
         self._D_in = self.D
         self._coords = "free"
         self.device = dev
@@ -380,8 +425,9 @@ class LogisticGLMM(object):
     def set_global_block(self, A):
         nat.check(self._lib.lrvb_glmm_set_global_block(self._h, nat.ptr(A), nat.stream_ptr()))
 
-    def hessian_csr(self):
-        """Device CSR of the cached Hessian."""
+    def _export_full(self, run_if=None):
+        """Full CSR export into fresh buffers -> (_Pattern, values); with ``run_if`` (device int32) the
+        export runs on the device only if the flag is set (lrvb_glmm_hessian_csr_if)."""
         torch = nat.require_cuda()
         cap = ctypes.c_int64()
         nat.check(self._lib.lrvb_glmm_hessian_csr_capacity(self._h, ctypes.byref(cap)))
@@ -389,14 +435,56 @@ class LogisticGLMM(object):
         col = torch.empty(cap.value, dtype=torch.int32, device=self.device)
         val = torch.empty(cap.value, dtype=torch.float64, device=self.device)
         nnz = torch.empty((), dtype=torch.int64, device=self.device)
-        nat.check(self._lib.lrvb_glmm_hessian_csr(self._h, nat.ptr(crow), nat.ptr(col), nat.ptr(val),
-                                                  cap.value, nat.ptr(nnz), nat.stream_ptr()))
-        return DeviceCSR(crow, col, val, (self.D, self.D), nnz_dev=nnz)
+        if run_if is None:
+            nat.check(self._lib.lrvb_glmm_hessian_csr(self._h, nat.ptr(crow), nat.ptr(col), nat.ptr(val),
+                                                      cap.value, nat.ptr(nnz), nat.stream_ptr()))
+        else:
+            nat.check(self._lib.lrvb_glmm_hessian_csr_if(self._h, nat.ptr(run_if), nat.ptr(crow), nat.ptr(col),
+                                                         nat.ptr(val), cap.value, nat.ptr(nnz), nat.stream_ptr()))
+        return _Pattern(crow, col, nnz, (self.D, self.D)), val
+
+    def hessian_csr(self):
+        """Device CSR of the cached Hessian.  The first call exports the pattern; later calls rewrite the
+        values alone for that pattern in one pass (csrc/csr.cu refill) while the device checks that the
+        set of exact zeros is unchanged -- if it is not, a conditional full export that was enqueued
+        behind the refill has produced the new pattern, which the returned object (and the next call)
+        adopt.  Nothing here synchronises the compute stream."""
+        torch = nat.require_cuda()
+        pend = self._csr_pending
+        if pend is not None:
+            # the previous refill's verdict (its kernel finished long ago: an event wait, no stream copy)
+            self._csr_pending = None
+            if pend.resolve():
+                self._csr_pattern = pend.fallback[0]
+        pat = self._csr_pattern
+        # small problems are launch-bound: the four launches of a full export are cheaper than the refill
+        # plus its conditional fallback (and the host-side bookkeeping of the pending check)
+        small = self.Dg * self.Dg + 4 * self.Dg * self.G < 400000
+        if pat is None or small or os.environ.get("LRVB_CSR_REFILL", "1") == "0":
+            pat, val = self._export_full()
+            self._csr_pattern = pat
+            return DeviceCSR(pat, val)
+        if self._csr_flag_pin is None:
+            self._csr_flag_pin = torch.zeros(8, dtype=torch.int32).pin_memory()
+            self._csr_slot = 0
+        slot = self._csr_slot = (self._csr_slot + 1) % 8
+        self._csr_flag_pin[slot] = 0
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        val = torch.empty(pat.nnz, dtype=torch.float64, device=self.device)
+        host_ptr = ctypes.c_void_p(self._csr_flag_pin.data_ptr() + 4 * slot)
+        nat.check(self._lib.lrvb_glmm_hessian_csr_refill(self._h, nat.ptr(pat.crow), nat.ptr(val), nat.ptr(flag),
+                                                         host_ptr, nat.stream_ptr()))
+        ev = torch.cuda.Event()
+        ev.record()
+        fallback = self._export_full(run_if=flag)
+        pend = _PendingRefill(ev, self._csr_flag_pin, slot, fallback)
+        self._csr_pending = pend
+        return DeviceCSR(pat, val, pend)
 
     def hessian_scipy(self):
         """Host ``scipy.sparse.csr_matrix`` of the cached Hessian (what ``Objective.fun_free_hessian``
         returns for numpy input, SparseObjectives.py:156-158); re-uses the cached pattern."""
-        return self.hessian_csr().to_scipy(cache=self._pattern_cache)
+        return self.hessian_csr().to_scipy()
 
     def hvp_cached(self, v_dev, out=None, include_A=True):
         """H v with the cached Hessian; v_dev a CUDA fp64 tensor (D,)."""

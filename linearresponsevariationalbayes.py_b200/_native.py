@@ -58,6 +58,8 @@ SIGNATURES = {
     "lrvb_glmm_weight_cross_rmatvec": (c_int32, [_P, _P, _P, _P]),
     "lrvb_glmm_hessian_csr_capacity": (c_int32, [_P, POINTER(c_int64)]),
     "lrvb_glmm_hessian_csr": (c_int32, [_P, _P, _P, _P, c_int64, _P, _P]),
+    "lrvb_glmm_hessian_csr_refill": (c_int32, [_P, _P, _P, _P, _P, _P]),
+    "lrvb_glmm_hessian_csr_if": (c_int32, [_P, _P, _P, _P, _P, c_int64, _P, _P]),
     "lrvb_glmm_hvp": (c_int32, [_P, _P, _P, c_int32, _P]),
     "lrvb_glmm_cg": (c_int32, [_P, _P, _P, c_int32, c_double, c_int32, _P, POINTER(c_int32),
                                POINTER(c_int32), _P]),

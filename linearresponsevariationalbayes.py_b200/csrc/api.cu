@@ -59,8 +59,8 @@ int lrvb_version(void) { return 100; }
 
 int lrvb_glmm_destroy(lrvb_glmm* h) {
   if (!h) return LRVB_OK;
-  void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart,
-                  h->jobs, h->gslots, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork,
+  void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart, h->fin_counter, h->fin_pre,
+                  h->jobs, h->gslots, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork, h->csrmask,
                   h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
                   h->schurpart};
   for (void* p : ptrs)
@@ -211,6 +211,9 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   if (h->loc_grid > 2 * kNumSMs) h->loc_grid = 2 * kNumSMs;
   if (h->loc_grid < 1) h->loc_grid = 1;
   CREATE_TRY(dev_alloc(&h->locpart, (size_t)h->loc_grid * 4));
+  CREATE_TRY(dev_alloc(&h->fin_counter, 1));
+  CREATE_TRY(dev_alloc(&h->fin_pre, 8 + 2 * (size_t)K));
+  CREATE_CUDA(cudaMemsetAsync(h->fin_counter, 0, sizeof(unsigned int), st));
 
   // Gram geometry
   {

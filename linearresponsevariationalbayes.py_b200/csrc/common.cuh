@@ -212,6 +212,8 @@ struct lrvb_glmm {
   double* BR = nullptr;       // (G, 4, K) raw borders: sum a x, sum b x, sum b s, sum c s
   int loc_grid = 0;
   double* locpart = nullptr;  // (loc_grid, 4) partials of sum dm, sum Sg, sum log u_info, -
+  double* fin_pre = nullptr;         // (8 + 2K) results of k_finish's block 0 for its last block
+  unsigned int* fin_counter = nullptr;   // finished work blocks of the running k_finish (reset by its global block)
   // Gram
   int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0;   // grid_y = job groups
   size_t gram_smem = 0;
@@ -238,6 +240,8 @@ struct lrvb_glmm {
   int32_t* scanblk = nullptr; // scan scratch
   int32_t* csrwork = nullptr; // cntA | coltot | chunkcnt | chunkoff
   int csr_cg = 0, csr_nchunk = 0;
+  uint32_t* csrmask = nullptr;   // zero mask of the last full export (refill compares against it)
+  int csr_pattern_valid = 0;     // csrwork / csrmask describe the pattern of the last full export
   int64_t csr_nnz = -1;
   // solver scratch
   double* cgbuf = nullptr;    // 6*D

@@ -15,6 +15,12 @@
 // contiguous, coalesced segment of that CSR row.  Per-(chunk, column) counts are scanned over
 // chunks to give each segment its offset.  Nothing synchronises with the host: nnz is left in a
 // device scalar.
+//
+// The sparsity pattern is static between evaluations unless an entry becomes (or stops being) exactly
+// zero, so the full export also records the ZERO MASK of every structural candidate (one bit each: A,
+// then B, then L) and keeps its scan results; lrvb_glmm_hessian_csr_refill then rewrites `data` alone in
+// ONE pass with the cached offsets and compares the mask of the new values with the recorded one -- any
+// difference raises a device flag, and the caller's conditional full export (run_if) takes over.
 #include "common.cuh"
 
 namespace lrvb {
@@ -22,10 +28,27 @@ namespace lrvb {
 constexpr int kScanChunk = 2048;  // per CTA (256 threads x 8)
 
 // ---- local rows: one warp per row ------------------------------------------------------------
-template <bool FILL>
+// mask words: [A: Dg rows x WA words | B: 2 G rows x WA words | L: G words (3 bits)], WA = ceil(Dg / 32)
+// mismatch: [0] the device flag the conditional export reads, [1] (nullable) its copy in mapped pinned
+// host memory, which the host reads after the kernel without a device-to-host copy on the stream
+struct MismatchFlag {
+  int* dev;
+  int* host;
+};
+template <int FILL>
+__device__ __forceinline__ void mask_word(uint32_t* __restrict__ mask, size_t w, unsigned m, const MismatchFlag& mm) {
+  if (FILL == 1) mask[w] = m;
+  else if (FILL == 2 && mask[w] != m) {
+    *mm.dev = 1;
+    if (mm.host) *(volatile int*)mm.host = 1;
+  }
+}
+
+template <int FILL>
 __device__ __forceinline__ void csr_local_rows_body(int bid, const double* __restrict__ B, const double* __restrict__ L, int Dg, int G,
                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ indptr,
-                 int32_t* __restrict__ indices, double* __restrict__ data) {
+                 int32_t* __restrict__ indices, double* __restrict__ data, uint32_t* __restrict__ mask,
+                 const MismatchFlag mismatch) {
   const int lane = threadIdx.x & 31;
   const int64_t wg = (int64_t)bid * 8 + (threadIdx.x >> 5);
   if (wg >= 2 * (int64_t)G) return;
@@ -35,6 +58,7 @@ __device__ __forceinline__ void csr_local_rows_body(int bid, const double* __res
   const double* b = B + (size_t)gi * 2 * Dg + (which ? Dg : 0);
   int64_t base = FILL ? indptr[row] : 0;
   int count = 0;
+  const int WA = (Dg + 31) >> 5;
   for (int c0 = 0; c0 < Dg; c0 += 32) {
     const int c = c0 + lane;
     const double v = (c < Dg) ? b[c] : 0.0;
@@ -42,9 +66,11 @@ __device__ __forceinline__ void csr_local_rows_body(int bid, const double* __res
     const unsigned m = __ballot_sync(0xffffffffu, nz);
     if (FILL && nz) {
       const int off = __popc(m & ((1u << lane) - 1));
-      indices[base + off] = c;
+      if (FILL == 1) indices[base + off] = c;
       data[base + off] = v;
     }
+    // the mask of B is recorded / compared by the local rows (every B entry belongs to exactly one)
+    if (FILL && lane == 0) mask_word<FILL>(mask, (size_t)(Dg + wg) * WA + (c0 >> 5), m, mismatch);
     base += __popc(m);
     count += __popc(m);
   }
@@ -53,22 +79,27 @@ __device__ __forceinline__ void csr_local_rows_body(int bid, const double* __res
     const double va = which ? l1 : l0;   // column u.mean_g
     const double vb = which ? l2 : l1;   // column u.info_g
     if (va != 0.0) {
-      if (FILL) { indices[base] = Dg + gi; data[base] = va; }
+      if (FILL == 1) indices[base] = Dg + gi;
+      if (FILL) data[base] = va;
       ++base; ++count;
     }
     if (vb != 0.0) {
-      if (FILL) { indices[base] = Dg + G + gi; data[base] = vb; }
+      if (FILL == 1) indices[base] = Dg + G + gi;
+      if (FILL) data[base] = vb;
       ++base; ++count;
     }
     if (!FILL) rowcnt[row] = count;
+    if (FILL && which == 0)
+      mask_word<FILL>(mask, (size_t)(Dg + 2 * (size_t)G) * WA + gi,
+                      (l0 != 0.0 ? 1u : 0u) | (l1 != 0.0 ? 2u : 0u) | (l2 != 0.0 ? 4u : 0u), mismatch);
   }
 }
 
 // ---- global rows, part 1: the dense block A (one warp per row) -----------------------------------
-template <bool FILL>
+template <int FILL>
 __device__ __forceinline__ void csr_A_rows_body(int bid, const double* __restrict__ A, int Dg, int32_t* __restrict__ cntA,
              const int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
-             double* __restrict__ data) {
+             double* __restrict__ data, uint32_t* __restrict__ mask, const MismatchFlag mismatch) {
   const int lane = threadIdx.x & 31;
   const int r = bid * 8 + (threadIdx.x >> 5);
   if (r >= Dg) return;
@@ -82,9 +113,10 @@ __device__ __forceinline__ void csr_A_rows_body(int bid, const double* __restric
     const unsigned m = __ballot_sync(0xffffffffu, nz);
     if (FILL && nz) {
       const int off = __popc(m & ((1u << lane) - 1));
-      indices[base + off] = c;
+      if (FILL == 1) indices[base + off] = c;
       data[base + off] = v;
     }
+    if (FILL && lane == 0) mask_word<FILL>(mask, (size_t)r * ((Dg + 31) >> 5) + (c0 >> 5), m, mismatch);
     base += __popc(m);
     count += __popc(m);
   }
@@ -93,7 +125,7 @@ __device__ __forceinline__ void csr_A_rows_body(int bid, const double* __restric
 
 // ---- global rows, part 2: columns of B, chunked over groups -----------------------------------
 // chunkcnt / chunkoff: (nchunk, 2*Dg) int32, column c = side*Dg + r.
-template <bool FILL>
+template <int FILL>
 __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restrict__ B, int Dg, int G, int CG, int32_t* __restrict__ chunkcnt,
              const int32_t* __restrict__ chunkoff, const int32_t* __restrict__ cntA,
              const int32_t* __restrict__ coltot, const int32_t* __restrict__ indptr,
@@ -123,7 +155,7 @@ __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restric
       const unsigned m = __ballot_sync(0xffffffffu, nz);
       if (FILL && nz) {
         const int off = __popc(m & ((1u << lane) - 1));
-        indices[base + off] = Dg + side * G + g0 + gl;
+        if (FILL == 1) indices[base + off] = Dg + side * G + g0 + gl;
         data[base + off] = v;
       }
       base += __popc(m);
@@ -135,44 +167,50 @@ __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restric
 
 // One launch per phase: blocks [0, nA) take the rows of A, the next nB blocks a chunk of B each,
 // the rest the local rows (block-uniform roles; only the B role uses the dynamic shared memory).
-template <bool FILL>
+// FILL = 0 count, 1 fill (and record the zero mask), 2 refill: data only with the cached offsets, the
+// zero mask compared with the recorded one.  run_if (nullable): the kernel is a no-op unless *run_if != 0
+// (the conditional full export behind a refill).
+template <int FILL>
 __global__ void __launch_bounds__(256)
 k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ L,
            int Dg, int G, int CG, int nA, int nB, int32_t* __restrict__ cntA,
            int32_t* __restrict__ chunkcnt, const int32_t* __restrict__ chunkoff,
            const int32_t* __restrict__ coltot, int32_t* __restrict__ rowcnt,
-           const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data) {
+           const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data,
+           uint32_t* __restrict__ mask, const MismatchFlag mismatch, const int* __restrict__ run_if) {
   const int bid = blockIdx.x;
-  if (!FILL && bid >= nA) {
-    // Counting the border columns and the local rows needs B and L only.  Those are written by
-    // k_finish, and every path to this kernel passes k_global, which signals its dependents after its
-    // own wait: B and L are complete when this CTA starts, so it counts ahead of the wait, behind
-    // k_global (one CTA) which is still finishing A.  The arrays written here (chunkcnt, rowcnt) are
-    // not read by a fill pass that might still be running in front of this kernel.
+  if (FILL == 2 && bid >= nA) {
+    // Refill: the border columns and the local rows need B and L only.  Those are written by k_finish, and
+    // every path to this kernel passes k_global_post (or a kernel launched even later), which signals its
+    // dependents after its own wait: B and L are complete when this CTA starts, so it runs ahead of the
+    // wait, behind k_global_post (one CTA), which is still finishing A.  Nothing written here is read by
+    // a kernel that might still be running in front of this one.
     pdl_launch_dependents();
     if (bid < nA + nB) {
       csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
     } else {
-      csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data);
+      csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
     }
     pdl_wait();        // completion of this kernel still implies completion of its prerequisite
     return;
   }
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   if (bid < nA) {
-    csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data);
+    csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data, mask, mismatch);
   } else if (bid < nA + nB) {
     csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
   } else {
-    csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data);
+    csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
   }
 }
 
 // exclusive scan of chunkcnt over chunks, one CTA per column; coltot[c] = column total
 __global__ void __launch_bounds__(256)
 k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunkoff,
-              int32_t* __restrict__ coltot, int nchunk, int ncol) {
+              int32_t* __restrict__ coltot, int nchunk, int ncol, const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   __shared__ int wsum[8];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -204,16 +242,18 @@ k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunko
 // rowcnt[r] for the global rows
 __global__ void k_csr_global_rowcnt(const int32_t* __restrict__ cntA,
                                     const int32_t* __restrict__ coltot, int Dg,
-                                    int32_t* __restrict__ rowcnt) {
+                                    int32_t* __restrict__ rowcnt, const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < Dg) rowcnt[r] = cntA[r] + coltot[r] + coltot[Dg + r];
 }
 
 // ---- exclusive scan of rowcnt (n entries) into indptr (n+1 entries), 3 phases --------------------
 __global__ void __launch_bounds__(256)
-k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk) {
+k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk, const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   __shared__ double red[32];
   const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
   long long s = 0;
@@ -225,8 +265,9 @@ k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk
 }
 
 __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restrict__ total,
-                           int64_t* __restrict__ nnz_out) {
+                           int64_t* __restrict__ nnz_out, const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int64_t run = 0;
   for (int i = 0; i < nblk; ++i) {
@@ -240,8 +281,10 @@ __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restr
 
 __global__ void __launch_bounds__(256)
 k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restrict__ blk,
-             const int64_t* __restrict__ total, int32_t* __restrict__ indptr) {
+             const int64_t* __restrict__ total, int32_t* __restrict__ indptr,
+             const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   __shared__ int wsum[8];
   const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -277,8 +320,9 @@ constexpr int64_t kIndptrOneCta = 262144;
 __global__ void __launch_bounds__(1024)
 k_csr_indptr_small(const int32_t* __restrict__ cntA, const int32_t* __restrict__ coltot, int Dg,
                    const int32_t* __restrict__ rowcnt, int64_t n, int32_t* __restrict__ indptr,
-                   int64_t* __restrict__ nnz_out) {
+                   int64_t* __restrict__ nnz_out, const int* __restrict__ run_if) {
   pdl_sync();
+  if (run_if && *run_if == 0) return;
   __shared__ int wsum[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   long long carry = 0;
@@ -345,9 +389,13 @@ static int ensure_csr_scratch(lrvb_glmm* h) {
   // cntA (Dg) | coltot (2Dg) | chunkcnt (nchunk*2Dg) | chunkoff (nchunk*2Dg)
   LRVB_CUDA(cudaMalloc((void**)&h->csrwork,
                        sizeof(int32_t) * ((size_t)3 * Dg + (size_t)4 * Dg * nchunk + 4)));
+  // zero mask of the last full export: A (Dg x WA) | B (2G x WA) | L (G) words
+  const size_t WA = ((size_t)Dg + 31) / 32;
+  LRVB_CUDA(cudaMalloc((void**)&h->csrmask, sizeof(uint32_t) * ((size_t)(Dg + 2 * (size_t)G) * WA + (size_t)G + 1)));
   const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
-  cudaFuncSetAttribute(k_csr_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_csr_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return LRVB_OK;
 }
 
@@ -363,18 +411,16 @@ int lrvb_glmm_hessian_csr_capacity(const lrvb_glmm* h, int64_t* capacity) {
   return LRVB_OK;
 }
 
-int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
-                          double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream) {
-  LRVB_REQUIRE(h != nullptr && indptr_dev && indices_dev && data_dev && nnz_dev,
-               "lrvb_glmm_hessian_csr: NULL argument");
+static int csr_full_export(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev,
+                           int64_t capacity, int64_t* nnz_dev, const int* run_if, const char* who, void* stream) {
+  LRVB_REQUIRE(h != nullptr && indptr_dev && indices_dev && data_dev && nnz_dev, "%s: NULL argument", who);
   if (!h->hess_valid) {
-    set_error("lrvb_glmm_hessian_csr: no Hessian cached (call lrvb_glmm_eval with order 2)");
+    set_error("%s: no Hessian cached (call lrvb_glmm_eval with order 2)", who);
     return LRVB_ESTATE;
   }
   int64_t cap = 0;
   lrvb_glmm_hessian_csr_capacity(h, &cap);
-  LRVB_REQUIRE(capacity >= cap, "lrvb_glmm_hessian_csr: capacity %lld < structural bound %lld",
-               (long long)capacity, (long long)cap);
+  LRVB_REQUIRE(capacity >= cap, "%s: capacity %lld < structural bound %lld", who, (long long)capacity, (long long)cap);
   LRVB_REQUIRE(cap < (int64_t)2147483647, "Hessian may have %lld nonzeros: exceeds int32 CSR indices",
                (long long)cap);
   LRVB_TRY(ensure_csr_scratch(h));
@@ -391,11 +437,12 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
 
   const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
   // ---- counts: rows of A, columns of B (per chunk) and local rows in one launch ----
-  LRVB_CUDA(launch_pdl(k_csr_pass<false>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G,
-                       CG, nA, nB, cntA, chunkcnt, nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr));
+  LRVB_CUDA(launch_pdl(k_csr_pass<0>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G,
+                       CG, nA, nB, cntA, chunkcnt, nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr,
+                       (uint32_t*)nullptr, MismatchFlag{nullptr, nullptr}, run_if));
   LRVB_CHECK_LAUNCH();
   if (G > 0) {
-    LRVB_CUDA(launch_pdl(k_csr_colscan, dim3(2 * Dg), dim3(256), 0, st, chunkcnt, chunkoff, coltot, nchunk, 2 * Dg));
+    LRVB_CUDA(launch_pdl(k_csr_colscan, dim3(2 * Dg), dim3(256), 0, st, chunkcnt, chunkoff, coltot, nchunk, 2 * Dg, run_if));
     LRVB_CHECK_LAUNCH();
   } else {
     LRVB_CUDA(cudaMemsetAsync(coltot, 0, sizeof(int32_t) * 2 * Dg, st));
@@ -403,21 +450,62 @@ int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_de
   // ---- indptr ----
   if (D <= kIndptrOneCta) {
     LRVB_CUDA(launch_pdl(k_csr_indptr_small, dim3(1), dim3(1024), 0, st, cntA, coltot, Dg, h->rowcnt, D,
-                         indptr_dev, (int64_t*)nnz_dev));
+                         indptr_dev, (int64_t*)nnz_dev, run_if));
     LRVB_CHECK_LAUNCH();
   } else {
-    LRVB_CUDA(launch_pdl(k_csr_global_rowcnt, dim3(cdiv(Dg, 256)), dim3(256), 0, st, cntA, coltot, Dg, h->rowcnt));
+    LRVB_CUDA(launch_pdl(k_csr_global_rowcnt, dim3(cdiv(Dg, 256)), dim3(256), 0, st, cntA, coltot, Dg, h->rowcnt, run_if));
     LRVB_CHECK_LAUNCH();
-    LRVB_CUDA(launch_pdl(k_scan_sum, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk));
+    LRVB_CUDA(launch_pdl(k_scan_sum, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, run_if));
     LRVB_CHECK_LAUNCH();
-    LRVB_CUDA(launch_pdl(k_scan_top, dim3(1), dim3(32), 0, st, blk, nblk, blk + nblk, nnz_dev));
+    LRVB_CUDA(launch_pdl(k_scan_top, dim3(1), dim3(32), 0, st, blk, nblk, blk + nblk, nnz_dev, run_if));
     LRVB_CHECK_LAUNCH();
-    LRVB_CUDA(launch_pdl(k_scan_apply, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, blk + nblk, indptr_dev));
+    LRVB_CUDA(launch_pdl(k_scan_apply, dim3(nblk), dim3(256), 0, st, h->rowcnt, D, blk, blk + nblk, indptr_dev, run_if));
     LRVB_CHECK_LAUNCH();
   }
-  // ---- fill: the same three roles, one launch ----
-  LRVB_CUDA(launch_pdl(k_csr_pass<true>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
-                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev));
+  // ---- fill: the same three roles, one launch; records the zero mask for later refills ----
+  LRVB_CUDA(launch_pdl(k_csr_pass<1>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
+                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev,
+                       h->csrmask, MismatchFlag{nullptr, nullptr}, run_if));
+  LRVB_CHECK_LAUNCH();
+  h->csr_pattern_valid = 1;
+  return LRVB_OK;
+}
+
+int lrvb_glmm_hessian_csr(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_dev,
+                          double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream) {
+  return csr_full_export(h, indptr_dev, indices_dev, data_dev, capacity, nnz_dev, nullptr, "lrvb_glmm_hessian_csr",
+                         stream);
+}
+
+int lrvb_glmm_hessian_csr_if(lrvb_glmm* h, const int32_t* run_if_dev, int32_t* indptr_dev, int32_t* indices_dev,
+                             double* data_dev, int64_t capacity, int64_t* nnz_dev, void* stream) {
+  LRVB_REQUIRE(run_if_dev != nullptr, "lrvb_glmm_hessian_csr_if: run_if is NULL");
+  return csr_full_export(h, indptr_dev, indices_dev, data_dev, capacity, nnz_dev, (const int*)run_if_dev,
+                         "lrvb_glmm_hessian_csr_if", stream);
+}
+
+int lrvb_glmm_hessian_csr_refill(lrvb_glmm* h, const int32_t* indptr_dev, double* data_dev, int32_t* mismatch_dev,
+                                 int32_t* mismatch_host_mapped, void* stream) {
+  LRVB_REQUIRE(h != nullptr && indptr_dev && data_dev && mismatch_dev, "lrvb_glmm_hessian_csr_refill: NULL argument");
+  if (!h->hess_valid) {
+    set_error("lrvb_glmm_hessian_csr_refill: no Hessian cached (call lrvb_glmm_eval with order 2)");
+    return LRVB_ESTATE;
+  }
+  if (!h->csr_pattern_valid || !h->rowcnt) {
+    set_error("lrvb_glmm_hessian_csr_refill: no pattern recorded (call lrvb_glmm_hessian_csr first)");
+    return LRVB_ESTATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Dg = h->Dg, G = h->G, CG = h->csr_cg, nchunk = h->csr_nchunk;
+  int32_t* cntA = h->csrwork;
+  int32_t* coltot = cntA + Dg;
+  int32_t* chunkcnt = coltot + 2 * Dg;
+  int32_t* chunkoff = chunkcnt + (size_t)2 * Dg * nchunk;
+  const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
+  const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
+  LRVB_CUDA(launch_pdl(k_csr_pass<2>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
+                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, (int32_t*)nullptr, data_dev,
+                       h->csrmask, MismatchFlag{(int*)mismatch_dev, (int*)mismatch_host_mapped}, (const int*)nullptr));
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }

@@ -345,13 +345,47 @@ __device__ __forceinline__ void gram_small_finish_body(int bid, const double* __
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-group sums as the finishing pass sees them.  The fused observation kernels write a group's sums
+// (gsc: 5 scalars, BR: 4 x K) directly when the group lies inside one warp's row range; a group that
+// straddles ranges has its pieces in bval (head / tail records per warp, layout [5 | 4K]) and they are
+// added here in row order -- the separate k_obs_fixup launch of round 1 folded into the consumer.
+// rpw = rows per warp of the producing kernel (0: gsc / BR are complete, e.g. the K > 62 path).
+struct GroupFix {
+  const int32_t* gptr;
+  const double* bval;
+  unsigned rpw;    // rows per warp (N < 2^31: 32-bit divisions)
+  int nb;          // 5 + 4K
+};
+struct GroupSpan {
+  unsigned wf, wl;     // first / last producing warp; wf > wl: empty group; wf == wl: the sums were written directly
+};
+__device__ __forceinline__ GroupSpan group_span(const GroupFix& fx, int gi) {
+  GroupSpan sp;
+  sp.wf = sp.wl = 0;
+  if (fx.rpw == 0) return sp;
+  const unsigned gb = (unsigned)fx.gptr[gi], ge = (unsigned)fx.gptr[gi + 1];
+  if (gb == ge) { sp.wf = 1; sp.wl = 0; return sp; }        // empty group: nobody wrote its sums
+  sp.wf = gb / fx.rpw;
+  sp.wl = (ge - 1) / fx.rpw;
+  return sp;
+}
+__device__ __forceinline__ double group_val(const GroupFix& fx, const GroupSpan& sp, const double* __restrict__ direct,
+                                            size_t di, int e) {
+  if (sp.wf == sp.wl) return direct[di];
+  if (sp.wf > sp.wl) return 0.0;
+  double s = fx.bval[((size_t)sp.wf * 2 + 1) * fx.nb + e];     // tail of the first warp
+  for (unsigned wi = sp.wf + 1; wi <= sp.wl; ++wi) s += fx.bval[((size_t)wi * 2) * fx.nb + e];   // heads, row order
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
 // Group-level chain rule: local gradient, local 2x2 blocks, and partial sums of the
 // random-effect term  sum_g [-1/2 E[tau]((E mu - E u_g)^2 + Var mu + Var u_g) + 1/2 E log tau]
 // (GammaParams.py:9-13, NormalParams.py:58-63).
 template <int ORDER>
 __device__ __forceinline__ void local_body(int bid, int nblk, const double* __restrict__ vec, const double* __restrict__ gsc,
         double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ locpart,
-        int K, int G, lrvb_glmm_bounds bd, int vecmode) {
+        int K, int G, lrvb_glmm_bounds bd, int vecmode, const GroupFix& fx) {
   __shared__ double red[32];
   const int Dg = 4 + 2 * K;
   const double mu_m = vec[0], mu_i = vec[1], a = vec[2], b = vec[3];
@@ -365,7 +399,11 @@ __device__ __forceinline__ void local_body(int bid, int nblk, const double* __re
     ssum += dm * dm + 1.0 / mu_i + r;
     lsum += log(ui);
     if (ORDER >= 1) {
-      const double* s = gsc + (size_t)gi * 5;
+      double s[5];
+      const GroupSpan sp = group_span(fx, gi);
+#pragma unroll
+      for (int e = 0; e < 5; ++e)
+        s[e] = (ORDER >= 2 || e < 2) ? group_val(fx, sp, gsc, (size_t)gi * 5 + e, e) : 0.0;
       const double r2 = r * r;
       const double gF_um = s[0] + E * dm;
       const double gF_ui = -s[1] * r2 + 0.5 * E * r2 - 0.5 * r;
@@ -397,68 +435,44 @@ __device__ __forceinline__ void local_body(int bid, int nblk, const double* __re
   }
 }
 
-// Border rows B (G,2,Dg) in free coordinates: row 0 = (u.mean_g, globals), row 1 = (u.info_g, .)
+// Border rows B (G,2,Dg) in free coordinates: row 0 = (u.mean_g, globals), row 1 = (u.info_g, .).
+// One warp per group (8 groups per block), lanes over the Dg columns: the group's producer span
+// (group_span: two loads and two divisions) is computed once per warp, not once per entry.
 __device__ __forceinline__ void border_body(int bid, const double* __restrict__ vec, const double* __restrict__ BR, double* __restrict__ B,
-         int K, int G, lrvb_glmm_bounds bd, int vecmode) {
+         int K, int G, lrvb_glmm_bounds bd, int vecmode, const GroupFix& fx) {
   const int Dg = 4 + 2 * K;
-  const int64_t idx = (int64_t)bid * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)G * Dg) return;
-  const int gi = (int)(idx / Dg), col = (int)(idx - (int64_t)gi * Dg);
+  const int lane = threadIdx.x & 31;
+  const int gi = bid * 8 + (threadIdx.x >> 5);
+  if (gi >= G) return;
   const double mu_m = vec[0], a = vec[2], b = vec[3];
   const double um = vec[Dg + gi], ui = vec[Dg + G + gi];
   const double r2 = 1.0 / (ui * ui);
   const double dr = -r2;
   const double ji = ui - bd.u_info;
-  double b0, b1, jg = 1.0;
-  if (col == 0) { b0 = a / b; b1 = 0.0; }
-  else if (col == 1) { b0 = 0.0; b1 = 0.0; jg = vec[1] - bd.mu_info; }
-  else if (col == 2) { b0 = (mu_m - um) / b; b1 = 0.5 * r2 / b; jg = a - bd.tau_shape; }
-  else if (col == 3) { b0 = -a * (mu_m - um) / (b * b); b1 = -0.5 * a * r2 / (b * b); jg = b - bd.tau_rate; }
-  else if (col < 4 + K) {
-    const int k = col - 4;
-    const double* br = BR + (size_t)gi * 4 * K;
-    b0 = br[k];
-    b1 = br[K + k] * dr;
-  } else {
-    const int k = col - 4 - K;
-    const double* br = BR + (size_t)gi * 4 * K;
-    const double ik = vec[4 + K + k];
-    const double dv = -1.0 / (ik * ik);
-    jg = ik - bd.beta_info;
-    b0 = br[2 * K + k] * dv;
-    b1 = br[3 * K + k] * dv * dr;
-  }
+  const GroupSpan sp = group_span(fx, gi);
+  const size_t br = (size_t)gi * 4 * K;
   double* out = B + (size_t)gi * 2 * Dg;
-  if (vecmode) jg = 1.0;
-  out[col] = -b0 * jg;
-  out[Dg + col] = -b1 * jg * (vecmode ? 1.0 : ji);
-}
-
-// ------------------------------------------------------------------------------------------
-// One launch for the three independent finishing passes: blocks [0, n_loc) run the group-level
-// chain rule, the next n_bor blocks the border rows, the rest the Gram finish (block-uniform roles).
-template <int ORDER>
-__global__ void __launch_bounds__(256)
-k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const double* __restrict__ BR,
-         double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ B,
-         double* __restrict__ locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
-         const GbSlot* __restrict__ slots, double* __restrict__ A, int K, int G, int n_loc, int n_bor,
-         int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode) {
-  // wait first: k_global, the dependent, reads the observation pass's partials ahead of its own wait and
-  // may only be scheduled once everything before this kernel has completed
-  pdl_wait();
-  pdl_launch_dependents();
-  const int bid = blockIdx.x;
-  const int Dg = 4 + 2 * K;
-  if (bid < n_loc) {
-    local_body<ORDER>(bid, n_loc, vec, gsc, gradl, L, locpart, K, G, bd, vecmode);
-  } else if (bid < n_loc + n_bor) {
-    border_body(bid - n_loc, vec, BR, B, K, G, bd, vecmode);
-  } else if (gram_small) {
-    gram_small_finish_body(bid - n_loc - n_bor, grampart, vec, A, K, Dg, NT, gram_chunks, bd, vecmode);
-  } else {
-    gram_big_finish_body(bid - n_loc - n_bor, grampart, jobs, slots, vec, A, K, Dg, gram_groups, gram_chunks,
-                         bd, vecmode);
+  for (int col = lane; col < Dg; col += 32) {
+    double b0, b1, jg = 1.0;
+    if (col == 0) { b0 = a / b; b1 = 0.0; }
+    else if (col == 1) { b0 = 0.0; b1 = 0.0; jg = vec[1] - bd.mu_info; }
+    else if (col == 2) { b0 = (mu_m - um) / b; b1 = 0.5 * r2 / b; jg = a - bd.tau_shape; }
+    else if (col == 3) { b0 = -a * (mu_m - um) / (b * b); b1 = -0.5 * a * r2 / (b * b); jg = b - bd.tau_rate; }
+    else if (col < 4 + K) {
+      const int k = col - 4;
+      b0 = group_val(fx, sp, BR, br + k, 5 + k);
+      b1 = group_val(fx, sp, BR, br + K + k, 5 + K + k) * dr;
+    } else {
+      const int k = col - 4 - K;
+      const double ik = vec[4 + K + k];
+      const double dv = -1.0 / (ik * ik);
+      jg = ik - bd.beta_info;
+      b0 = group_val(fx, sp, BR, br + 2 * K + k, 5 + 2 * K + k) * dv;
+      b1 = group_val(fx, sp, BR, br + 3 * K + k, 5 + 3 * K + k) * dv * dr;
+    }
+    if (vecmode) jg = 1.0;
+    out[col] = -b0 * jg;
+    out[Dg + col] = -b1 * jg * (vecmode ? 1.0 : ji);
   }
 }
 
@@ -468,48 +482,62 @@ k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const d
 // :191-195 priors), the global gradient and the 4x4 corner / diagonal extras of A,
 // then the vector->free chain rule (Parameters.py:397-424 for diagonal transforms).
 // out = [KL, grad_g (Dg), A (Dg*Dg)].
+struct GlobalArgs {
+  const double* klpart; int n_kl; const double* gradpart; int n_gp; int n_lp; double* out;
+  lrvb_glmm_prior pr; int include_global; unsigned int* counter;
+  double* pre;      // scratch [data_ll, psi, psi1, psi2, lgamma | gsum (2K)] from block 0 for the last block
+};
+// Block 0 of k_finish: what needs only the kernels BEFORE k_finish -- the special functions of tau.shape
+// (long serial chains: one lane of four different warps each) and the fixed-order sums of the observation
+// pass's partials -- computed while the other blocks do the group-level work.
 template <int ORDER>
-__global__ void __launch_bounds__(256)
-k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int n_kl,
-         const double* __restrict__ gradpart, int n_gp, const double* __restrict__ locpart,
-         int n_lp, double* __restrict__ out, int K, int G, lrvb_glmm_prior pr,
-         lrvb_glmm_bounds bd, int include_global, int vecmode) {
-  // Programmatic dependent launch: this CTA is resident while k_finish, its prerequisite, still runs.
-  // k_finish signals its dependents only after its own wait, so every kernel before it -- k_prep (vec)
-  // and the observation pass (klpart, gradpart) -- has completed: the special functions and the
-  // reductions over those partials run here, hidden behind k_finish; only the group-level partials
-  // (locpart) and the global block A need the wait.
+__device__ __forceinline__ void global_pre(const double* __restrict__ vec, const GlobalArgs& ga, int K) {
   __shared__ double red[32];
-  __shared__ double sh[8];
-  extern __shared__ double gsum[];  // 2K
   const int tid = threadIdx.x;
-  const int Dg = 4 + 2 * K;
-  // the special functions of tau.shape are long serial chains: one lane of four different warps
-  // evaluates one each while the block reduces the partials (joined at the barriers below)
-  __shared__ double spec[4];
-  if (tid == 32) spec[0] = digamma_pos(vec[2]);
-  else if (tid == 64) spec[1] = trigamma_pos(vec[2]);
-  else if (tid == 96) spec[2] = tetragamma_pos(vec[2]);
-  else if (tid == 128) spec[3] = lgamma(vec[2]);
+  double* pre = ga.pre;
+  if (tid == 32) pre[1] = digamma_pos(vec[2]);
+  else if (tid == 64) pre[2] = trigamma_pos(vec[2]);
+  else if (tid == 96) pre[3] = tetragamma_pos(vec[2]);
+  else if (tid == 128) pre[4] = lgamma(vec[2]);
   double v = 0.0;
-  for (int i = tid; i < n_kl; i += blockDim.x) v += klpart[i];
+  for (int i = tid; i < ga.n_kl; i += blockDim.x) v += ga.klpart[i];
   const double data_ll = block_sum(v, red);
+  if (tid == 0) pre[0] = data_ll;
   if (ORDER >= 1) {
     // one warp per column, lanes over the per-CTA partials (fixed order: deterministic)
     for (int k = tid >> 5; k < 2 * K; k += blockDim.x >> 5) {
       double s = 0.0;
-      for (int p = tid & 31; p < n_gp; p += 32) s += gradpart[(size_t)k * n_gp + p];
+      for (int p = tid & 31; p < ga.n_gp; p += 32) s += ga.gradpart[(size_t)k * ga.n_gp + p];
       s = warp_sum(s);
-      if ((tid & 31) == 0) gsum[k] = s;
+      if ((tid & 31) == 0) pre[8 + k] = s;
     }
   }
-  pdl_wait();                       // k_finish has completed: locpart, A
-  pdl_launch_dependents();          // after the wait: the CSR count pass reads B and L ahead of ITS wait
+}
+// k_global_post (one CTA, after k_finish): fixed-order sums of
+// the group-level partials, the non-data terms (ExponentialFamilies.py:23-25 uvn entropy, :33-35 gamma
+// entropy, :111-112 E log tau, :191-195 priors), the global gradient, the 4x4 corner / diagonal extras of
+// A and the vector->free chain rule (Parameters.py:397-424).
+template <int ORDER>
+__device__ __forceinline__ void global_post(const double* __restrict__ vec, const GlobalArgs& ga, const double* locpart,
+                                            int K, int G, lrvb_glmm_bounds bd, int vecmode) {
+  const int n_lp = ga.n_lp, include_global = ga.include_global;
+  double* out = ga.out;
+  const lrvb_glmm_prior pr = ga.pr;
+  __shared__ double red[32];
+  __shared__ double sh[8];
+  __shared__ double spec[4];
+  extern __shared__ double gsum[];  // 2K
+  const int tid = threadIdx.x;
+  const int Dg = 4 + 2 * K;
+  if (tid < 4) spec[tid] = __ldcg(ga.pre + 1 + tid);
+  if (ORDER >= 1)
+    for (int k = tid; k < 2 * K; k += blockDim.x) gsum[k] = __ldcg(ga.pre + 8 + k);
+  const double data_ll = __ldcg(ga.pre);
   double d0 = 0, d1 = 0, d2 = 0;
-  for (int i = tid; i < n_lp; i += blockDim.x) {
-    d0 += locpart[i * 4 + 0];
-    d1 += locpart[i * 4 + 1];
-    d2 += locpart[i * 4 + 2];
+  for (int i = tid; i < n_lp; i += blockDim.x) {      // written by other CTAs of this grid: L2 loads
+    d0 += __ldcg(locpart + i * 4 + 0);
+    d1 += __ldcg(locpart + i * 4 + 1);
+    d2 += __ldcg(locpart + i * 4 + 2);
   }
   d0 = block_sum(d0, red);
   d1 = block_sum(d1, red);
@@ -600,13 +628,60 @@ k_global(const double* __restrict__ vec, const double* __restrict__ klpart, int 
           emm += -pr.beta_info;
           eii += 0.5 * rb * rb - pr.beta_info * rb * rb * rb;
         }
-        A[(size_t)(4 + k) * Dg + 4 + k] += -emm;
-        A[(size_t)(4 + K + k) * Dg + 4 + K + k] += -eii * jb * jb + (vecmode ? 0.0 : (-gbi) * jb);
+        double* a0 = A + (size_t)(4 + k) * Dg + 4 + k;
+        double* a1 = A + (size_t)(4 + K + k) * Dg + 4 + K + k;
+        *a0 = __ldcg(a0) - emm;
+        *a1 = __ldcg(a1) - eii * jb * jb + (vecmode ? 0.0 : (-gbi) * jb);
       }
     }
   }
   fpart = block_sum(fpart, red);
   if (tid == 0) out[0] = -(sh[4] + fpart);
+}
+
+// ------------------------------------------------------------------------------------------
+// One launch for the finishing passes (round 1: k_obs_fixup, k_finish and the first half of k_global):
+// block 0 runs global_pre; blocks [1, 1 + n_loc) the group-level chain rule, the next n_bor the border
+// rows, the next n_gf the Gram finish (block-uniform roles).
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const double* __restrict__ BR,
+         double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ B,
+         double* locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
+         const GbSlot* __restrict__ slots, double* A, int K, int G, int n_loc, int n_bor,
+         int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode,
+         GroupFix fx, GlobalArgs ga) {
+  // wait first: the dependent (k_global_post) signals ITS dependents after its own wait, so whoever follows
+  // it may read B and L ahead of its wait (the CSR refill does)
+  pdl_wait();
+  pdl_launch_dependents();
+  const int Dg = 4 + 2 * K;
+  const int bid = (int)blockIdx.x - 1;
+  if (bid < 0) {
+    global_pre<ORDER>(vec, ga, K);
+  } else if (bid < n_loc) {
+    local_body<ORDER>(bid, n_loc, vec, gsc, gradl, L, locpart, K, G, bd, vecmode, fx);
+  } else if (bid < n_loc + n_bor) {
+    border_body(bid - n_loc, vec, BR, B, K, G, bd, vecmode, fx);
+  } else if (gram_small) {
+    gram_small_finish_body(bid - n_loc - n_bor, grampart, vec, A, K, Dg, NT, gram_chunks, bd, vecmode);
+  } else {
+    gram_big_finish_body(bid - n_loc - n_bor, grampart, jobs, slots, vec, A, K, Dg, gram_groups, gram_chunks,
+                         bd, vecmode);
+  }
+}
+
+// Single-CTA end of the evaluation: global_post on the results of k_finish.  Signals its dependents only
+// after its own wait: when the next kernel's CTAs start, k_finish has completed (B, L and the Gram part
+// of A are final); only what this kernel writes (KL, global gradient, corner and diagonal of A) needs
+// the next kernel's own wait.
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+k_global_post(const double* __restrict__ vec, const double* locpart, int K, int G, lrvb_glmm_bounds bd, int vecmode,
+              GlobalArgs ga) {
+  pdl_wait();
+  pdl_launch_dependents();
+  global_post<ORDER>(vec, ga, locpart, K, G, bd, vecmode);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -624,6 +699,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   LRVB_CHECK_LAUNCH();
 
   int n_obs_cta = 0;
+  int64_t fix_rpw = 0;       // rows per warp of the fused producer whose straddling-group pieces sit in bval
   const bool one_pass = h->fused2 && order >= 2 && N > 0;
   h->ev_gram = 0;
   if (one_pass) {
@@ -641,11 +717,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     LRVB_CHECK_LAUNCH();
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
     n_obs_cta = h->fu_grid;
-    if (G > 0) {
-      LRVB_CUDA(launch_pdl(k_obs_fixup<2>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G,
-                           h->fu_rows_per_team));
-      LRVB_CHECK_LAUNCH();
-    }
+    fix_rpw = h->fu_rows_per_team;       // pieces of straddling groups are added by k_finish's readers
   } else if (h->obs_fused) {
     // K <= 62: observation pass and per-group sums in one kernel (obs_fused.cuh)
     if (N > 0) {
@@ -669,12 +741,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
       n_obs_cta = h->of_grid;
     }
-    if (order >= 1 && G > 0) {
-      const int64_t rpw = h->of_rows_per_warp > 0 ? h->of_rows_per_warp : 32;
-      if (order == 1) LRVB_CUDA(launch_pdl(k_obs_fixup<1>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G, rpw));
-      else LRVB_CUDA(launch_pdl(k_obs_fixup<2>, dim3(cdiv(G, 8)), dim3(256), 0, st, h->gptr, h->bval, h->gsc, h->BR, K, G, rpw));
-      LRVB_CHECK_LAUNCH();
-    }
+    if (N > 0) fix_rpw = h->of_rows_per_warp > 0 ? h->of_rows_per_warp : 32;
   } else {
   if (N > 0) {
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
@@ -729,36 +796,40 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     const int packed_gram = (h->gram_small || h->gram_mid || one_pass) ? 1 : 0;   // partial layout (n_cta, NT, 64)
     const int packed_ctas = one_pass ? h->fu_grid : h->gram_grid_x;
     if (order >= 2) {
-      if (G > 0) n_bor = cdiv((int64_t)G * Dg, 256);
+      if (G > 0) n_bor = cdiv(G, 8);
       if (N > 0) {
         if (packed_gram) { NT = gram_small_shape(K).NT; n_gf = NT; }
         else n_gf = h->gram_jobs * 16;
       }
     }
-    const int grid = n_loc + n_bor + n_gf;
-
+    const int n_work = n_loc + n_bor + n_gf;
+    GroupFix fx;
+    fx.gptr = h->gptr; fx.bval = h->bval; fx.rpw = (N > 0) ? (unsigned)fix_rpw : 0u; fx.nb = 5 + 4 * K;
+    if (N == 0 && h->obs_fused) {
+      // no observation kernel ran: every group is empty, which the readers must see as zeros
+      fx.rpw = 32;
+    }
+    GlobalArgs ga;
+    ga.klpart = h->klpart; ga.n_kl = n_obs_cta; ga.gradpart = h->gradpart; ga.n_gp = n_obs_cta;
+    ga.n_lp = h->loc_grid; ga.out = outp; ga.pr = h->prior; ga.include_global = h->include_global;
+    ga.counter = h->fin_counter;
+    ga.pre = h->fin_pre;
+    const size_t gsm = sizeof(double) * 2 * (size_t)K;
 #define LRVB_FIN(O)                                                                              \
-  LRVB_CUDA(launch_pdl(k_finish<O>, dim3(grid), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
+  LRVB_CUDA(launch_pdl(k_finish<O>, dim3(n_work + 1), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
                        h->locpart, h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,   \
                        outp + 1 + Dg, K, G, n_loc, n_bor, packed_gram, NT, h->gram_grid_y,         \
                        packed_gram ? packed_ctas : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
-                       h->bounds, h->vecmode))
-    if (order == 0) LRVB_FIN(0);
-    else if (order == 1) LRVB_FIN(1);
-    else LRVB_FIN(2);
+                       h->bounds, h->vecmode, fx, ga));                                            \
+  LRVB_CHECK_LAUNCH();                                                                           \
+  LRVB_CUDA(launch_pdl(k_global_post<O>, dim3(1), dim3(256), gsm, st, h->vec, h->locpart, K, G, h->bounds, \
+                       h->vecmode, ga))
+    if (order == 0) { LRVB_FIN(0); }
+    else if (order == 1) { LRVB_FIN(1); }
+    else { LRVB_FIN(2); }
 #undef LRVB_FIN
     LRVB_CHECK_LAUNCH();
   }
-  const size_t gsm = sizeof(double) * 2 * (size_t)K;
-#define LRVB_GLOB(O)                                                                          \
-  LRVB_CUDA(launch_pdl(k_global<O>, dim3(1), dim3(256), gsm, st, h->vec, h->klpart, n_obs_cta, \
-                       h->gradpart, n_obs_cta, h->locpart, h->loc_grid, outp, K, G, h->prior,    \
-                       h->bounds, h->include_global, h->vecmode))
-  if (order == 0) LRVB_GLOB(0);
-  else if (order == 1) LRVB_GLOB(1);
-  else LRVB_GLOB(2);
-#undef LRVB_GLOB
-  LRVB_CHECK_LAUNCH();
   if (outp != h->outg) {
     const size_t nout = 1 + (order >= 1 ? Dg : 0) + (order >= 2 ? (size_t)Dg * Dg : 0);
     LRVB_CUDA(cudaMemcpyAsync(h->outg, outp, sizeof(double) * nout, cudaMemcpyDeviceToDevice, st));

@@ -203,6 +203,61 @@ def test_cg_general_preconditioner(vb):
         solver.get_hinv_vec(b)
 
 
+def test_csr_refill_follows_pattern_changes(vb):
+    """The CSR export after the first one rewrites the values for the cached pattern and checks the zero
+    mask on the device; when an entry becomes exactly zero (or stops being zero) the conditional full
+    export must take over -- without any help from the host -- and later refills use the new pattern."""
+    import scipy.sparse
+    case = make_case(N=4000, K=6, G=40, Q=8, seed=91, ragged=True, empty_groups=3)
+    oracle, model = make_oracle(case), make_model(vb, case)
+    x = case["free"]
+
+    def dense_from_blocks():
+        A, B, L = [t.cpu().numpy() for t in model.blocks()]
+        return oracle.blocks_to_dense(oracle.lay, dict(A=A, B=B, L=L))
+
+    def check(H):
+        ref = scipy.sparse.csr_matrix(dense_from_blocks())
+        ref.sort_indices()
+        Hs = H.to_scipy()
+        np.testing.assert_array_equal(Hs.indptr, ref.indptr)
+        np.testing.assert_array_equal(Hs.indices, ref.indices)
+        np.testing.assert_array_equal(Hs.data, ref.data)
+
+    model.evaluate(x, 2)
+    H1 = model.hessian_csr()                 # full export
+    check(H1)
+    H2 = model.hessian_csr()                 # refill, same pattern
+    assert H2._pending is not None
+    check(H2)
+    assert H2._pattern is H1._pattern        # shared index arrays
+    A = model.blocks()[0].clone()
+    A2 = A.clone()
+    A2[5, 7] = A2[7, 5] = 0.0
+    A2[0, 0] = 0.0
+    model.set_global_block(A2)
+    H3 = model.hessian_csr()                 # refill sees a different zero mask -> conditional export ran
+    check(H3)
+    assert H3.nnz == H1.nnz - 3
+    H4 = model.hessian_csr()                 # refill against the NEW pattern
+    check(H4)
+    assert H4._pattern is H3._pattern and H4._pattern is not H1._pattern
+    model.set_global_block(A)
+    H5 = model.hessian_csr()                 # and back
+    check(H5)
+    assert H5.nnz == H1.nnz
+    # a new evaluation point through the objective (host matrices share the pattern's index arrays)
+    obj = vb.Objective(model.glmm_par, model)
+    x2 = x + 0.05 * np.random.default_rng(2).standard_normal(x.size)
+    Ha, Hb = obj.fun_free_hessian(x), obj.fun_free_hessian(x2)
+    He = oracle.kl_hessian_csr(x2)
+    np.testing.assert_array_equal(Hb.indices, He.indices)
+    assert_close(Hb.data, He.data, scale=np.abs(He.data).max() * 1e-6, what="hessian data after refill")
+    assert Ha.indices is Hb.indices or np.shares_memory(Ha.indices, Hb.indices)
+    with pytest.raises(ValueError):
+        Hb.indices[0] = 3                    # shared index arrays are read-only
+
+
 def test_no_observations(vb):
     """N = 0 (a rank that owns no group in a sharded job, or priors only): the data kernels are
     skipped, the non-data terms and the Hessian pattern must still match the oracle."""

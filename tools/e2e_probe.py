@@ -28,7 +28,7 @@ def main():
         model.evaluate(x, 2); t = lap("evaluate (launch)", t)
         obj._set_par(x, "free"); t = lap("_set_par", t)
         csr = model.hessian_csr(); t = lap("hessian_csr (launch)", t)
-        H = csr.to_scipy(cache=model._pattern_cache); t = lap("to_scipy (sync + D2H)", t)
+        H = csr.to_scipy(); t = lap("to_scipy (sync + D2H)", t)
         gr = obj.fun_free_grad(x); t = lap("fun_free_grad", t)
         kl = obj.fun_free(x); t = lap("fun_free", t)
     for k, v in acc.items():
