@@ -300,9 +300,9 @@ def time_workload(ctx, wl, mode, steps, warmup, sampler=None, kernel_steps=30):
     torch.cuda.synchronize()                # the allocator then owns both ping-pong result blocks
     if sampler is not None:
         sampler.start()
-        for _ in range(3):                  # the sampler thread's first NVML calls happen untimed
-            flush.zero_()
-            csr = device_step()
+    for _ in range(3):                      # the sampler thread's first NVML calls happen untimed (every
+        flush.zero_()                       # rank runs these steps: they contain a collective)
+        csr = device_step()
     if peer is not None:
         peer.set_stats(True)
     gc.collect()
@@ -478,6 +478,47 @@ def cov_entry(ctx, model, K, G_local, peak_tf, ncov=20):
             "bound": "latency (work far below one wave of the tensor pipe)" if Dg < 128 else "tensor / latency"}
 
 
+def cov_cg_entry(ctx, res, max_seconds=40.0):
+    """BASELINE configs[3]: the global-parameter LRVB covariance by CONJUGATE GRADIENT with device Hessian-
+    vector products (ConjugateGradient.py:81-105), one solve per global parameter, block-Jacobi
+    preconditioner, rtol 1e-8 -- next to the Schur path.  Columns are solved until `max_seconds` of device
+    time are spent; the total is extrapolated from the per-solve mean when not all Dg columns were run."""
+    torch = ctx.torch
+    model, x_dev = res["model"], res["x_dev"]
+    model.evaluate(x_dev, 2)
+    Dg, D = model.Dg, model.D
+    sinv = model.global_covariance()
+    e = torch.zeros(D, dtype=torch.float64, device=ctx.device)
+    iters, ms, err = [], [], 0.0
+    t_all = 0.0
+    for i in range(Dg):
+        e.zero_()
+        e[i] = 1.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x, info, it = model.cg(e, None, precond="block_jacobi", rtol=1e-8)
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        ms.append(t); iters.append(it)
+        t_all += t
+        err = max(err, float(((x[:Dg] - sinv[i]).abs().max() / sinv.abs().max()).item()))
+        if info != 0:
+            break
+        if t_all > 1e3 * max_seconds:
+            break
+    n = len(ms)
+    return {"what": "(H^-1)[:Dg,:Dg] column by column: device CG (scipy.sparse.linalg.cg semantics, rtol 1e-8, "
+                    "block-Jacobi M), Hessian-vector products on the cached arrowhead blocks",
+            "columns_solved": n, "columns_total": Dg, "iterations_mean": float(np.mean(iters)),
+            "iterations_max": int(np.max(iters)), "ms_per_solve": float(np.mean(ms)),
+            "us_per_iteration": 1e3 * float(np.sum(ms)) / max(1, int(np.sum(iters))),
+            "ms_total_all_columns": float(np.mean(ms)) * Dg, "extrapolated": n < Dg,
+            "max_rel_diff_vs_schur": err,
+            "note": "the point is the bench's (not an optimum): if H is not positive definite there CG reports "
+                    "info != 0 and the run stops"}
+
+
 def e2e_measure(ctx, res, steps, warmup):
     """The same metric through the public API with HOST buffers: numpy x in, scipy CSR + numpy gradient
     + float out, every step at a different point; wall clock, max over ranks."""
@@ -525,11 +566,24 @@ def e2e_measure(ctx, res, steps, warmup):
 
 def parity_single(ctx, res, wl):
     """Untimed check of the very model that was timed (N = 1): KL / gradient / CSR against the CPU oracle
-    on the same data and point (tolerance of the north star: 1e-9 relative)."""
+    on the same data and point (tolerance of the north star: 1e-9 relative).  Workloads whose oracle pass
+    would take minutes (N K > 4e7) are checked on their first 200k observations / 2000 groups, same K."""
     from oracle import glmm_oracle as go
     model, x_dev = res["model"], res["x_dev"]
     t0 = time.perf_counter()
     gh_x, gh_w = np.polynomial.hermite.hermgauss(wl["Q"])
+    if wl["N"] * wl["K"] > 4e7:
+        per = wl["N"] // wl["G"]
+        Gs = max(1, 200_000 // per)
+        Ns = Gs * per
+        sub = ctx.vb.LogisticGLMM(model.X[:Ns], model.y[:Ns], model.g[:Ns], num_gh_points=wl["Q"], num_groups=Gs)
+        Dg = 4 + 2 * wl["K"]
+        idx = ctx.torch.cat([ctx.torch.arange(Dg, device=ctx.device),
+                             Dg + ctx.torch.arange(Gs, device=ctx.device),
+                             Dg + wl["G"] + ctx.torch.arange(Gs, device=ctx.device)])
+        x_dev = x_dev[idx].contiguous()
+        model = sub
+        wl = dict(wl, N=Ns, G=Gs)
     o = go.GLMMOracle(model.X.cpu().numpy(), model.y.cpu().numpy(), model.g.cpu().numpy().astype(np.int64),
                       gh_x, gh_w, G=wl["G"])
     x = x_dev.cpu().numpy()
@@ -670,12 +724,16 @@ def run_ours(args, wl):
         return
 
     K, G, Q = wl["K"], wl["G"], wl["Q"]
+    if wl["N"] * K >= 10 ** 9:                 # C3 / C4 as the headline workload: steps of 6 - 150 ms
+        args.steps = min(args.steps, 20 if K <= 64 else 5)
     mode = "single" if world == 1 else "weak"
     sampler = ClockSampler(local_rank) if rank == 0 else None
     res = time_workload(ctx, wl, mode, args.steps, args.warmup, sampler=sampler)
     peak_tf = measure_dgemm_tflops(torch) if rank == 0 else 1.0
-    cov = cov_entry(ctx, res["model"], K, G, peak_tf)
-    e2e = e2e_measure(ctx, res, min(args.steps, 50), min(args.warmup, 5))
+    cov = cov_entry(ctx, res["model"], K, G, peak_tf, ncov=20 if K <= 64 else 3)
+    if args.workload == "c4" and world == 1:
+        cov["cg"] = cov_cg_entry(ctx, res)
+    e2e = e2e_measure(ctx, res, min(args.steps, 50 if K <= 64 else 2), min(args.warmup, 5 if K <= 64 else 1))
     parity = parity_single(ctx, res, wl) if world == 1 else parity_sharded(ctx, res)
 
     line = None

@@ -231,6 +231,13 @@ int lrvb_ef_gamma_entropy(const double* shape, const double* rate, int64_t M, do
 /* :111-112 get_e_log_gamma, out (M,). */
 int lrvb_ef_e_log_gamma(const double* shape, const double* rate, int64_t M, double* out,
                         void* stream);
+/* :33-35 and :111-112 in one pass over (shape, rate) -- they share digamma(shape) and log(rate):
+ * entropy (M,) and / or e_log (M,); either may be NULL. */
+int lrvb_ef_gamma_terms(const double* shape, const double* rate, int64_t M, double* entropy,
+                        double* e_log, void* stream);
+/* :43-52 and :118-120 in one pass over alpha (d, M): entropy (M,) and / or e_log (d, M); either may be NULL. */
+int lrvb_ef_dirichlet_terms(const double* alpha, int32_t d, int64_t M, double* entropy, double* e_log,
+                            void* stream);
 /* :23-25 univariate_normal_entropy per factor (the reference sums them), out (M,). */
 int lrvb_ef_uvn_entropy(const double* info, int64_t M, double* out, void* stream);
 /* :43-52 dirichlet_entropy: alpha (d, M) row-major, simplex dimension is axis 0; out (M,). */

@@ -102,6 +102,30 @@ def gamma_entropy_batched(shape, rate):
     return like_input(out, shape, rate)
 
 
+def gamma_entropy_and_e_log(shape, rate):
+    """:33-35 and :111-112 per factor from ONE launch (they share digamma(shape) and log(rate)):
+    returns (entropy, e_log), both shaped like ``shape``."""
+    a, b = to_device(shape), to_device(rate)
+    shp = a.shape
+    assert a.numel() == b.numel()
+    ent, el = _empty(a.numel(), a), _empty(a.numel(), a)
+    nat.check(nat.load().lrvb_ef_gamma_terms(nat.ptr(a.reshape(-1)), nat.ptr(b.reshape(-1)), a.numel(),
+                                             nat.ptr(ent), nat.ptr(el), nat.stream_ptr()))
+    return like_input(ent.reshape(shp), shape, rate), like_input(el.reshape(shp), shape, rate)
+
+
+def dirichlet_entropy_and_e_log(alpha):
+    """:43-52 and :118-120 from ONE launch; alpha (d, ...): returns (entropy (...), e_log (d, ...))."""
+    d = to_device(alpha)
+    dim, rest = d.shape[0], tuple(d.shape[1:])
+    flat = d.reshape(dim, -1).contiguous()
+    M = flat.shape[1]
+    ent, el = _empty(M, d), _empty(dim * M, d)
+    nat.check(nat.load().lrvb_ef_dirichlet_terms(nat.ptr(flat), dim, M, nat.ptr(ent), nat.ptr(el),
+                                                 nat.stream_ptr()))
+    return like_input(ent.reshape(rest), alpha), like_input(el.reshape(d.shape), alpha)
+
+
 def gamma_entropy(shape, rate):
     """:33-35 (sums over factors)."""
     a, b = to_device(shape).reshape(-1), to_device(rate).reshape(-1)

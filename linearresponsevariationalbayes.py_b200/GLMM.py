@@ -278,6 +278,7 @@ class LogisticGLMM(object):
         self._csr_pattern = None          # _Pattern of the last full export (shared by refilled matrices)
         self._csr_pending = None          # refill whose pattern check has not been read yet
         self._csr_flag_pin, self._csr_slot = None, 0
+        self._csr_refill_min = 400000     # structural nnz below which a full export is cheaper than a refill
         self._D_in = self.D
         self._coords = "free"
         self.device = dev
@@ -459,7 +460,7 @@ class LogisticGLMM(object):
         pat = self._csr_pattern
         # small problems are launch-bound: the four launches of a full export are cheaper than the refill
         # plus its conditional fallback (and the host-side bookkeeping of the pending check)
-        small = self.Dg * self.Dg + 4 * self.Dg * self.G < 400000
+        small = self.Dg * self.Dg + 4 * self.Dg * self.G < self._csr_refill_min
         if pat is None or small or os.environ.get("LRVB_CSR_REFILL", "1") == "0":
             pat, val = self._export_full()
             self._csr_pattern = pat

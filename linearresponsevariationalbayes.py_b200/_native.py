@@ -72,6 +72,8 @@ SIGNATURES = {
     "lrvb_glmm_local_cov": (c_int32, [_P, _P, _P, _P]),
     "lrvb_ef_gamma_entropy": (c_int32, [_P, _P, c_int64, _P, _P]),
     "lrvb_ef_e_log_gamma": (c_int32, [_P, _P, c_int64, _P, _P]),
+    "lrvb_ef_gamma_terms": (c_int32, [_P, _P, c_int64, _P, _P, _P]),
+    "lrvb_ef_dirichlet_terms": (c_int32, [_P, c_int32, c_int64, _P, _P, _P]),
     "lrvb_ef_uvn_entropy": (c_int32, [_P, c_int64, _P, _P]),
     "lrvb_ef_dirichlet_entropy": (c_int32, [_P, c_int32, c_int64, _P, _P]),
     "lrvb_ef_e_log_dirichlet": (c_int32, [_P, c_int32, c_int64, _P, _P]),

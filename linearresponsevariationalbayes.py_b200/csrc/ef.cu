@@ -16,47 +16,42 @@ constexpr double kLog2Pi = 1.8378770664093454836;
 constexpr double kLogPi = 1.1447298858494001741;
 constexpr double kLog2 = 0.69314718055994530942;
 
-// :33-35
-__global__ void k_gamma_entropy(const double* __restrict__ shape, const double* __restrict__ rate,
-                                int64_t M, double* __restrict__ out) {
+// :33-35 gamma_entropy and :111-112 get_e_log_gamma in ONE pass over (shape, rate): they share digamma(a) and
+// log b.  Either output may be NULL.  16 B in, 8 - 16 B out per factor.
+__global__ void __launch_bounds__(256)
+k_gamma_terms(const double* __restrict__ shape, const double* __restrict__ rate, int64_t M,
+              double* __restrict__ entropy, double* __restrict__ e_log) {
   LRVB_GRID_STRIDE(i, M) {
     const double a = shape[i], b = rate[i];
-    out[i] = a - log(b) + lgamma(a) + (1.0 - a) * digamma_pos(a);
+    const PsiLg f = digamma_lgamma_pos(a, entropy != nullptr);
+    const double lb = log(b);
+    if (entropy) entropy[i] = a - lb + f.lg + (1.0 - a) * f.psi;
+    if (e_log) e_log[i] = f.psi - lb;
   }
-}
-// :111-112
-__global__ void k_e_log_gamma(const double* __restrict__ shape, const double* __restrict__ rate,
-                              int64_t M, double* __restrict__ out) {
-  LRVB_GRID_STRIDE(i, M) out[i] = digamma_pos(shape[i]) - log(rate[i]);
 }
 // :23-25 (per factor)
 __global__ void k_uvn_entropy(const double* __restrict__ info, int64_t M, double* __restrict__ out) {
   LRVB_GRID_STRIDE(i, M) out[i] = 0.5 * (-log(info[i]) + 1.0 + kLog2Pi);
 }
-// :43-52, alpha (d, M): simplex dimension is axis 0
-__global__ void k_dirichlet_entropy(const double* __restrict__ alpha, int d, int64_t M,
-                                    double* __restrict__ out) {
+// :43-52 dirichlet_entropy and :118-120 get_e_log_dirichlet in ONE pass; alpha (d, M): simplex dimension is
+// axis 0.  entropy (M,) and / or e_log (d, M); either may be NULL.
+__global__ void __launch_bounds__(256)
+k_dirichlet_terms(const double* __restrict__ alpha, int d, int64_t M, double* __restrict__ entropy,
+                  double* __restrict__ e_log) {
   LRVB_GRID_STRIDE(i, M) {
     double sum_alpha = 0.0, sum_lg = 0.0, sum_ad = 0.0;
     for (int j = 0; j < d; ++j) {
       const double a = alpha[(int64_t)j * M + i];
+      const PsiLg f = digamma_lgamma_pos(a, entropy != nullptr);
       sum_alpha += a;
-      sum_lg += lgamma(a);
-      sum_ad += (a - 1.0) * digamma_pos(a);
+      sum_lg += f.lg;
+      sum_ad += (a - 1.0) * f.psi;
+      if (e_log) e_log[(int64_t)j * M + i] = f.psi;       // minus digamma(sum) below
     }
-    const double log_beta = sum_lg - lgamma(sum_alpha);
-    out[i] = log_beta - ((double)d - sum_alpha) * digamma_pos(sum_alpha) - sum_ad;
-  }
-}
-// :118-120, out (d, M)
-__global__ void k_e_log_dirichlet(const double* __restrict__ alpha, int d, int64_t M,
-                                  double* __restrict__ out) {
-  LRVB_GRID_STRIDE(i, M) {
-    double sum_alpha = 0.0;
-    for (int j = 0; j < d; ++j) sum_alpha += alpha[(int64_t)j * M + i];
-    const double ds = digamma_pos(sum_alpha);
-    for (int j = 0; j < d; ++j)
-      out[(int64_t)j * M + i] = digamma_pos(alpha[(int64_t)j * M + i]) - ds;
+    const PsiLg fs = digamma_lgamma_pos(sum_alpha, entropy != nullptr);
+    if (entropy) entropy[i] = (sum_lg - fs.lg) - ((double)d - sum_alpha) * fs.psi - sum_ad;
+    if (e_log)
+      for (int j = 0; j < d; ++j) e_log[(int64_t)j * M + i] -= fs.psi;
   }
 }
 // :54-69 per row of tau (M,2)
@@ -64,9 +59,8 @@ __global__ void k_beta_entropy(const double* __restrict__ tau, int64_t M, double
   LRVB_GRID_STRIDE(i, M) {
     const double2 t = reinterpret_cast<const double2*>(tau)[i];
     const double s = t.x + t.y;
-    const double lbeta = lgamma(t.x) + lgamma(t.y) - lgamma(s);
-    out[i] = lbeta - (t.x - 1.0) * digamma_pos(t.x) - (t.y - 1.0) * digamma_pos(t.y) +
-             (s - 2.0) * digamma_pos(s);
+    const PsiLg fx = digamma_lgamma_pos(t.x, true), fy = digamma_lgamma_pos(t.y, true), fs = digamma_lgamma_pos(s, true);
+    out[i] = (fx.lg + fy.lg - fs.lg) - (t.x - 1.0) * fx.psi - (t.y - 1.0) * fy.psi + (s - 2.0) * fs.psi;
   }
 }
 // :20-21, p (M, d)
@@ -85,13 +79,19 @@ __global__ void k_multinoulli_entropy(const double* __restrict__ p, int d, int64
 // :5-13
 __device__ __forceinline__ double mv_digamma(double x, int k) {
   double s = 0.0;
-  for (int j = 0; j < k; ++j) s += digamma_pos(x - 0.5 * j);
+  for (int j = 0; j < k; ++j) s += digamma_lgamma_pos(x - 0.5 * j, false).psi;
   return s;
 }
-__device__ __forceinline__ double mv_gammaln(double x, int k) {
-  double s = 0.0;
-  for (int j = 0; j < k; ++j) s += lgamma(x - 0.5 * j);
-  return s + 0.25 * kLogPi * k * (k - 1.0);
+// multivariate digamma and log-gamma of the same argument, sharing every factor's evaluation
+__device__ __forceinline__ void mv_digamma_gammaln(double x, int k, double& dg, double& lg) {
+  dg = 0.0;
+  lg = 0.0;
+  for (int j = 0; j < k; ++j) {
+    const PsiLg f = digamma_lgamma_pos(x - 0.5 * j, true);
+    dg += f.psi;
+    lg += f.lg;
+  }
+  lg += 0.25 * kLogPi * k * (k - 1.0);
 }
 
 // :72-82 wishart_entropy, :88-94 e_log_det_wishart, :97-102 e_log_inv_wishart_diag, batched:
@@ -120,15 +120,16 @@ __global__ void k_wishart(const double* __restrict__ df, const double* __restric
     }
     if (!ok) atomicExch(status, 1);
     const double n = df[i], kk = (double)k;
+    double mvd, mvl;
+    mv_digamma_gammaln(0.5 * n, k, mvd, mvl);
     if (entropy) {
       entropy[i] = 0.5 * (kk + 1.0) * logdet + 0.5 * kk * (kk + 1.0) * kLog2 +
-                   mv_gammaln(0.5 * n, k) - 0.5 * (n - kk - 1.0) * mv_digamma(0.5 * n, k) +
-                   0.5 * n * kk;
+                   mvl - 0.5 * (n - kk - 1.0) * mvd + 0.5 * n * kk;
     }
-    if (e_log_det) e_log_det[i] = mv_digamma(0.5 * n, k) + kk * kLog2 + logdet;
+    if (e_log_det) e_log_det[i] = mvd + kk * kLog2 + logdet;
     if (e_log_inv_diag) {
       // diag(v^-1)[c] = sum_r (L^-1[r][c])^2 ; column c of L^-1 by forward substitution
-      const double dg = digamma_pos(0.5 * (n - kk + 1.0));
+      const double dg = digamma_lgamma_pos(0.5 * (n - kk + 1.0), false).psi;
       for (int c = 0; c < k; ++c) {
         double col[8];
         double acc = 0.0;
@@ -194,7 +195,7 @@ int lrvb_ef_gamma_entropy(const double* shape, const double* rate, int64_t M, do
                           void* stream) {
   EF_ARGS_OK(M >= 0 && (M == 0 || (shape && rate && out)), "lrvb_ef_gamma_entropy");
   if (M == 0) return LRVB_OK;
-  k_gamma_entropy<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(shape, rate, M, out);
+  k_gamma_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(shape, rate, M, out, nullptr);
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -203,7 +204,25 @@ int lrvb_ef_e_log_gamma(const double* shape, const double* rate, int64_t M, doub
                         void* stream) {
   EF_ARGS_OK(M >= 0 && (M == 0 || (shape && rate && out)), "lrvb_ef_e_log_gamma");
   if (M == 0) return LRVB_OK;
-  k_e_log_gamma<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(shape, rate, M, out);
+  k_gamma_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(shape, rate, M, nullptr, out);
+  LRVB_CHECK_LAUNCH();
+  return LRVB_OK;
+}
+
+int lrvb_ef_gamma_terms(const double* shape, const double* rate, int64_t M, double* entropy, double* e_log,
+                        void* stream) {
+  EF_ARGS_OK(M >= 0 && (M == 0 || (shape && rate && (entropy || e_log))), "lrvb_ef_gamma_terms");
+  if (M == 0) return LRVB_OK;
+  k_gamma_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(shape, rate, M, entropy, e_log);
+  LRVB_CHECK_LAUNCH();
+  return LRVB_OK;
+}
+
+int lrvb_ef_dirichlet_terms(const double* alpha, int32_t d, int64_t M, double* entropy, double* e_log,
+                            void* stream) {
+  EF_ARGS_OK(d >= 1 && M >= 0 && (M == 0 || (alpha && (entropy || e_log))), "lrvb_ef_dirichlet_terms");
+  if (M == 0) return LRVB_OK;
+  k_dirichlet_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(alpha, d, M, entropy, e_log);
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -220,7 +239,7 @@ int lrvb_ef_dirichlet_entropy(const double* alpha, int32_t d, int64_t M, double*
                               void* stream) {
   EF_ARGS_OK(d >= 1 && M >= 0 && (M == 0 || (alpha && out)), "lrvb_ef_dirichlet_entropy");
   if (M == 0) return LRVB_OK;
-  k_dirichlet_entropy<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(alpha, d, M, out);
+  k_dirichlet_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(alpha, d, M, out, nullptr);
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -229,7 +248,7 @@ int lrvb_ef_e_log_dirichlet(const double* alpha, int32_t d, int64_t M, double* o
                             void* stream) {
   EF_ARGS_OK(d >= 1 && M >= 0 && (M == 0 || (alpha && out)), "lrvb_ef_e_log_dirichlet");
   if (M == 0) return LRVB_OK;
-  k_e_log_dirichlet<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(alpha, d, M, out);
+  k_dirichlet_terms<<<ew_grid(M), 256, 0, (cudaStream_t)stream>>>(alpha, d, M, nullptr, out);
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }

@@ -210,6 +210,7 @@ def test_csr_refill_follows_pattern_changes(vb):
     import scipy.sparse
     case = make_case(N=4000, K=6, G=40, Q=8, seed=91, ragged=True, empty_groups=3)
     oracle, model = make_oracle(case), make_model(vb, case)
+    model._csr_refill_min = 0                # the refill path whatever the size
     x = case["free"]
 
     def dense_from_blocks():
