@@ -268,3 +268,70 @@ def uvn_prior(prior_mean, prior_info, e_obs, var_obs):
 
 def gamma_prior(prior_shape, prior_rate, e_obs, e_log_obs):
     return (prior_shape - 1) * e_log_obs - prior_rate * e_obs
+
+
+def exponential_prior(lambda_par, e_obs):
+    """:197-198."""
+    return -1 * lambda_par * e_obs
+
+
+def dirichlet_prior(alpha, log_e_obs):
+    """:200-204 (the argument is E log of the observation, as the reference's own comment says)."""
+    xp = _xp(alpha)
+    assert tuple(alpha.shape) == tuple(log_e_obs.shape), "shape of alpha and log_e_obs do not match"
+    return xp.dot(alpha - 1, log_e_obs) if xp is np else ((alpha - 1) * log_e_obs).sum()
+
+
+def expected_ljk_prior(lkj_param, df, v):
+    """:206-211: if Sigma^-1 ~ Wishart(v, df), the expected LKJ prior (lkj_param - 1) E log |R|."""
+    e_log_r = -1 * e_log_det_wishart(df, v) - e_log_inv_wishart_diag(df, v).sum()
+    return (lkj_param - 1) * e_log_r
+
+
+# ---- numeric integration (:123-172) --------------------------------------------------------------
+def get_e_fun_normal(means, infos, gh_loc, gh_weights, fun):
+    """E fun(X), X an array of normals (means, infos), by Gauss-Hermite quadrature (:125-141); ``fun`` is any
+    elementwise callable of the caller's array library (numpy or torch)."""
+    xp = _xp(means)
+    assert tuple(means.shape) == tuple(infos.shape)
+    if xp is np:
+        loc = np.sqrt(2) * np.asarray(gh_loc) / np.sqrt(np.expand_dims(infos, means.ndim)) \
+            + np.expand_dims(means, means.ndim)
+        return np.sum(1 / np.sqrt(np.pi) * np.asarray(gh_weights) * fun(loc), axis=means.ndim)
+    import torch
+    gl = torch.as_tensor(gh_loc, dtype=means.dtype, device=means.device)
+    gw = torch.as_tensor(gh_weights, dtype=means.dtype, device=means.device)
+    loc = math.sqrt(2) * gl / torch.sqrt(infos.unsqueeze(-1)) + means.unsqueeze(-1)
+    return torch.sum(1 / math.sqrt(math.pi) * gw * fun(loc), dim=-1)
+
+
+def get_e_logitnormal(lognorm_means, lognorm_infos, gh_loc, gh_weights):
+    """:143-148."""
+    xp = _xp(lognorm_means)
+    expit = (lambda x: 1.0 / (1.0 + np.exp(-x))) if xp is np else (lambda x: xp.sigmoid(x))
+    return get_e_fun_normal(lognorm_means, lognorm_infos, gh_loc, gh_weights, expit)
+
+
+def get_e_log_logitnormal(lognorm_means, lognorm_infos, gh_loc, gh_weights):
+    """:150-172: (E log X, E log(1 - X)) for a logit-normal X.  log(expit(v)) is evaluated as
+    min(v, 0) - log1p(exp(-|v|)): the same function as the reference's guarded two-branch expression
+    (-1e16 / x <= -100 cut-offs) wherever that one is finite, and finite everywhere."""
+    xp = _xp(lognorm_means)
+    if xp is np:
+        log_v = lambda x: np.minimum(x, 0.0) - np.log1p(np.exp(-np.abs(x)))   # noqa: E731
+    else:
+        log_v = lambda x: xp.clamp(x, max=0.0) - xp.log1p(xp.exp(-xp.abs(x)))   # noqa: E731
+    e_log_v = get_e_fun_normal(lognorm_means, lognorm_infos, gh_loc, gh_weights, log_v)
+    return e_log_v, -lognorm_means + e_log_v
+
+
+def get_uvn_from_natural_parameters(e_term, e2_term):
+    """:179-182: mean and info of the normal with log p(x) = e_term x + e2_term x^2 + C."""
+    x_info = -2.0 * e2_term
+    return e_term / x_info, x_info
+
+
+def get_e_dp_prior_logitnorm_approx(alpha, lognorm_means, lognorm_infos, gh_loc, gh_weights):
+    """:213-221: expected Dirichlet-process prior with logit-normal sticks."""
+    _, e_log_1mv = get_e_log_logitnormal(lognorm_means, lognorm_infos, gh_loc, gh_weights)
+    return (alpha - 1) * e_log_1mv

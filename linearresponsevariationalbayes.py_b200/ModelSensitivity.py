@@ -119,11 +119,81 @@ class LinearResponseCovariances(object):
         x = self._opt0.detach().cpu().numpy() if is_torch(self._opt0) else self._opt0
         return self.model.moment_jacobian(x)
 
-    def get_lr_covariance_from_jacobians(self, moment_jacobian1, moment_jacobian2=None):
-        """J1 H^{-1} J2^T for (m1, D) / (m2, D) Jacobians (dense, scipy-sparse or torch)."""
+    def get_lr_covariance_factors(self, moment_jacobian1, moment_jacobian2=None):
+        """J1 H^{-1} J2^T WITHOUT forming H^{-1} J2^T (a dense (m2, D) block -- 160 GB at the target size)
+        or the (m1, m2) result: for the arrowhead H = [[A, B^T], [B, L]] with S = A - B^T L^{-1} B and
+        T = L^{-1} B,
+
+            J1 H^{-1} J2^T = W1 S^{-1} W2^T + J1l L^{-1} J2l^T,      W = Jg - Jl T   (m, Dg),
+
+        where Jg / Jl are the global / local columns of a Jacobian.  The Jacobians stay sparse (scipy
+        sparse, dense arrays or torch tensors are accepted); the only dense objects are (m, Dg).
+        Returns an ``ArrowheadCovariance`` (``diagonal()``, ``block(rows1, rows2)``, ``matvec``,
+        ``toarray()`` for small m)."""
         import torch
         if moment_jacobian2 is None:
             moment_jacobian2 = moment_jacobian1
+        model = self.model
+        local = getattr(model, "local", None)
+        if local is not None:
+            raise NotImplementedError("factored covariances of a sharded model: use get_global_covariance / "
+                                      "get_local_covariances, or hinv() on explicit right-hand sides")
+        self._ensure_point()
+        if self._sinv is None:
+            self._sinv = model.global_covariance()
+        Dg, G, D = model.Dg, model.G, model.D
+        _, B, L = model.blocks()
+        det = L[:, 0] * L[:, 2] - L[:, 1] * L[:, 1]
+        linv = torch.stack([L[:, 2] / det, -L[:, 1] / det, L[:, 0] / det], dim=1)          # (G, 3): 00, 01, 11
+        # T in the column order of the local parameters [u.mean (G) | u.info (G)]: (2G, Dg)
+        T = torch.cat([linv[:, 0:1] * B[:, 0, :] + linv[:, 1:2] * B[:, 1, :],
+                       linv[:, 1:2] * B[:, 0, :] + linv[:, 2:3] * B[:, 1, :]], dim=0)
+        linv_h = linv.cpu().numpy()
+
+        def split(j):
+            if is_torch(j):
+                j = j.detach().cpu().numpy()
+            js = scipy.sparse.csr_matrix(j) if not scipy.sparse.issparse(j) else j.tocsr()
+            if js.shape[1] != D:
+                raise ValueError("Wrong number of columns for a moment Jacobian.  Expected {}, got {}".format(
+                    D, js.shape[1]))
+            jg = torch.from_numpy(np.ascontiguousarray(js[:, :Dg].toarray())).to(model.device)
+            jl = js[:, Dg:].tocsr()
+            jl_t = torch.sparse_csr_tensor(torch.from_numpy(jl.indptr.astype(np.int64)),
+                                           torch.from_numpy(jl.indices.astype(np.int64)),
+                                           torch.from_numpy(jl.data.astype(np.float64)),
+                                           size=jl.shape).to(model.device)
+            w = jg - (torch.sparse.mm(jl_t, T) if jl.nnz else torch.zeros_like(jg))
+            return w, jl
+
+        w1, jl1 = split(moment_jacobian1)
+        same = moment_jacobian2 is moment_jacobian1
+        w2, jl2 = (w1, jl1) if same else split(moment_jacobian2)
+        # sparse local term J1l L^-1 J2l^T on the host (L^-1 is 2x2 block diagonal)
+        gi = np.arange(G)
+        Ls = scipy.sparse.csr_matrix(
+            (np.concatenate([linv_h[:, 0], linv_h[:, 1], linv_h[:, 1], linv_h[:, 2]]),
+             (np.concatenate([gi, gi, gi + G, gi + G]), np.concatenate([gi, gi + G, gi, gi + G]))), (2 * G, 2 * G))
+        local_term = (jl1 @ Ls @ jl2.T).tocsr()
+        return ArrowheadCovariance(w1, self._sinv, w2, local_term, symmetric=same)
+
+    MAX_DENSE = 1 << 26
+
+    def get_lr_covariance_from_jacobians(self, moment_jacobian1, moment_jacobian2=None):
+        """J1 H^{-1} J2^T for (m1, D) / (m2, D) Jacobians (dense, scipy-sparse or torch) as a dense
+        matrix; beyond 2^26 entries use ``get_lr_covariance_factors``."""
+        import torch
+        if moment_jacobian2 is None:
+            moment_jacobian2 = moment_jacobian1
+        m1, m2 = moment_jacobian1.shape[0], moment_jacobian2.shape[0]
+        if m1 * m2 > self.MAX_DENSE:
+            raise ValueError("the covariance would have {} x {} entries; use get_lr_covariance_factors "
+                             "(diagonal / blocks / products without the dense matrix)".format(m1, m2))
+        if self.method == "schur" and getattr(self.model, "local", None) is None:
+            cov = self.get_lr_covariance_factors(moment_jacobian1, moment_jacobian2).toarray()
+            cov = torch.from_numpy(cov) if not is_torch(cov) else cov
+            return cov.to(self.model.device) if (is_torch(moment_jacobian1) or is_torch(self._opt0)) \
+                else cov.cpu().numpy()
 
         def dense(j):
             if scipy.sparse.issparse(j):
@@ -141,6 +211,46 @@ class LinearResponseCovariances(object):
         """LRVB covariance of the model's default moments [E mu, E tau, E beta, E u]."""
         j = self.get_moment_jacobian(calculate_moments)
         return self.get_lr_covariance_from_jacobians(j, j)
+
+
+class ArrowheadCovariance(object):
+    """C = W1 Sinv W2^T + R with W (m, Dg) dense on the device, Sinv (Dg, Dg), R (m1, m2) scipy sparse:
+    the linear-response covariance J1 H^{-1} J2^T of an arrowhead Hessian in factored form."""
+
+    def __init__(self, w1, sinv, w2, local_term, symmetric=False):
+        self.w1, self.sinv, self.w2, self.local_term, self.symmetric = w1, sinv, w2, local_term, symmetric
+        self.shape = (w1.shape[0], w2.shape[0])
+
+    def diagonal(self):
+        """diag(C) (m1 == m2) as a numpy array."""
+        import torch
+        assert self.shape[0] == self.shape[1]
+        d = torch.sum(torch.matmul(self.w1, self.sinv) * self.w2, dim=1)
+        return d.cpu().numpy() + self.local_term.diagonal()
+
+    def block(self, rows1, rows2):
+        """Dense C[rows1][:, rows2] (index arrays or slices) as numpy."""
+        import torch
+        r1 = np.arange(self.shape[0])[rows1]
+        r2 = np.arange(self.shape[1])[rows2]
+        t1 = torch.from_numpy(r1).to(self.w1.device)
+        t2 = torch.from_numpy(r2).to(self.w1.device)
+        low = torch.matmul(torch.matmul(self.w1.index_select(0, t1), self.sinv), self.w2.index_select(0, t2).t())
+        return low.cpu().numpy() + self.local_term[r1][:, r2].toarray()
+
+    def matvec(self, v):
+        """C v for v (m2,) numpy -> numpy."""
+        import torch
+        vt = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(self.w1.device)
+        low = torch.matmul(self.w1, torch.matmul(self.sinv, torch.matmul(self.w2.t(), vt)))
+        return low.cpu().numpy() + self.local_term @ np.asarray(v, dtype=np.float64)
+
+    def toarray(self):
+        if self.shape[0] * self.shape[1] > LinearResponseCovariances.MAX_DENSE:
+            raise ValueError("covariance of {} x {} entries: use diagonal() / block() / matvec()".format(*self.shape))
+        import torch
+        low = torch.matmul(torch.matmul(self.w1, self.sinv), self.w2.t())
+        return low.cpu().numpy() + self.local_term.toarray()
 
 
 class WeightSensitivityLinearApproximation(object):

@@ -113,6 +113,15 @@ class Objective(object):
         self.logger = Logger()
         self._par_key, self._par_coords = None, None
 
+    def invalidate(self):
+        """Forget the cached evaluation.  The "already evaluated at this point?" check compares numpy input
+        by value, but a torch tensor by identity (storage address, shape, strides and torch's in-place
+        version counter, ``_tensors.PointKey``): a write that bypasses the version counter -- a raw-pointer
+        write by other CUDA code, ``x.data`` updates, a CPU tensor changed through its shared ``.numpy()``
+        view -- is invisible to it.  Call this (or pass a fresh tensor) after such a write."""
+        self.model.invalidate()
+        self._par_key, self._par_coords = None, None
+
     # ---- helpers ----
     def _set_par(self, x, coords):
         # ``par`` follows the evaluation point (:142-150).  The model keeps one key object per

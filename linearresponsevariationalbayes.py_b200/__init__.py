@@ -10,10 +10,13 @@ from .Parameters import (ScalarParam, VectorParam, ArrayParam, constrain, uncons
                          get_free_offset, get_vector_offset, free_to_vector_jac_offset,
                          free_to_vector_hess_offset)
 from .ParameterDictionary import ModelParamsDict  # noqa: F401
-from .NormalParams import UVNParam, UVNParamVector, UVNParamArray  # noqa: F401
-from .GammaParams import GammaParam  # noqa: F401
 from .MatrixParameters import (PosDefMatrixParam, PosDefMatrixParamVector,  # noqa: F401
                                PosDefMatrixParamArray)
+from .NormalParams import (UVNParam, UVNParamVector, UVNParamArray, MVNParam,  # noqa: F401
+                           UVNMomentParamArray, MVNArray)
+from .GammaParams import GammaParam  # noqa: F401
+from .DirichletParams import DirichletParamArray  # noqa: F401
+from .WishartParams import WishartParam  # noqa: F401
 from .SimplexParams import SimplexParam  # noqa: F401
 from . import MatrixParameters  # noqa: F401
 from . import SimplexParams  # noqa: F401
@@ -29,7 +32,7 @@ from .SparseObjectives import (Objective, Logger, Timer, make_index_param,  # no
                                unpack_csr_matrix, json_pack_csr_matrix,
                                json_unpack_csr_matrix, safe_matmul)
 from .ConjugateGradient import ConjugateGradientSolver  # noqa: F401
-from .ModelSensitivity import (LinearResponseCovariances,  # noqa: F401
+from .ModelSensitivity import (LinearResponseCovariances, ArrowheadCovariance,  # noqa: F401
                                WeightSensitivityLinearApproximation)
 from .GLMM import LogisticGLMM, GLMMPrior, DeviceCSR  # noqa: F401
 

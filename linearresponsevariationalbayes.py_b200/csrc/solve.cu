@@ -1098,8 +1098,10 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
   LRVB_REQUIRE(S_dev && info_host, "lrvb_spd_inverse: NULL argument");
   LRVB_REQUIRE(n >= 1 && n <= 4 + 2 * kMaxK, "lrvb_spd_inverse: n = %d out of range", n);
   cudaStream_t st = (cudaStream_t)stream;
-  static int* dinfo = nullptr;   // one device word per process (no malloc / free per call)
-  if (!dinfo) LRVB_CUDA(cudaMalloc((void**)&dinfo, sizeof(int)));
+  // the status word: stream-ordered allocation on the caller's stream and current device (a process-wide
+  // static word would be shared by every device, stream and thread)
+  int* dinfo = nullptr;
+  LRVB_CUDA(cudaMallocAsync((void**)&dinfo, sizeof(int), st));
   size_t smem = sizeof(double) * (2 * (size_t)n + (size_t)n * n);
   int use_smem = 1;
   if (smem > 200 * 1024) {
@@ -1128,6 +1130,7 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(info_host, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(dinfo, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("lrvb_spd_inverse failed: %s", cudaGetErrorString(e));

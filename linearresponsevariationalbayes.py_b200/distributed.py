@@ -252,23 +252,27 @@ class ShardedLogisticGLMM(object):
         return v_full.index_select(-1, self._map).contiguous()
 
     def from_local(self, v_local):
-        """Local-layout vector (Dg + 2 G_local,) -> full vector (D,), identical on every rank
-        (globals taken as they are -- they are replicated -- locals all-gathered)."""
+        """Local-layout vector(s) (..., Dg + 2 G_local) -> full vector(s) (..., D), identical on every
+        rank (globals taken as they are -- they are replicated -- locals all-gathered): ONE all_gather
+        whatever the number of vectors."""
         import torch
         import torch.distributed as dist
         Dg, Gl = self.Dg, self.g1 - self.g0
+        lead = tuple(v_local.shape[:-1])
+        v2 = v_local.reshape(-1, Dg + 2 * Gl)
+        n = v2.shape[0]
         gmax = max(b - a for a, b in self.group_ranges)
-        pad = torch.zeros(2, gmax, dtype=v_local.dtype, device=v_local.device)
-        pad[0, :Gl] = v_local[Dg:Dg + Gl]
-        pad[1, :Gl] = v_local[Dg + Gl:]
+        pad = torch.zeros(n, 2, gmax, dtype=v_local.dtype, device=v_local.device)
+        pad[:, 0, :Gl] = v2[:, Dg:Dg + Gl]
+        pad[:, 1, :Gl] = v2[:, Dg + Gl:]
         gathered = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(gathered, pad, group=self.pg)
-        out = torch.empty(self.D, dtype=v_local.dtype, device=v_local.device)
-        out[:Dg] = v_local[:Dg]
+        out = torch.empty(n, self.D, dtype=v_local.dtype, device=v_local.device)
+        out[:, :Dg] = v2[:, :Dg]
         for (a, b), t in zip(self.group_ranges, gathered):
-            out[Dg + a:Dg + b] = t[0, :b - a]
-            out[Dg + self.G + a:Dg + self.G + b] = t[1, :b - a]
-        return out
+            out[:, Dg + a:Dg + b] = t[:, 0, :b - a]
+            out[:, Dg + self.G + a:Dg + self.G + b] = t[:, 1, :b - a]
+        return out.reshape(lead + (self.D,))
 
     def _dev(self, x):
         import torch
@@ -280,6 +284,11 @@ class ShardedLogisticGLMM(object):
     def _same_point(self, x, coords):
         c = self._cache
         return c["x"] is not None and c["coords"] == coords and c["x"].matches(x)
+
+    def invalidate(self):
+        self._cache = dict(x=None, order=-1, coords=None)
+        self._sinv = None
+        self.local.invalidate() if hasattr(self.local, "invalidate") else None
 
     # ---- the model interface used by Objective / ConjugateGradientSolver / LRVB --------------
     def evaluate(self, x, order, coords="free", force=False):
@@ -463,7 +472,7 @@ class ShardedLogisticGLMM(object):
         rhs = self.local.solve_reduce_rhs(bl, include_bg=(self.rank == 0))
         self._allreduce(rhs)
         xl = self.local.solve_finish(Sinv, rhs, bl)
-        out = torch.stack([self.from_local(row) for row in xl])
+        out = self.from_local(xl)           # one all_gather for all right-hand sides
         shape = tuple(b_full.shape) if hasattr(b_full, "shape") else (self.D,)
         return out.reshape(shape)
 

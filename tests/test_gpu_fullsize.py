@@ -97,6 +97,13 @@ def test_lrvb_and_cg_at_the_optimum(vb, name, kw):
     refm = J @ Hinv @ J.T
     assert_close(lr.get_lr_covariance(), refm, rtol=1e-8, scale=np.abs(refm).max() * 1e-3,
                  what="moment covariance")
+    fac = lr.get_lr_covariance_factors(J)
+    assert_close(fac.diagonal(), np.diag(refm), rtol=1e-8, scale=np.abs(refm).max() * 1e-3, what="factored diagonal")
+    rows = np.array([0, 1, 2 + model.K // 2, refm.shape[0] - 1])
+    assert_close(fac.block(rows, slice(None)), refm[rows], rtol=1e-8, scale=np.abs(refm).max() * 1e-3,
+                 what="factored block")
+    vv = np.random.default_rng(8).standard_normal(refm.shape[0])
+    assert_close(fac.matvec(vv), refm @ vv, rtol=1e-8, scale=np.abs(refm @ vv).max() * 1e-3, what="factored matvec")
     b = np.random.default_rng(6).standard_normal(D)
     xe = Hinv @ b
     solver = vb.ConjugateGradientSolver(obj.fun_free_hvp, xo)
@@ -111,3 +118,29 @@ def test_lrvb_and_cg_at_the_optimum(vb, name, kw):
     cov_cg = lrc.get_global_covariance()
     assert_close(cov_cg, Hinv[:Dg, :Dg], rtol=1e-8, scale=np.abs(Hinv[:Dg, :Dg]).max() * 1e-3,
                  what="global covariance (CG)")
+
+
+@pytest.mark.timeout(900)
+def test_moment_covariance_at_scale(vb):
+    """The moment covariance of a C2-sized model (m = 2 + K + G = 10,022 moments, D = 20,044): never a dense
+    (m, D) right-hand side block nor the (m, m) result -- diagonal and rows from the factored form against
+    direct arrowhead solves of single Jacobian rows."""
+    case = make_case(N=400_000, K=20, G=10_000, Q=8, seed=2100)
+    model = make_model(vb, case)
+    obj = vb.Objective(model.glmm_par, model)
+    xo, res = vb.OptimizationUtils.minimize_objective_newton(obj, case["free"], maxiter=60, gtol=1e-7)
+    assert res.success, res.message
+    lr = vb.LinearResponseCovariances(obj, xo)
+    J = model.moment_jacobian(xo)
+    with pytest.raises(ValueError):
+        lr.get_lr_covariance_from_jacobians(J, J)          # 10,022^2 entries: refused as a dense matrix
+    fac = lr.get_lr_covariance_factors(J)
+    diag = fac.diagonal()
+    rows = np.array([0, 1, 5, 22, 23, 5000, J.shape[0] - 1])
+    blk = fac.block(rows, slice(None))
+    for k, r in enumerate(rows):
+        hr = lr.hinv(J[r].toarray().reshape(-1)).cpu().numpy()
+        ref_row = J @ hr
+        assert_close(blk[k], ref_row, rtol=1e-8, scale=np.abs(ref_row).max() * 1e-3, what="row %d" % r)
+        assert abs(diag[r] - ref_row[r]) <= 1e-8 * abs(ref_row[r]) + 1e-14
+    assert (diag > 0).all()

@@ -230,3 +230,31 @@ def test_point_key_identity_semantics():
     t.add_(1.0)
     assert not kt.matches(t)                             # in-place update bumps the version
     assert not PointKey(x).matches(t)
+
+
+def test_ef_numeric_integration_helpers_host():
+    """ExponentialFamilies.py:123-221 (Gauss-Hermite expectations of functions of normals, natural-parameter
+    update, small priors): pure host arithmetic, checked against direct quadrature / closed forms as
+    test_exponential_families.py:122-172 does."""
+    import scipy.integrate
+    import scipy.stats
+    from lrvb_b200 import ExponentialFamilies as ef
+    gx, gw = np.polynomial.hermite.hermgauss(40)
+    means, infos = np.array([0.3, -1.2, 2.0]), np.array([2.0, 0.7, 5.0])
+    got = ef.get_e_logitnormal(means, infos, gx, gw)
+    el, el1 = ef.get_e_log_logitnormal(means, infos, gx, gw)
+    for k in range(3):
+        pdf = scipy.stats.norm(means[k], 1 / np.sqrt(infos[k])).pdf
+        ref = scipy.integrate.quad(lambda x: pdf(x) / (1 + np.exp(-x)), -30, 30)[0]
+        assert abs(got[k] - ref) < 1e-9
+        ref_l = scipy.integrate.quad(lambda x: pdf(x) * -np.log1p(np.exp(-x)), -30, 30)[0]
+        assert abs(el[k] - ref_l) < 1e-8
+        assert abs(el1[k] - (ref_l - means[k])) < 1e-8
+    sq = ef.get_e_fun_normal(means, infos, gx, gw, lambda x: x ** 2)
+    np.testing.assert_allclose(sq, means ** 2 + 1 / infos, rtol=1e-12)
+    m, i = ef.get_uvn_from_natural_parameters(1.5, -2.0)
+    assert (m, i) == (1.5 / 4.0, 4.0)
+    assert ef.exponential_prior(2.0, 3.0) == -6.0
+    assert abs(ef.dirichlet_prior(np.array([2.0, 3.0]), np.array([-1.0, -0.5])) - (-1.0 - 1.0)) < 1e-15
+    dp = ef.get_e_dp_prior_logitnorm_approx(3.0, means, infos, gx, gw)
+    np.testing.assert_allclose(dp, 2.0 * el1)
