@@ -534,9 +534,9 @@ def e2e_measure(ctx, res, steps, warmup):
         if sharded:
             # sharded: every rank brings ITS part of the distributed Hessian / gradient to its host
             model.evaluate(xh, 2)
-            H = model.local.hessian_scipy()
-            gr = model.grad_local_layout().cpu().numpy()
-            kl = float(model.kl_tensor().item())
+            H = model.local.hessian_scipy()      # one synchronisation: values + gradient + KL
+            gr = model.local.grad_host()
+            kl = model.local.kl_host()
             return H, gr, kl
         H = obj.fun_free_hessian(xh)     # scipy CSR on the host (order-2 evaluation, cached)
         gr = obj.fun_free_grad(xh)       # numpy (D,)
@@ -545,6 +545,7 @@ def e2e_measure(ctx, res, steps, warmup):
     for i in range(warmup):
         step(i)
     gc.collect()
+    gc.disable()                            # as in the device loop: no collector pauses inside the timed steps
     torch.cuda.synchronize()
     if sharded:
         dist.barrier()
@@ -553,6 +554,7 @@ def e2e_measure(ctx, res, steps, warmup):
         H, gr, kl = step(warmup + i)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    gc.enable()
     dt = float(_gather_floats(ctx, [dt])[:, 0].max()) if sharded else dt
     nnz = int(H.nnz)
     return {"value": res["n_total"] / (dt / steps), "unit": UNIT, "ms_per_step": 1e3 * dt / steps,

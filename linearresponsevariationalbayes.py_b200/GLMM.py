@@ -275,6 +275,9 @@ class LogisticGLMM(object):
         self._x_event = None
         self._g_pin = None
         self._cache = dict(x=None, order=-1, coords=None)
+        self._eval_id = 0                 # bumped by every evaluation: keys the host copies below
+        self._host = dict(id=-1)          # KL / gradient of evaluation `id` already on the host
+        self._kl_pin = None
         self._csr_pattern = None          # _Pattern of the last full export (shared by refilled matrices)
         self._csr_pending = None          # refill whose pattern check has not been read yet
         self._csr_flag_pin, self._csr_slot = None, 0
@@ -368,27 +371,54 @@ class LogisticGLMM(object):
         nat.check(self._lib.lrvb_glmm_eval(self._h, nat.ptr(xd), int(order), None, None,
                                            nat.stream_ptr()))
         self._cache = dict(x=PointKey(x), order=int(order), coords=coords)
+        self._eval_id += 1
 
     def invalidate(self):
         self._cache = dict(x=None, order=-1, coords=None)
+        self._eval_id += 1
 
     # raw device results of the last evaluation
     def kl_tensor(self):
         return self._out_global[0]
+
+    def _enqueue_host_copies(self):
+        """Asynchronous copies of KL and the gradient of the current evaluation into pinned host memory
+        on the current stream (no synchronisation): whoever synchronises next -- typically the download of
+        the Hessian values -- makes them readable, so ``fun_free_hessian`` + ``fun_free_grad`` + ``fun_free``
+        at one point cost ONE stream synchronisation instead of three."""
+        torch = nat.require_cuda()
+        if self._g_pin is None:
+            self._g_pin = torch.empty(self.D, dtype=torch.float64).pin_memory()
+            self._kl_pin = torch.empty(1, dtype=torch.float64).pin_memory()
+        self._kl_pin.copy_(self._out_global[0:1], non_blocking=True)
+        if self._cache["order"] >= 1:
+            self._g_pin[:self.Dg].copy_(self._out_global[1:1 + self.Dg], non_blocking=True)
+            self._g_pin[self.Dg:].copy_(self._grad_local, non_blocking=True)
+        self._host = dict(id=self._eval_id, order=self._cache["order"], pending=True)
+
+    def kl_host(self):
+        """KL of the last evaluation as a Python float."""
+        torch = nat.require_cuda()
+        if self._host.get("id") != self._eval_id:
+            self._enqueue_host_copies()
+        if self._host.get("pending"):
+            torch.cuda.current_stream().synchronize()
+            self._host["pending"] = False
+        return float(self._kl_pin[0])
 
     def grad_tensor(self):
         import torch
         return torch.cat([self._out_global[1:1 + self.Dg], self._grad_local])
 
     def grad_host(self):
-        """Gradient of the last evaluation as a fresh numpy array: the global and the local part go
-        to one pinned buffer by two asynchronous copies (one synchronisation, no device concat)."""
+        """Gradient of the last evaluation as a fresh numpy array (pinned staging buffer, at most one
+        synchronisation; none if an earlier host read of this evaluation already synchronised)."""
         torch = nat.require_cuda()
-        if self._g_pin is None:
-            self._g_pin = torch.empty(self.D, dtype=torch.float64).pin_memory()
-        self._g_pin[:self.Dg].copy_(self._out_global[1:1 + self.Dg], non_blocking=True)
-        self._g_pin[self.Dg:].copy_(self._grad_local, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if self._host.get("id") != self._eval_id or self._host.get("order", -1) < 1:
+            self._enqueue_host_copies()
+        if self._host.get("pending"):
+            torch.cuda.current_stream().synchronize()
+            self._host["pending"] = False
         return self._g_pin.numpy().copy()
 
     def blocks(self):
@@ -485,7 +515,11 @@ class LogisticGLMM(object):
     def hessian_scipy(self):
         """Host ``scipy.sparse.csr_matrix`` of the cached Hessian (what ``Objective.fun_free_hessian``
         returns for numpy input, SparseObjectives.py:156-158); re-uses the cached pattern."""
-        return self.hessian_csr().to_scipy()
+        csr = self.hessian_csr()
+        self._enqueue_host_copies()           # KL and gradient ride on the same synchronisation
+        m = csr.to_scipy()
+        self._host["pending"] = False
+        return m
 
     def hvp_cached(self, v_dev, out=None, include_A=True):
         """H v with the cached Hessian; v_dev a CUDA fp64 tensor (D,)."""

@@ -140,8 +140,11 @@ class Objective(object):
     def _value(self, x, coords):
         self.model.evaluate(x, 0, coords)
         self._set_par(x, coords)
-        v = self.model.kl_tensor()
-        return v.clone() if is_torch(x) else float(v.item())
+        if is_torch(x):
+            return self.model.kl_tensor().clone()
+        if hasattr(self.model, "kl_host"):
+            return self.model.kl_host()
+        return float(self.model.kl_tensor().item())
 
     def _grad(self, x, coords):
         self.model.evaluate(x, 1, coords)

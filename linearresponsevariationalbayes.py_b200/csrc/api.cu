@@ -177,6 +177,23 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     h->of_smem = obs_fused_smem(K, Q, h->of_warps);
     int64_t nrec = tw;
     {
+      // one-slot rings when they buy at least three more warps per SM (K >= ~36)
+      const char* e1 = getenv("LRVB_OBS_ONESLOT");
+      const int w1 = obs_fused_warps(K, 1);
+      if (e1 ? (e1[0] != '0') : (w1 >= h->of_warps + 3)) {
+        int64_t g1 = (nst + w1 - 1) / w1;
+        if (g1 > kNumSMs) g1 = kNumSMs;
+        if (g1 < 1) g1 = 1;
+        const int64_t tw1 = g1 * w1;
+        h->of1_grid = (int)g1;
+        h->of1_warps = w1;
+        h->of1_rows_per_warp = ((nst + tw1 - 1) / tw1) * kOfRows;
+        h->of1_smem = obs_fused_smem(K, Q, w1, 1);
+        if (tw1 > nrec) nrec = tw1;
+        if (h->obs_grid < h->of1_grid) h->obs_grid = h->of1_grid;
+      }
+    }
+    {
       // order 2 in one pass (fused.cuh): teams of NQ quadrature warps + P DMMA warps, one CTA per SM; every
       // Q warp owns a contiguous multiple-of-32 range of rows
       const char* fe = getenv("LRVB_FUSED");
@@ -198,7 +215,7 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
       if (tt > nrec) nrec = tt;
     }
     CREATE_TRY(dev_alloc(&h->bval, (size_t)nrec * 2 * (5 + 4 * (size_t)K)));
-    configure_obs_fused(h->of_smem);
+    configure_obs_fused(h->of_smem > h->of1_smem ? h->of_smem : h->of1_smem);
     if (h->obs_grid < h->of_grid) h->obs_grid = h->of_grid;
     if (h->obs_grid < h->fu_grid) h->obs_grid = h->fu_grid;     // klpart / gradpart are sized by obs_grid
   }

@@ -236,6 +236,10 @@ struct lrvb_glmm {
   size_t of_smem = 0;
   int64_t of_rows_per_warp = 0;
   double* bval = nullptr;     // (of_grid * of_warps, 2, 5 + 4K) head / tail pieces of straddling groups
+  // one-slot variant of the fused observation pass for the evaluation (larger K: more warps per SM)
+  int of1_grid = 0, of1_warps = 0;
+  size_t of1_smem = 0;
+  int64_t of1_rows_per_warp = 0;
   // order-2 evaluation in one pass (team.cuh): teams of warps do quadrature, group sums and Gram per stage
   int fused2 = 0, fu_grid = 0, fu_teams = 0, fu_warps = 0;
   int64_t fu_rows_per_team = 0;

@@ -724,9 +724,16 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
       const int nch = (K + 1 + 31) / 32;
 #define LRVB_OF(O, C)                                                                          \
-  LRVB_CUDA(launch_pdl(k_obs_fused<O, C>, dim3(h->of_grid), dim3(32 * h->of_warps), h->of_smem, st, \
-      h->X, h->y, h->g, h->w, h->vec, h->gh, h->gptr, h->W, h->ldw, h->klpart, h->gradpart,    \
-      h->gsc, h->BR, h->bval, N, K, G, Q, h->of_rows_per_warp))
+  do {                                                                                         \
+    if (h->of1_warps > 0)                                                                      \
+      LRVB_CUDA(launch_pdl(k_obs_fused<O, C, 1>, dim3(h->of1_grid), dim3(32 * h->of1_warps), h->of1_smem, st, \
+          h->X, h->y, h->g, h->w, h->vec, h->gh, h->gptr, h->W, h->ldw, h->klpart, h->gradpart,    \
+          h->gsc, h->BR, h->bval, N, K, G, Q, h->of1_rows_per_warp));                          \
+    else                                                                                       \
+      LRVB_CUDA(launch_pdl(k_obs_fused<O, C>, dim3(h->of_grid), dim3(32 * h->of_warps), h->of_smem, st, \
+          h->X, h->y, h->g, h->w, h->vec, h->gh, h->gptr, h->W, h->ldw, h->klpart, h->gradpart,    \
+          h->gsc, h->BR, h->bval, N, K, G, Q, h->of_rows_per_warp));                           \
+  } while (0)
       if (nch == 1) {
         if (order == 0) LRVB_OF(0, 1);
         else if (order == 1) LRVB_OF(1, 1);
@@ -739,9 +746,12 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
 #undef LRVB_OF
       LRVB_CHECK_LAUNCH();
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[1], st));
-      n_obs_cta = h->of_grid;
+      n_obs_cta = h->of1_warps > 0 ? h->of1_grid : h->of_grid;
     }
-    if (N > 0) fix_rpw = h->of_rows_per_warp > 0 ? h->of_rows_per_warp : 32;
+    if (N > 0) {
+      const int64_t rpw = h->of1_warps > 0 ? h->of1_rows_per_warp : h->of_rows_per_warp;
+      fix_rpw = rpw > 0 ? rpw : 32;
+    }
   } else {
   if (N > 0) {
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
@@ -861,6 +871,12 @@ void configure_obs_fused(size_t smem) {
   cudaFuncSetAttribute(k_obs_fused<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
   cudaFuncSetAttribute(k_obs_fused<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
   cudaFuncSetAttribute(k_obs_fused<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+  cudaFuncSetAttribute(k_obs_fused<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
   cudaGetLastError();
 }
 void configure_kernels(size_t obs_smem, size_t gram_smem) {

@@ -39,17 +39,22 @@ constexpr int kOfMaxK = 62;      // K + 1 columns in at most two 32-lane chunks
 // doubles per stage: X rows | y | w | g (int32, 16 doubles)
 __host__ __device__ inline int obs_fused_stage_elems(int K) { return kOfRows * K + 2 * kOfRows + kOfRows / 2; }
 // per-warp shared memory (doubles): ring + weights of the current stage (32 rows x 6: l_m, l_v, a, b, c, -)
-__host__ __device__ inline int obs_fused_warp_elems(int K) {
-  return kOfStages * obs_fused_stage_elems(K) + 6 * kOfRows;
+__host__ __device__ inline int obs_fused_warp_elems(int K, int slots = kOfStages) {
+  return slots * obs_fused_stage_elems(K) + 6 * kOfRows;
 }
-inline int obs_fused_warps(int K) {
-  int w = (int)((200 * 1024) / (sizeof(double) * obs_fused_warp_elems(K)));
-  if (w > kOfMaxWarps) w = kOfMaxWarps;
+// One-slot variant (SLOTS = 1): from K ~ 36 on a two-slot ring leaves room for fewer than 10 warps per SM
+// (7 at K = 50) and the pass is latency-bound; with ONE slot per warp -- the next stage is requested when
+// the current one is finished, the other warps cover the copy -- up to 14 warps fit.
+constexpr int kOfMaxWarps1 = 14;
+inline int obs_fused_warps(int K, int slots = kOfStages) {
+  int w = (int)((200 * 1024) / (sizeof(double) * obs_fused_warp_elems(K, slots)));
+  const int cap = slots == 1 ? kOfMaxWarps1 : kOfMaxWarps;
+  if (w > cap) w = cap;
   return w < 1 ? 1 : w;
 }
-inline size_t obs_fused_smem(int K, int Q, int warps) {
-  return sizeof(double) * ((size_t)warps * obs_fused_warp_elems(K) + 2 * K + 2 * Q + 2 * (size_t)warps * K +
-                           warps) + sizeof(unsigned long long) * warps * kOfStages;
+inline size_t obs_fused_smem(int K, int Q, int warps, int slots = kOfStages) {
+  return sizeof(double) * ((size_t)warps * obs_fused_warp_elems(K, slots) + 2 * K + 2 * Q + 2 * (size_t)warps * K +
+                           warps) + sizeof(unsigned long long) * warps * slots;
 }
 
 struct GHSumsF {
@@ -251,8 +256,8 @@ __device__ __forceinline__ void gh_all_nodes_f(double zm, double zs, const doubl
 }
 
 // bval: (total_warps, 2, 5 + 4K) head / tail partials of groups that straddle a range boundary.
-template <int ORDER, int NCH>
-__global__ void __launch_bounds__(32 * kOfMaxWarps, 1)
+template <int ORDER, int NCH, int SLOTS = kOfStages>
+__global__ void __launch_bounds__(32 * (SLOTS == 1 ? kOfMaxWarps1 : kOfMaxWarps), 1)
 k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
             const double* __restrict__ w, const double* __restrict__ vec, const double* __restrict__ gh,
             const int32_t* __restrict__ gptr, double* __restrict__ W, int64_t ldw,
@@ -263,16 +268,16 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int stage_elems = obs_fused_stage_elems(K);
-  const int warp_elems = obs_fused_warp_elems(K);
+  const int warp_elems = obs_fused_warp_elems(K, SLOTS);
   double* ring = sm + (size_t)warp * warp_elems;
-  double* wsm = ring + kOfStages * stage_elems;            // 32 x 6 weights of the current stage
+  double* wsm = ring + SLOTS * stage_elems;            // 32 x 6 weights of the current stage
   double* bm = sm + (size_t)nwarp * warp_elems;            // K   E[beta]
   double* bv = bm + K;                                     // K   Var[beta]
   double* ghc = bv + K;                                    // Q   sqrt(2) x_q
   double* ghw = ghc + Q;                                   // Q   w_q / sqrt(pi)
   double* gred = ghw + Q;                                  // nwarp x 2K gradient partials
   double* kred = gred + (size_t)nwarp * 2 * K;             // nwarp
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(kred + nwarp) + warp * kOfStages;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(kred + nwarp) + warp * SLOTS;
   const unsigned ring_u = smem_u32(ring), bars_u = smem_u32(bars);
 
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -285,7 +290,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
   }
   if (lane == 0) {
 #pragma unroll
-    for (int p = 0; p < kOfStages; ++p) mbar_init(bars_u + 8 * p, 1);
+    for (int p = 0; p < SLOTS; ++p) mbar_init(bars_u + 8 * p, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -385,7 +390,7 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
   };
 
 #pragma unroll
-  for (int p = 0; p < kOfStages; ++p) issue(p, p);
+  for (int p = 0; p < SLOTS; ++p) issue(p, p);
 
   int slot = 0;
   unsigned phase = 0;
@@ -514,8 +519,8 @@ k_obs_fused(const double* __restrict__ X, const double* __restrict__ y, const in
       }
     }
     __syncwarp();   // every lane is done with this slot (and with wsm) before the refill
-    issue(st + kOfStages, slot);
-    if (++slot == kOfStages) { slot = 0; phase ^= 1; }
+    issue(st + SLOTS, slot);
+    if (++slot == SLOTS) { slot = 0; phase ^= 1; }
   }
   if (ORDER >= 1) flush();
 

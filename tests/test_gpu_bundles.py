@@ -5,6 +5,7 @@ test_variational_bayes.py:74-106 and checked against closed forms / scipy.stats 
 tests do (test_exponential_families.py:25-31, 40-58)."""
 import numpy as np
 import pytest
+import scipy.special
 import scipy.stats
 
 pytestmark = pytest.mark.gpu
@@ -73,7 +74,6 @@ def test_dirichlet_param_array(vb):
         ref = scipy.stats.dirichlet(alpha[:, j])
         assert abs(np.asarray(par.entropy())[j] - ref.entropy()) < 1e-10
         np.testing.assert_allclose(np.asarray(par.e())[:, j], ref.mean(), rtol=1e-12)
-    import scipy.special
     np.testing.assert_allclose(np.asarray(par.e_log()),
                                scipy.special.digamma(alpha) - scipy.special.digamma(alpha.sum(0))[None, :], rtol=1e-11)
 
@@ -88,7 +88,6 @@ def test_wishart_param(vb):
     assert abs(float(par.entropy()) - ref.entropy()) < 1e-9
     np.testing.assert_allclose(par.e(), 4.3 * v)
     np.testing.assert_allclose(par.e_inv(), 4.3 * np.linalg.inv(v), rtol=1e-12)
-    import scipy.special
     eld = sum(scipy.special.digamma(0.5 * (4.3 - j)) for j in range(3)) + 3 * np.log(2) + np.linalg.slogdet(v)[1]
     assert abs(float(par.e_log_det()) - eld) < 1e-10
     assert np.isfinite(float(par.e_log_lkj_inv_prior(2.0)))
