@@ -196,12 +196,18 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
   }
   pdl_sync();
   if (run_if && *run_if == 0) return;
-  if (bid < nA) {
-    csr_A_rows_body<FILL>(bid, A, Dg, cntA, indptr, indices, data, mask, mismatch);
-  } else if (bid < nA + nB) {
-    csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
-  } else {
-    csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
+  // a conditional export is launched with a capped grid (its usual fate is the early return above): the
+  // CTAs then walk the block-uniform roles with a grid stride
+  const int total = nA + nB + (int)((2 * (int64_t)G + 7) / 8);
+  for (int vb = bid; vb < total; vb += gridDim.x) {
+    if (vb < nA) {
+      csr_A_rows_body<FILL>(vb, A, Dg, cntA, indptr, indices, data, mask, mismatch);
+    } else if (vb < nA + nB) {
+      csr_B_cols_body<FILL>(vb - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
+      __syncthreads();      // the staging tile is reused by the next role of this CTA
+    } else {
+      csr_local_rows_body<FILL>(vb - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
+    }
   }
 }
 
@@ -437,7 +443,9 @@ static int csr_full_export(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_d
 
   const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
   // ---- counts: rows of A, columns of B (per chunk) and local rows in one launch ----
-  LRVB_CUDA(launch_pdl(k_csr_pass<0>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G,
+  int pass_grid = nA + nB + nL;
+  if (run_if && pass_grid > 4 * kNumSMs) pass_grid = 4 * kNumSMs;
+  LRVB_CUDA(launch_pdl(k_csr_pass<0>, dim3(pass_grid), dim3(256), smem, st, h->A, h->B, h->L, Dg, G,
                        CG, nA, nB, cntA, chunkcnt, nullptr, nullptr, h->rowcnt, nullptr, nullptr, nullptr,
                        (uint32_t*)nullptr, MismatchFlag{nullptr, nullptr}, run_if));
   LRVB_CHECK_LAUNCH();
@@ -463,7 +471,7 @@ static int csr_full_export(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_d
     LRVB_CHECK_LAUNCH();
   }
   // ---- fill: the same three roles, one launch; records the zero mask for later refills ----
-  LRVB_CUDA(launch_pdl(k_csr_pass<1>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
+  LRVB_CUDA(launch_pdl(k_csr_pass<1>, dim3(pass_grid), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
                        nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev,
                        h->csrmask, MismatchFlag{nullptr, nullptr}, run_if));
   LRVB_CHECK_LAUNCH();

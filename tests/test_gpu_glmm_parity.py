@@ -203,12 +203,13 @@ def test_cg_general_preconditioner(vb):
         solver.get_hinv_vec(b)
 
 
-def test_csr_refill_follows_pattern_changes(vb):
+@pytest.mark.parametrize("N,G", [(4000, 40), (30000, 3000)])    # the second: the conditional export walks its roles with a grid stride
+def test_csr_refill_follows_pattern_changes(vb, N, G):
     """The CSR export after the first one rewrites the values for the cached pattern and checks the zero
     mask on the device; when an entry becomes exactly zero (or stops being zero) the conditional full
     export must take over -- without any help from the host -- and later refills use the new pattern."""
     import scipy.sparse
-    case = make_case(N=4000, K=6, G=40, Q=8, seed=91, ragged=True, empty_groups=3)
+    case = make_case(N=N, K=6, G=G, Q=8, seed=91, ragged=True, empty_groups=3)
     oracle, model = make_oracle(case), make_model(vb, case)
     model._csr_refill_min = 0                # the refill path whatever the size
     x = case["free"]
