@@ -282,8 +282,53 @@ def packing_cases():
     print("packing.npz:", len(out), "arrays")
 
 
+def sparse_pattern_cases(vb):
+    """The reference's own sparse emission (SparseObjectives.py:591-619, get_sparse_sub_hessian /
+    get_sparse_sub_matrix + scipy's COO -> CSR summation) applied to seeded dense blocks laid out like the
+    arrowhead Hessian: a global block and one (Dg + 2) x (Dg + 2) block per group, with exact zeros, an
+    all-zero group and float-typed index vectors (make_index_param returns floats, :581-584).  Pins
+    oracle.get_sparse_sub_matrix / get_sparse_sub_hessian and the pattern the oracle's kl_hessian_csr emits."""
+    import scipy.sparse
+    so = vb.SparseObjectives if hasattr(vb, "SparseObjectives") else __import__(
+        "LinearResponseVariationalBayes.SparseObjectives", fromlist=["x"])
+    rng = np.random.default_rng(77)
+    K, G = 3, 5
+    Dg, D = 4 + 2 * K, 4 + 2 * K + 2 * G
+    out = {"pat_K": K, "pat_G": G}
+    A = rng.standard_normal((Dg, Dg)); A = A + A.T
+    A[0, 1] = A[1, 0] = 0.0
+    A[:2, 4:] = 0.0; A[4:, :2] = 0.0
+    H = so.get_sparse_sub_hessian(A, np.arange(Dg, dtype=float), D)
+    subs = []
+    for g in range(G):
+        sub = np.zeros((Dg + 2, Dg + 2))
+        if g != 3:                                   # group 3: no observations, all-zero border
+            b = rng.standard_normal((2, Dg))
+            b[1, 0] = 0.0                            # structural zero (mu.mean x u.info)
+            if g == 1:
+                b[0, 5] = 0.0                        # an accidental exact zero
+            sub[Dg:, :Dg] = b
+            sub[:Dg, Dg:] = b.T
+        l = rng.standard_normal(3)
+        sub[Dg, Dg], sub[Dg, Dg + 1], sub[Dg + 1, Dg], sub[Dg + 1, Dg + 1] = l[0], l[1], l[1], l[2]
+        idx = np.concatenate([np.arange(Dg), [Dg + g, Dg + G + g]]).astype(float)
+        H = H + so.get_sparse_sub_hessian(sub, idx, D)
+        subs.append(sub)
+    H = scipy.sparse.csr_matrix(H)
+    H.sort_indices()
+    out.update(pat_A=A, pat_subs=np.stack(subs), pat_indptr=H.indptr, pat_indices=H.indices, pat_data=H.data)
+    # rectangular sub-matrix with distinct row / column index vectors
+    M = rng.standard_normal((3, 4)); M[1, 2] = 0.0
+    R = so.get_sparse_sub_matrix(M, np.array([7.0, 2.0, 2.0]), np.array([0.0, 5.0, 1.0, 5.0]), 9, 6)
+    R = scipy.sparse.csr_matrix(R); R.sum_duplicates(); R.sort_indices()
+    out.update(pat_M=M, pat_R_indptr=R.indptr, pat_R_indices=R.indices, pat_R_data=R.data)
+    np.savez_compressed(os.path.join(OUT, "sparse_pattern.npz"), **out)
+    print("sparse_pattern.npz: nnz", H.nnz, "of", D * D)
+
+
 def main():
     vb = import_reference()
+    sparse_pattern_cases(vb)
     import LinearResponseVariationalBayes.Modeling as M
     import LinearResponseVariationalBayes.ExponentialFamilies as ef
     mods = (vb, M, ef)

@@ -71,3 +71,34 @@ def test_forward_functions_against_reference_golden(vb):
                                f["mv_digamma"], **tol)
     np.testing.assert_allclose([ef.multivariate_gammaln(3.7, 4), ef.multivariate_gammaln(2.2, 2)],
                                f["mv_gammaln"], **tol)
+
+
+def test_device_csr_export_against_the_references_sparse_emission(vb):
+    """The device CSR export (csrc/csr.cu: full export, refill, conditional re-export) on the very blocks of
+    tests/golden/sparse_pattern.npz -- emitted there by the reference's own get_sparse_sub_hessian +
+    scipy summation: indptr / indices / data bit-exact, exact zeros dropped, empty group included."""
+    import torch
+    from oracle import glmm_oracle as go
+    d = load("sparse_pattern")
+    K, G = int(d["pat_K"]), int(d["pat_G"])
+    Dg = 4 + 2 * K
+    X, y, g = go.make_glmm_data(200, K, G, seed=5)
+    model = vb.LogisticGLMM(X, y, g, num_gh_points=4, num_groups=G)
+    model._csr_refill_min = 0
+    model.evaluate(go.make_free(model.D, 5), 2)
+    A, B, L = model.blocks()
+    subs = d["pat_subs"]
+
+    def load_blocks(scale=1.0):
+        A.copy_(torch.from_numpy(d["pat_A"] * scale))
+        B.copy_(torch.from_numpy(np.stack([subs[:, Dg, :Dg], subs[:, Dg + 1, :Dg]], axis=1) * scale))
+        L.copy_(torch.from_numpy(np.stack([subs[:, Dg, Dg], subs[:, Dg, Dg + 1], subs[:, Dg + 1, Dg + 1]], axis=1) * scale))
+
+    load_blocks()
+    for rep in range(3):            # refill of the model's data pattern -> mismatch -> conditional export; then refills
+        H = model.hessian_csr().to_scipy()
+        assert H.indptr.dtype == np.int32 and H.indices.dtype == np.int32
+        np.testing.assert_array_equal(H.indptr, d["pat_indptr"])
+        np.testing.assert_array_equal(H.indices, d["pat_indices"])
+        np.testing.assert_array_equal(H.data, d["pat_data"] * (1.0 if rep == 0 else 2.0 ** (rep)))
+        load_blocks(2.0 ** (rep + 1))

@@ -121,3 +121,39 @@ def test_oracle_cg_and_schur_agree_with_dense_solve():
     assert np.max(np.abs(xs - np.linalg.solve(H, b))) < 1e-8   # test_objectives.py:552-554
     cov, _ = o.schur_global_cov(x)
     np.testing.assert_allclose(cov, np.linalg.inv(H)[:o.lay.Dg, :o.lay.Dg], rtol=1e-9, atol=1e-12)
+
+
+def test_sparse_emission_against_the_references_own_helpers():
+    """oracle.get_sparse_sub_matrix / get_sparse_sub_hessian (and the dense -> CSR route the parity tests use)
+    against tests/golden/sparse_pattern.npz, which make_golden.py produced with the reference's OWN
+    SparseObjectives.get_sparse_sub_hessian / get_sparse_sub_matrix (:591-619): indptr / indices bit-exact,
+    data bit-exact (no arithmetic is involved beyond scipy's duplicate summation)."""
+    import scipy.sparse
+    from oracle import glmm_oracle as go
+    d = np.load(os.path.join(GOLD, "sparse_pattern.npz"))
+    K, G = int(d["pat_K"]), int(d["pat_G"])
+    Dg, D = 4 + 2 * K, 4 + 2 * K + 2 * G
+    H = go.get_sparse_sub_hessian(d["pat_A"], np.arange(Dg, dtype=float), D)
+    for g in range(G):
+        idx = np.concatenate([np.arange(Dg), [Dg + g, Dg + G + g]]).astype(float)
+        H = H + go.get_sparse_sub_hessian(d["pat_subs"][g], idx, D)
+    H = scipy.sparse.csr_matrix(H)
+    H.sort_indices()
+    assert H.indptr.dtype == np.int32 and H.indices.dtype == np.int32
+    np.testing.assert_array_equal(H.indptr, d["pat_indptr"])
+    np.testing.assert_array_equal(H.indices, d["pat_indices"])
+    np.testing.assert_array_equal(H.data, d["pat_data"])
+    # the same matrix through the arrowhead blocks (what GLMMOracle.kl_hessian_csr and the GPU export emit)
+    subs = d["pat_subs"]
+    blk = dict(A=d["pat_A"], B=np.stack([subs[:, Dg, :Dg], subs[:, Dg + 1, :Dg]], axis=1),
+               L=np.stack([subs[:, Dg, Dg], subs[:, Dg, Dg + 1], subs[:, Dg + 1, Dg + 1]], axis=1))
+    Hd = scipy.sparse.csr_matrix(go.GLMMOracle.blocks_to_dense(go.Layout(K, G), blk))
+    Hd.sort_indices()
+    np.testing.assert_array_equal(Hd.indptr, d["pat_indptr"])
+    np.testing.assert_array_equal(Hd.indices, d["pat_indices"])
+    np.testing.assert_array_equal(Hd.data, d["pat_data"])
+    R = go.get_sparse_sub_matrix(d["pat_M"], np.array([7.0, 2.0, 2.0]), np.array([0.0, 5.0, 1.0, 5.0]), 9, 6)
+    R = scipy.sparse.csr_matrix(R); R.sum_duplicates(); R.sort_indices()
+    np.testing.assert_array_equal(R.indptr, d["pat_R_indptr"])
+    np.testing.assert_array_equal(R.indices, d["pat_R_indices"])
+    np.testing.assert_allclose(R.data, d["pat_R_data"], rtol=0, atol=0)
