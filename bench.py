@@ -549,15 +549,31 @@ def e2e_measure(ctx, res, steps, warmup):
     torch.cuda.synchronize()
     if sharded:
         dist.barrier()
+    prof = None
+    if os.environ.get("LRVB_BENCH_PROFILE"):
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
+    marks = []
     for i in range(steps):
         H, gr, kl = step(warmup + i)
+        marks.append(time.perf_counter())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     gc.enable()
+    per = np.diff(np.asarray([t0] + marks)) * 1e3
+    if ctx.rank == 0:
+        print("e2e step ms (rank 0): min %.3f median %.3f max %.3f mean %.3f" % (
+            per.min(), np.median(per), per.max(), per.mean()), file=sys.stderr)
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(14)
     dt = float(_gather_floats(ctx, [dt])[:, 0].max()) if sharded else dt
     nnz = int(H.nnz)
     return {"value": res["n_total"] / (dt / steps), "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
+            "median_ms_rank0": float(np.median(per)), "steps": steps, "warmup": warmup,
             "h2d_bytes_per_step": 8 * D,
             "d2h_bytes_per_step": 8 + 8 * int(gr.size) + 12 * nnz + 4 * (int(H.shape[0]) + 1),
             "d2h_note": "bytes of the RESULT handed to the caller (data + indices + indptr + gradient + KL); "
@@ -735,7 +751,9 @@ def run_ours(args, wl):
     cov = cov_entry(ctx, res["model"], K, G, peak_tf, ncov=20 if K <= 64 else 3)
     if args.workload == "c4" and world == 1:
         cov["cg"] = cov_cg_entry(ctx, res)
-    e2e = e2e_measure(ctx, res, min(args.steps, 50 if K <= 64 else 2), min(args.warmup, 5 if K <= 64 else 1))
+    # warm-up of the host path: the pinned staging blocks of torch's caching host allocator (three 14 MB
+    # blocks rotate at C2) are created by cudaHostAlloc calls of several milliseconds each the first time
+    e2e = e2e_measure(ctx, res, min(args.steps, 50 if K <= 64 else 2), max(args.warmup, 10) if K <= 64 else 1)
     parity = parity_single(ctx, res, wl) if world == 1 else parity_sharded(ctx, res)
 
     line = None
@@ -784,7 +802,7 @@ def run_ours(args, wl):
         tmode = "single" if world == 1 else "strong"
         rt = time_workload(ctx, wt, tmode, tsteps, twarm, kernel_steps=5)
         tcov = cov_entry(ctx, rt["model"], wt["K"], rt["local"].G, peak_tf, ncov=5)
-        te2e = e2e_measure(ctx, rt, 3, 1) if world == 1 else None
+        te2e = e2e_measure(ctx, rt, 5, 3) if world == 1 else None
         tline = None
         if rank == 0:
             tline = {"workload": wt["name"], "n_gpus": world,

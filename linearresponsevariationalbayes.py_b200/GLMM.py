@@ -281,6 +281,7 @@ class LogisticGLMM(object):
         self._csr_pattern = None          # _Pattern of the last full export (shared by refilled matrices)
         self._csr_pending = None          # refill whose pattern check has not been read yet
         self._csr_flag_pin, self._csr_slot = None, 0
+        self._csr_flag_dev, self._csr_fallback = None, None
         self._csr_refill_min = 400000     # structural nnz below which a full export is cheaper than a refill
         self._D_in = self.D
         self._coords = "free"
@@ -456,16 +457,19 @@ class LogisticGLMM(object):
     def set_global_block(self, A):
         nat.check(self._lib.lrvb_glmm_set_global_block(self._h, nat.ptr(A), nat.stream_ptr()))
 
-    def _export_full(self, run_if=None):
-        """Full CSR export into fresh buffers -> (_Pattern, values); with ``run_if`` (device int32) the
-        export runs on the device only if the flag is set (lrvb_glmm_hessian_csr_if)."""
+    def _export_full(self, run_if=None, bufs=None):
+        """Full CSR export -> (_Pattern, values); with ``run_if`` (device int32) the export runs on the
+        device only if the flag is set (lrvb_glmm_hessian_csr_if).  ``bufs``: (crow, col, val, nnz) to
+        write into instead of fresh tensors."""
         torch = nat.require_cuda()
         cap = ctypes.c_int64()
         nat.check(self._lib.lrvb_glmm_hessian_csr_capacity(self._h, ctypes.byref(cap)))
-        crow = torch.empty(self.D + 1, dtype=torch.int32, device=self.device)
-        col = torch.empty(cap.value, dtype=torch.int32, device=self.device)
-        val = torch.empty(cap.value, dtype=torch.float64, device=self.device)
-        nnz = torch.empty((), dtype=torch.int64, device=self.device)
+        if bufs is None:
+            bufs = (torch.empty(self.D + 1, dtype=torch.int32, device=self.device),
+                    torch.empty(cap.value, dtype=torch.int32, device=self.device),
+                    torch.empty(cap.value, dtype=torch.float64, device=self.device),
+                    torch.empty((), dtype=torch.int64, device=self.device))
+        crow, col, val, nnz = bufs
         if run_if is None:
             nat.check(self._lib.lrvb_glmm_hessian_csr(self._h, nat.ptr(crow), nat.ptr(col), nat.ptr(val),
                                                       cap.value, nat.ptr(nnz), nat.stream_ptr()))
@@ -487,6 +491,8 @@ class LogisticGLMM(object):
             self._csr_pending = None
             if pend.resolve():
                 self._csr_pattern = pend.fallback[0]
+                self._csr_fallback = None            # consumed: they now ARE the pattern / a result
+                self._csr_flag_dev.zero_()           # stream-ordered before the next refill
         pat = self._csr_pattern
         # small problems are launch-bound: the four launches of a full export are cheaper than the refill
         # plus its conditional fallback (and the host-side bookkeeping of the pending check)
@@ -497,17 +503,27 @@ class LogisticGLMM(object):
             return DeviceCSR(pat, val)
         if self._csr_flag_pin is None:
             self._csr_flag_pin = torch.zeros(8, dtype=torch.int32).pin_memory()
+            self._csr_flag_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._csr_slot = 0
         slot = self._csr_slot = (self._csr_slot + 1) % 8
         self._csr_flag_pin[slot] = 0
-        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        flag = self._csr_flag_dev         # stays 0 until a mismatch; reset when that mismatch is resolved
         val = torch.empty(pat.nnz, dtype=torch.float64, device=self.device)
         host_ptr = ctypes.c_void_p(self._csr_flag_pin.data_ptr() + 4 * slot)
         nat.check(self._lib.lrvb_glmm_hessian_csr_refill(self._h, nat.ptr(pat.crow), nat.ptr(val), nat.ptr(flag),
                                                          host_ptr, nat.stream_ptr()))
         ev = torch.cuda.Event()
         ev.record()
-        fallback = self._export_full(run_if=flag)
+        # the conditional full export writes into buffers that are kept from call to call (they are touched
+        # only if the pattern changed, in which case they leave with the result and new ones are made)
+        if self._csr_fallback is None:
+            cap = ctypes.c_int64()
+            nat.check(self._lib.lrvb_glmm_hessian_csr_capacity(self._h, ctypes.byref(cap)))
+            self._csr_fallback = (torch.empty(self.D + 1, dtype=torch.int32, device=self.device),
+                                  torch.empty(cap.value, dtype=torch.int32, device=self.device),
+                                  torch.empty(cap.value, dtype=torch.float64, device=self.device),
+                                  torch.empty((), dtype=torch.int64, device=self.device))
+        fallback = self._export_full(run_if=flag, bufs=self._csr_fallback)
         pend = _PendingRefill(ev, self._csr_flag_pin, slot, fallback)
         self._csr_pending = pend
         return DeviceCSR(pat, val, pend)
