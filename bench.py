@@ -564,8 +564,8 @@ def e2e_measure(ctx, res, steps, warmup):
     gc.enable()
     per = np.diff(np.asarray([t0] + marks)) * 1e3
     if ctx.rank == 0:
-        print("e2e step ms (rank 0): min %.3f median %.3f max %.3f mean %.3f" % (
-            per.min(), np.median(per), per.max(), per.mean()), file=sys.stderr)
+        print("e2e step ms (rank 0): min %.3f median %.3f max %.3f (step #%d) mean %.3f" % (
+            per.min(), np.median(per), per.max(), int(per.argmax()), per.mean()), file=sys.stderr)
     if prof is not None:
         import pstats
         prof.disable()
