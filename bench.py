@@ -543,7 +543,7 @@ def e2e_measure(ctx, res, steps, warmup):
         kl = obj.fun_free(xh)            # float
         return H, gr, kl
     for i in range(warmup):
-        step(i)
+        H, gr, kl = step(i)                 # bound as in the timed loop: the previous result lives until the next is back
     gc.collect()
     gc.disable()                            # as in the device loop: no collector pauses inside the timed steps
     torch.cuda.synchronize()

@@ -153,6 +153,12 @@ class DeviceCSR(object):
             hr = torch.empty(pat.crow.numel(), dtype=torch.int32, pin_memory=True)
             hc.copy_(pat.col[:nnz], non_blocking=True)
             hr.copy_(pat.crow, non_blocking=True)
+            if 8 * nnz <= (1 << 30):
+                # a caller that still holds the previous matrix when it asks for the next one needs TWO value
+                # blocks in rotation; pinning a block costs milliseconds (8 ms for 16 MB), so the second one
+                # is created now, next to the pattern download, and parked in the host allocator's cache
+                spare = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
+                del spare
             torch.cuda.current_stream().synchronize()
             m = scipy.sparse.csr_matrix((hv.numpy(), hc.numpy(), hr.numpy()), shape=self.shape, copy=False)
             m.has_sorted_indices = True

@@ -146,7 +146,7 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
     return LRVB_EINVAL;
   }
 
-  CREATE_TRY(dev_alloc(&h->vec, (size_t)h->D));
+  CREATE_TRY(dev_alloc(&h->vec, (size_t)h->D + 8 + (size_t)K + (size_t)G));   // + k_prep's derived factors (prep_aux)
   h->ldw = (N + 7) / 8 * 8;
   CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)h->ldw));
 

@@ -22,6 +22,7 @@
 // ONE pass with the cached offsets and compares the mask of the new values with the recorded one -- any
 // difference raises a device flag, and the caller's conditional full export (run_if) takes over.
 #include "common.cuh"
+#include "gram_small.cuh"   // mbarrier / bulk-copy helpers
 
 namespace lrvb {
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restric
              const int32_t* __restrict__ chunkoff, const int32_t* __restrict__ cntA,
              const int32_t* __restrict__ coltot, const int32_t* __restrict__ indptr,
              int32_t* __restrict__ indices, double* __restrict__ data) {
-  extern __shared__ double tile[];   // CG x (2*Dg + 1)  (+1: conflict-free column reads)
+  extern __shared__ __align__(16) double tile[];   // CG x (2*Dg + 1)  (+1: conflict-free column reads)
   const int ncol = 2 * Dg, ld = ncol + 1;
   const int chunk = bid;
   const int g0 = chunk * CG;
@@ -147,6 +148,9 @@ __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restric
     int64_t base = 0;
     if (FILL)
       base = (int64_t)indptr[r] + cntA[r] + (side ? coltot[r] : 0) + chunkoff[(size_t)chunk * ncol + c];
+    // the fill pass records where this (chunk, column) segment starts: the refill then needs ONE index load
+    // per segment (chunkcnt is the segment-base array in that launch)
+    if (FILL == 1 && lane == 0 && chunkcnt) chunkcnt[(size_t)chunk * ncol + c] = (int32_t)base;
     int count = 0;
     for (int s0 = 0; s0 < ng; s0 += 32) {
       const int gl = s0 + lane;
@@ -165,6 +169,180 @@ __device__ __forceinline__ void csr_B_cols_body(int bid, const double* __restric
   }
 }
 
+// ---- refill of one chunk of CG groups: border columns AND local rows from one staged tile -------------
+// B is read from HBM once (the full export reads it twice: transposed for the global rows, row-wise for the
+// local rows).  The index words the chunk needs are fetched into shared memory BEFORE the tile is awaited,
+// so no warp walks a chain of dependent loads per column or row:
+//   sseg  (2 Dg)   start of every (chunk, column) segment of a global row (recorded by the fill pass)
+//   sbase (2 CG)   indptr of the chunk's local rows
+//   sl    (CG x 4) the local 2x2 block | recorded 3-bit mask
+//   spos  (2 Dg)   uniform chunks: per side, the recorded-nonzero columns of a local row in order
+// Usual case ("uniform"): all local rows of a side have the SAME recorded zero mask in this chunk (the
+// structural zeros: d2/d u d mu.info and d2/d u.info d mu.mean) and all 2x2 blocks the same 3-bit mask.
+// Then every position is known without looking at the values: a local-row entry sits at base + spos[c], a
+// border-column segment holds either all of the chunk's groups in order or none, nothing is compacted, and
+// the check is "zero exactly where the record says zero".  Otherwise ballots compact the values and the
+// masks are compared word by word.  CG is a power of two <= 32 (a warp packs 32 / CG columns per pass).
+// The tile rows are 2 Dg + 2 doubles apart: bulk async copies (TMA) need 16-byte aligned destinations, and the
+// even stride costs a two-way bank conflict on the column reads, which is noise next to the copies it saves.
+__host__ __device__ inline size_t csr_refill_smem(int Dg, int CG) {
+  return sizeof(double) * ((size_t)CG * (2 * Dg + 2) + (size_t)CG * 4 + 1) +
+         sizeof(int32_t) * ((size_t)4 * Dg + 2 * CG + 2 * ((Dg + 31) / 32) + 4);
+}
+__device__ __forceinline__ void csr_refill_chunk_body(int chunk, const double* __restrict__ B, const double* __restrict__ L,
+                 int Dg, int G, int CG, const int32_t* __restrict__ segbase, const int32_t* __restrict__ indptr,
+                 double* __restrict__ data, const uint32_t* __restrict__ mask, const MismatchFlag mismatch) {
+  extern __shared__ __align__(16) double tile[];   // CG x (2*Dg + 2)
+  const int ncol = 2 * Dg, ld = ncol + 2;
+  const int WA = (Dg + 31) >> 5;
+  double* sl = tile + (size_t)CG * ld;
+  unsigned long long* mbar = (unsigned long long*)(sl + (size_t)CG * 4);
+  int32_t* sseg = (int32_t*)(mbar + 1);
+  int32_t* sbase = sseg + ncol;
+  int32_t* spos = sbase + 2 * CG;
+  uint32_t* spm = (uint32_t*)(spos + ncol);      // [2][WA] mask of the first row of each side | [2*WA + 0] L mask
+  const int g0 = chunk * CG;
+  const int ng = (G - g0 < CG) ? (G - g0) : CG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t maskL = ((size_t)Dg + 2 * (size_t)G) * WA;
+  // --- tile: one bulk async copy per group row (warp 0 issues them; nobody touches a register for it) ---
+  const unsigned bar = smem_u32(mbar);
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      mbar_arrive_expect_tx(bar, (unsigned)(ng * ncol * sizeof(double)));
+    }
+    __syncwarp();
+    if (lane < ng)
+      bulk_g2s(smem_u32(tile + lane * ld), B + ((size_t)g0 + lane) * ncol, (unsigned)(ncol * sizeof(double)), bar);
+  }
+  // --- metadata (independent of the tile) ---
+  bool uniform = true;
+  for (int t = tid; t < ncol; t += 256) sseg[t] = segbase[(size_t)chunk * ncol + t];
+  {
+    const uint32_t* mfirst0 = mask + ((size_t)Dg + g0) * WA;                  // first row of side 0 / 1
+    const uint32_t* mfirst1 = mask + ((size_t)Dg + (size_t)G + g0) * WA;
+    const int32_t* ip0 = indptr + (size_t)Dg + g0;
+    const int32_t* ip1 = ip0 + G;
+    for (int rr = warp; rr < 2 * ng; rr += 8) {
+      const int side = rr >= ng ? 1 : 0, gl = rr - side * ng;
+      const uint32_t* mf = side ? mfirst1 : mfirst0;
+      const uint32_t* mr = mf + (size_t)gl * WA;
+      for (int k = lane; k < WA; k += 32) {
+        const uint32_t m = mr[k];
+        uniform &= (m == mf[k]);
+        if (gl == 0) spm[side * WA + k] = m;
+      }
+      if (lane == 31) sbase[rr] = (side ? ip1 : ip0)[gl];
+    }
+  }
+  {
+    const uint32_t lm0 = mask[maskL + g0];
+    if (tid == 0) spm[2 * WA] = lm0;
+    for (int t = tid; t < ng * 4; t += 256) {
+      const int gl = t >> 2, k = t & 3;
+      double v;
+      if (k < 3) v = L[(size_t)(g0 + gl) * 3 + k];
+      else {
+        const uint32_t lm = mask[maskL + g0 + gl];
+        uniform &= (lm == lm0);
+        v = (double)lm;
+      }
+      sl[t] = v;
+    }
+  }
+  uniform = __syncthreads_and(uniform ? 1 : 0) != 0;
+  mbar_wait(bar, 0);               // the tile has landed (the barrier above ordered the mbarrier's init)
+  bool bad = false;
+  const int per = 32 / CG;                       // columns per warp pass
+  const int sub = lane / CG, glc = lane - sub * CG;
+  if (uniform) {
+    // per side: the list of recorded-nonzero columns in order (spos[side * Dg + j] = column of the j-th entry
+    // of a local row), and sseg[c] = -1 for a recorded-zero column
+    for (int t = tid; t < ncol; t += 256) {
+      const int side = t >= Dg ? 1 : 0, c = t - side * Dg;
+      const uint32_t* pm = spm + side * WA;
+      int p = 0;
+      for (int w = 0; w < (c >> 5); ++w) p += __popc(pm[w]);
+      const uint32_t mw = pm[c >> 5];
+      p += __popc(mw & ((1u << (c & 31)) - 1u));
+      if ((mw >> (c & 31)) & 1u) spos[side * Dg + p] = c;
+      else sseg[t] = -1;
+    }
+    __syncthreads();
+    // --- border columns: all of the chunk's groups in order, or none; EVERY tile element is checked here ---
+    if (glc < ng) {
+      const double* tp = tile + glc * ld;
+      for (int c = warp * per + sub; c < ncol; c += 8 * per) {
+        const double v = tp[c];
+        const int sg = sseg[c];
+        bad |= ((v != 0.0) != (sg >= 0));
+        if (sg >= 0) data[sg + glc] = v;
+      }
+    }
+    // --- local rows: the recorded border entries in order, then the recorded entries of the 2x2 block ---
+    const uint32_t lm = spm[2 * WA];
+    int nzs[2] = {0, 0};                       // recorded border entries per local row of side 0 / 1
+    for (int w = 0; w < WA; ++w) { nzs[0] += __popc(spm[w]); nzs[1] += __popc(spm[WA + w]); }
+    for (int rr = warp; rr < 2 * ng; rr += 8) {
+      const int side = rr >= ng ? 1 : 0, gl = rr - side * ng;
+      double* drow = data + sbase[rr];
+      const double* b = tile + gl * ld + side * Dg;
+      const int32_t* pc = spos + side * Dg;
+      const int nz = side ? nzs[1] : nzs[0];
+      for (int j = lane; j < nz; j += 32) drow[j] = b[pc[j]];
+      if (lane < 2) {
+        // side 0: (mm, mi) = bits 0, 1 of the 3-bit mask; side 1: (mi, ii) = bits 1, 2
+        const double v = sl[gl * 4 + side + lane];
+        const bool rec = (lm >> (side + lane)) & 1u;
+        const int before = (lane == 1) ? (int)((lm >> side) & 1u) : 0;
+        bad |= ((v != 0.0) != rec);
+        if (rec) drow[nz + before] = v;
+      }
+    }
+  } else {
+    const unsigned cgmask = (CG == 32) ? 0xffffffffu : ((1u << CG) - 1u);
+    for (int cb = warp * per; cb < ncol; cb += 8 * per) {
+      const int c = cb + sub;
+      const bool on = (c < ncol) && (glc < ng);
+      const double v = on ? tile[glc * ld + c] : 0.0;
+      const bool nz = (v != 0.0);
+      const unsigned m = (__ballot_sync(0xffffffffu, nz) >> (sub * CG)) & cgmask;
+      if (nz) data[(int64_t)sseg[c] + __popc(m & ((1u << glc) - 1u))] = v;
+    }
+    for (int rr = warp; rr < 2 * ng; rr += 8) {
+      const int side = rr >= ng ? 1 : 0, gl = rr - side * ng;
+      const size_t wg = (size_t)side * G + g0 + gl;
+      int64_t base = sbase[rr];
+      const double* b = tile + gl * ld + side * Dg;
+      for (int c0 = 0; c0 < Dg; c0 += 32) {
+        const int c = c0 + lane;
+        const double v = (c < Dg) ? b[c] : 0.0;
+        const bool nz = (v != 0.0);
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (nz) data[base + __popc(m & ((1u << lane) - 1u))] = v;
+        bad |= (m != mask[((size_t)Dg + wg) * WA + (c0 >> 5)]);
+        base += __popc(m);
+      }
+      if (lane == 0) {
+        const double l0 = sl[gl * 4], l1 = sl[gl * 4 + 1], l2 = sl[gl * 4 + 2];
+        const double va = side ? l1 : l0, vb = side ? l2 : l1;
+        if (va != 0.0) data[base++] = va;
+        if (vb != 0.0) data[base] = vb;
+        if (side == 0) {
+          const unsigned lmc = (l0 != 0.0 ? 1u : 0u) | (l1 != 0.0 ? 2u : 0u) | (l2 != 0.0 ? 4u : 0u);
+          bad |= (lmc != (unsigned)sl[gl * 4 + 3]);
+        }
+      }
+    }
+  }
+  if (bad) {
+    *mismatch.dev = 1;
+    if (mismatch.host) *(volatile int*)mismatch.host = 1;
+  }
+}
+
 // One launch per phase: blocks [0, nA) take the rows of A, the next nB blocks a chunk of B each,
 // the rest the local rows (block-uniform roles; only the B role uses the dynamic shared memory).
 // FILL = 0 count, 1 fill (and record the zero mask), 2 refill: data only with the cached offsets, the
@@ -179,20 +357,25 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
            const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ data,
            uint32_t* __restrict__ mask, const MismatchFlag mismatch, const int* __restrict__ run_if) {
   const int bid = blockIdx.x;
-  if (FILL == 2 && bid >= nA) {
+  if constexpr (FILL == 2) {
+  if (bid >= nA) {
     // Refill: the border columns and the local rows need B and L only.  Those are written by k_finish, and
     // every path to this kernel passes k_global_post (or a kernel launched even later), which signals its
     // dependents after its own wait: B and L are complete when this CTA starts, so it runs ahead of the
     // wait, behind k_global_post (one CTA), which is still finishing A.  Nothing written here is read by
     // a kernel that might still be running in front of this one.
     pdl_launch_dependents();
-    if (bid < nA + nB) {
+    if (chunkcnt != nullptr) {
+      // merged refill (large G), grid = nA + nB: every chunk block writes its border segments and its local rows (chunkcnt = segment bases)
+      csr_refill_chunk_body(bid - nA, B, L, Dg, G, CG, chunkcnt, indptr, data, mask, mismatch);
+    } else if (bid < nA + nB) {
       csr_B_cols_body<FILL>(bid - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
     } else {
       csr_local_rows_body<FILL>(bid - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
     }
     pdl_wait();        // completion of this kernel still implies completion of its prerequisite
     return;
+  }
   }
   pdl_sync();
   if (run_if && *run_if == 0) return;
@@ -375,9 +558,10 @@ k_csr_indptr_small(const int32_t* __restrict__ cntA, const int32_t* __restrict__
 }
 
 static int csr_chunk_groups(int Dg) {
-  // stage CG x (2 Dg + 1) doubles in <= ~96 KB of shared memory
+  // stage CG x (2 Dg + 1) doubles in <= 54 KB of shared memory
+  // (4 CTAs of 8 warps per SM; a power of two <= 32 -- the refill packs 32 / cg columns per ballot)
   int cg = 32;
-  while (cg > 4 && sizeof(double) * (size_t)cg * (2 * Dg + 1) > 27 * 1024) cg >>= 1;   // the merged pass keeps 8 CTAs/SM
+  while (cg > 4 && csr_refill_smem(Dg, cg) > 55 * 1024 + 512) cg >>= 1;
   return cg;
 }
 
@@ -392,16 +576,16 @@ static int ensure_csr_scratch(lrvb_glmm* h) {
   h->csr_nchunk = nchunk;
   LRVB_CUDA(cudaMalloc((void**)&h->rowcnt, sizeof(int32_t) * (size_t)(D + 1)));
   LRVB_CUDA(cudaMalloc((void**)&h->scanblk, sizeof(int64_t) * ((size_t)nblk + 2)));
-  // cntA (Dg) | coltot (2Dg) | chunkcnt (nchunk*2Dg) | chunkoff (nchunk*2Dg)
+  // cntA (Dg) | coltot (2Dg) | chunkcnt (nchunk*2Dg) | chunkoff (nchunk*2Dg) | segbase (nchunk*2Dg)
   LRVB_CUDA(cudaMalloc((void**)&h->csrwork,
-                       sizeof(int32_t) * ((size_t)3 * Dg + (size_t)4 * Dg * nchunk + 4)));
+                       sizeof(int32_t) * ((size_t)3 * Dg + (size_t)6 * Dg * nchunk + 4)));
   // zero mask of the last full export: A (Dg x WA) | B (2G x WA) | L (G) words
   const size_t WA = ((size_t)Dg + 31) / 32;
   LRVB_CUDA(cudaMalloc((void**)&h->csrmask, sizeof(uint32_t) * ((size_t)(Dg + 2 * (size_t)G) * WA + (size_t)G + 1)));
   const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
   cudaFuncSetAttribute(k_csr_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_csr_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_csr_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_csr_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_refill_smem(Dg, CG));
   return LRVB_OK;
 }
 
@@ -471,8 +655,9 @@ static int csr_full_export(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_d
     LRVB_CHECK_LAUNCH();
   }
   // ---- fill: the same three roles, one launch; records the zero mask for later refills ----
+  int32_t* segbase = chunkoff + (size_t)2 * Dg * nchunk;
   LRVB_CUDA(launch_pdl(k_csr_pass<1>, dim3(pass_grid), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
-                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev,
+                       nA, nB, cntA, segbase, chunkoff, coltot, nullptr, indptr_dev, indices_dev, data_dev,
                        h->csrmask, MismatchFlag{nullptr, nullptr}, run_if));
   LRVB_CHECK_LAUNCH();
   h->csr_pattern_valid = 1;
@@ -509,10 +694,14 @@ int lrvb_glmm_hessian_csr_refill(lrvb_glmm* h, const int32_t* indptr_dev, double
   int32_t* coltot = cntA + Dg;
   int32_t* chunkcnt = coltot + 2 * Dg;
   int32_t* chunkoff = chunkcnt + (size_t)2 * Dg * nchunk;
-  const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
+  const size_t smem = csr_refill_smem(Dg, CG);
   const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
-  LRVB_CUDA(launch_pdl(k_csr_pass<2>, dim3(nA + nB + nL), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
-                       nA, nB, cntA, nullptr, chunkoff, coltot, nullptr, indptr_dev, (int32_t*)nullptr, data_dev,
+  int32_t* segbase = chunkoff + (size_t)2 * Dg * nchunk;
+  // large G: one block per chunk writes border segments and local rows from one staged tile (B read once);
+  // small G is launch- and latency-bound, where the many short blocks of the separate roles finish sooner
+  const bool merged = G >= 32768;
+  LRVB_CUDA(launch_pdl(k_csr_pass<2>, dim3(nA + nB + (merged ? 0 : nL)), dim3(256), smem, st, h->A, h->B, h->L, Dg, G, CG,
+                       nA, nB, cntA, merged ? segbase : nullptr, chunkoff, coltot, nullptr, indptr_dev, (int32_t*)nullptr, data_dev,
                        h->csrmask, MismatchFlag{(int*)mismatch_dev, (int*)mismatch_host_mapped}, (const int*)nullptr));
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;

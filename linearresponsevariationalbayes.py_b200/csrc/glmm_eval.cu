@@ -50,7 +50,22 @@ __global__ void k_prep(const double* __restrict__ free_v, double* __restrict__ v
   else if (i < 4 + 2 * K) lb = bd.beta_info;
   else if (i < 4 + 2 * K + G) con = false;
   else lb = bd.u_info;
-  vec[i] = (con && !vecmode) ? exp(f) + lb : f;   // Parameters.py:53-55
+  const double v = (con && !vecmode) ? exp(f) + lb : f;   // Parameters.py:53-55
+  vec[i] = v;
+  // factors the finishing pass would otherwise re-derive with an fp64 division per (group, column):
+  // aux = vec + D: [E tau = a/b, 1/b, a/b^2, -, -, -, -, - | -1/beta.info_k^2 (K) | 1/u.info_g^2 (G)]
+  double* aux = vec + D;
+  if (i == 3) {
+    const double a = vecmode ? free_v[2] : exp(free_v[2]) + bd.tau_shape;
+    const double ib = 1.0 / v;
+    aux[0] = a / v;
+    aux[1] = ib;
+    aux[2] = a / (v * v);
+  } else if (i >= 4 + K && i < 4 + 2 * K) {
+    aux[8 + (i - 4 - K)] = -1.0 / (v * v);
+  } else if (i >= 4 + 2 * K + G) {
+    aux[8 + K + (i - 4 - 2 * K - G)] = 1.0 / (v * v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -353,9 +368,16 @@ __device__ __forceinline__ void gram_small_finish_body(int bid, const double* __
 struct GroupFix {
   const int32_t* gptr;
   const double* bval;
-  unsigned rpw;    // rows per warp (N < 2^31: 32-bit divisions)
+  unsigned rpw;    // rows per warp (N < 2^31)
   int nb;          // 5 + 4K
+  double inv_rpw;  // 1 / rpw: the quotient comes from one multiplication and an exact correction step
 };
+__device__ __forceinline__ unsigned div_rpw(unsigned n, const GroupFix& fx) {
+  unsigned q = __double2uint_rz((double)n * fx.inv_rpw);      // floor(n / rpw) or one off
+  if ((unsigned long long)(q + 1) * fx.rpw <= n) ++q;
+  else if ((unsigned long long)q * fx.rpw > n) --q;
+  return q;
+}
 struct GroupSpan {
   unsigned wf, wl;     // first / last producing warp; wf > wl: empty group; wf == wl: the sums were written directly
 };
@@ -365,8 +387,8 @@ __device__ __forceinline__ GroupSpan group_span(const GroupFix& fx, int gi) {
   if (fx.rpw == 0) return sp;
   const unsigned gb = (unsigned)fx.gptr[gi], ge = (unsigned)fx.gptr[gi + 1];
   if (gb == ge) { sp.wf = 1; sp.wl = 0; return sp; }        // empty group: nobody wrote its sums
-  sp.wf = gb / fx.rpw;
-  sp.wl = (ge - 1) / fx.rpw;
+  sp.wf = div_rpw(gb, fx);
+  sp.wl = div_rpw(ge - 1, fx);
   return sp;
 }
 __device__ __forceinline__ double group_val(const GroupFix& fx, const GroupSpan& sp, const double* __restrict__ direct,
@@ -401,9 +423,27 @@ __device__ __forceinline__ void local_body(int bid, int nblk, const double* __re
     if (ORDER >= 1) {
       double s[5];
       const GroupSpan sp = group_span(fx, gi);
+      // the five sums of a group: written directly, or the pieces of a straddling group added in row order
+      // (all five of a record are loaded before they are added: independent loads, one chain of additions)
+      if (sp.wf == sp.wl) {
 #pragma unroll
-      for (int e = 0; e < 5; ++e)
-        s[e] = (ORDER >= 2 || e < 2) ? group_val(fx, sp, gsc, (size_t)gi * 5 + e, e) : 0.0;
+        for (int e = 0; e < 5; ++e) s[e] = (ORDER >= 2 || e < 2) ? gsc[(size_t)gi * 5 + e] : 0.0;
+      } else if (sp.wf > sp.wl) {
+#pragma unroll
+        for (int e = 0; e < 5; ++e) s[e] = 0.0;
+      } else {
+        const double* t = fx.bval + ((size_t)sp.wf * 2 + 1) * fx.nb;
+#pragma unroll
+        for (int e = 0; e < 5; ++e) s[e] = (ORDER >= 2 || e < 2) ? t[e] : 0.0;
+        for (unsigned wi = sp.wf + 1; wi <= sp.wl; ++wi) {
+          const double* hd = fx.bval + ((size_t)wi * 2) * fx.nb;
+          double q[5];
+#pragma unroll
+          for (int e = 0; e < 5; ++e) q[e] = (ORDER >= 2 || e < 2) ? hd[e] : 0.0;
+#pragma unroll
+          for (int e = 0; e < 5; ++e) s[e] += q[e];
+        }
+      }
       const double r2 = r * r;
       const double gF_um = s[0] + E * dm;
       const double gF_ui = -s[1] * r2 + 0.5 * E * r2 - 0.5 * r;
@@ -436,43 +476,144 @@ __device__ __forceinline__ void local_body(int bid, int nblk, const double* __re
 }
 
 // Border rows B (G,2,Dg) in free coordinates: row 0 = (u.mean_g, globals), row 1 = (u.info_g, .).
-// One warp per group (8 groups per block), lanes over the Dg columns: the group's producer span
-// (group_span: two loads and two divisions) is computed once per warp, not once per entry.
+// A block covers 8 x gpw consecutive groups: their per-group scalars and producer spans are fetched
+// cooperatively once (one round trip for the block), then every warp streams its gpw groups with lanes over
+// the K fixed effects: a lane reads its four sums (a x, b x, b s, c s) of all its groups before it writes
+// anything (the pass is a pure stream and needs the memory-level parallelism).  No fp64 division here:
+// -1/beta.info^2, 1/u.info^2 and the tau ratios come from k_prep (one division per parameter instead of one
+// per (group, column)).  A group whose sums were written by one producer warp is read from BR; one that
+// straddles two producer ranges (every sixth group at C2, where a warp's range holds six groups) is the sum
+// of two records of bval, read as two more coalesced streams; more pieces (rare: a group longer than a
+// warp's range) go through group_val.
+constexpr int kBorderBigG = 32768;
+__host__ __device__ inline int border_groups_per_warp(int G) { return G >= kBorderBigG ? 2 : 1; }
+
+struct BorderSrc {
+  const double* pa;     // first (or only) source record, element (e, k) at pa[e * K + k]
+  const double* pb;     // second record or nullptr
+};
+template <int NG>
+__device__ __forceinline__ void border_stream(const double* __restrict__ vec, double* __restrict__ B,
+         const double* __restrict__ adv, int K, int Dg, int g0, int lane, const BorderSrc (&src)[2],
+         const double (&r2)[2], const double (&ji)[2], bool two, lrvb_glmm_bounds bd, int vecmode) {
+  double* __restrict__ o0 = B + (size_t)g0 * 2 * Dg + 4 + lane;        // (group, 2, Dg)
+  const double* __restrict__ pj = vec + 4 + K + lane;
+  const double* __restrict__ pd = adv + lane;
+  const int K2 = 2 * K, K3 = 3 * K, D2 = 2 * Dg;
+#pragma unroll 2
+  for (int k = lane; k < K; k += 32, o0 += 32, pj += 32, pd += 32) {
+    double v[NG][4];
+#pragma unroll
+    for (int r = 0; r < NG; ++r) {
+      const double* p = src[r].pa + k;
+      v[r][0] = p[0]; v[r][1] = p[K]; v[r][2] = p[K2]; v[r][3] = p[K3];
+    }
+    if (two) {
+#pragma unroll
+      for (int r = 0; r < NG; ++r) {
+        if (src[r].pb) {
+          const double* p = src[r].pb + k;
+          v[r][0] += p[0]; v[r][1] += p[K]; v[r][2] += p[K2]; v[r][3] += p[K3];
+        }
+      }
+    }
+    const double dv = *pd;
+    const double jg = vecmode ? 1.0 : *pj - bd.beta_info;
+#pragma unroll
+    for (int r = 0; r < NG; ++r) {
+      const double dr = -r2[r];
+      double* o = o0 + r * D2;
+      o[0] = -v[r][0];
+      o[Dg] = -(v[r][1] * dr) * ji[r];
+      o[K] = -(v[r][2] * dv) * jg;
+      o[Dg + K] = -(v[r][3] * dv * dr) * jg * ji[r];
+    }
+  }
+}
+
 __device__ __forceinline__ void border_body(int bid, const double* __restrict__ vec, const double* __restrict__ BR, double* __restrict__ B,
          int K, int G, lrvb_glmm_bounds bd, int vecmode, const GroupFix& fx) {
+  __shared__ double s_um[16], s_ji[16], s_r2[16];
+  __shared__ unsigned s_wf[16], s_wl[16];
   const int Dg = 4 + 2 * K;
   const int lane = threadIdx.x & 31;
-  const int gi = bid * 8 + (threadIdx.x >> 5);
-  if (gi >= G) return;
-  const double mu_m = vec[0], a = vec[2], b = vec[3];
-  const double um = vec[Dg + gi], ui = vec[Dg + G + gi];
-  const double r2 = 1.0 / (ui * ui);
-  const double dr = -r2;
-  const double ji = ui - bd.u_info;
-  const GroupSpan sp = group_span(fx, gi);
-  const size_t br = (size_t)gi * 4 * K;
-  double* out = B + (size_t)gi * 2 * Dg;
-  for (int col = lane; col < Dg; col += 32) {
-    double b0, b1, jg = 1.0;
-    if (col == 0) { b0 = a / b; b1 = 0.0; }
-    else if (col == 1) { b0 = 0.0; b1 = 0.0; jg = vec[1] - bd.mu_info; }
-    else if (col == 2) { b0 = (mu_m - um) / b; b1 = 0.5 * r2 / b; jg = a - bd.tau_shape; }
-    else if (col == 3) { b0 = -a * (mu_m - um) / (b * b); b1 = -0.5 * a * r2 / (b * b); jg = b - bd.tau_rate; }
-    else if (col < 4 + K) {
-      const int k = col - 4;
-      b0 = group_val(fx, sp, BR, br + k, 5 + k);
-      b1 = group_val(fx, sp, BR, br + K + k, 5 + K + k) * dr;
+  const int gpw = border_groups_per_warp(G);
+  const int gb = bid * 8 * gpw;                    // first group of the block
+  const double* __restrict__ aux = vec + Dg + 2 * (size_t)G;
+  const double* __restrict__ adv = aux + 8;
+  if ((int)threadIdx.x < 8 * gpw && gb + (int)threadIdx.x < G) {
+    const int gi = gb + threadIdx.x;
+    s_um[threadIdx.x] = vec[Dg + gi];
+    s_ji[threadIdx.x] = vecmode ? 1.0 : vec[Dg + G + gi] - bd.u_info;
+    s_r2[threadIdx.x] = aux[8 + K + gi];
+    const GroupSpan sp = group_span(fx, gi);
+    s_wf[threadIdx.x] = sp.wf;
+    s_wl[threadIdx.x] = sp.wl;
+  }
+  __syncthreads();
+  const int l0 = (threadIdx.x >> 5) * gpw;         // first group of the warp, block-local
+  const int g0 = gb + l0;
+  if (g0 >= G) return;
+  const int ng = (gpw == 2 && g0 + 1 < G) ? 2 : 1;
+  double um[2], r2[2], ji[2];
+  GroupSpan sp[2];
+  BorderSrc src[2];
+  bool two = false, many = false;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int l = (r < ng) ? l0 + r : l0;
+    um[r] = s_um[l]; ji[r] = s_ji[l]; r2[r] = s_r2[l];
+    sp[r].wf = s_wf[l]; sp[r].wl = s_wl[l];
+    src[r].pb = nullptr;
+    if (sp[r].wf == sp[r].wl) {
+      src[r].pa = BR + (size_t)(gb + l) * 4 * K;
+    } else if (sp[r].wf + 1 == sp[r].wl) {
+      src[r].pa = fx.bval + ((size_t)sp[r].wf * 2 + 1) * fx.nb + 5;     // tail record of the first warp
+      src[r].pb = fx.bval + ((size_t)sp[r].wl * 2) * fx.nb + 5;         // head record of the second
+      two = true;
     } else {
-      const int k = col - 4 - K;
-      const double ik = vec[4 + K + k];
-      const double dv = -1.0 / (ik * ik);
-      jg = ik - bd.beta_info;
-      b0 = group_val(fx, sp, BR, br + 2 * K + k, 5 + 2 * K + k) * dv;
-      b1 = group_val(fx, sp, BR, br + 3 * K + k, 5 + 3 * K + k) * dv * dr;
+      src[r].pa = BR;          // empty group (wf > wl: zeros) or more than two pieces: generic path below
+      many = true;
     }
-    if (vecmode) jg = 1.0;
-    out[col] = -b0 * jg;
-    out[Dg + col] = -b1 * jg * (vecmode ? 1.0 : ji);
+  }
+  if (lane < 4) {
+    const double mu_m = vec[0], a = vec[2], b = vec[3];
+    const double E = aux[0], ib = aux[1], aib2 = aux[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r >= ng) break;
+      double b0, b1, jg = 1.0;
+      if (lane == 0) { b0 = E; b1 = 0.0; }
+      else if (lane == 1) { b0 = 0.0; b1 = 0.0; jg = vec[1] - bd.mu_info; }
+      else if (lane == 2) { b0 = (mu_m - um[r]) * ib; b1 = 0.5 * r2[r] * ib; jg = a - bd.tau_shape; }
+      else { b0 = -(mu_m - um[r]) * aib2; b1 = -0.5 * r2[r] * aib2; jg = b - bd.tau_rate; }
+      if (vecmode) jg = 1.0;
+      double* out = B + (size_t)(g0 + r) * 2 * Dg;
+      out[lane] = -b0 * jg;
+      out[Dg + lane] = -b1 * jg * ji[r];
+    }
+  }
+  if (!many) {
+    if (ng == 2) border_stream<2>(vec, B, adv, K, Dg, g0, lane, src, r2, ji, two, bd, vecmode);
+    else border_stream<1>(vec, B, adv, K, Dg, g0, lane, src, r2, ji, two, bd, vecmode);
+    return;
+  }
+  for (int r = 0; r < ng; ++r) {
+    const size_t br = (size_t)(g0 + r) * 4 * K;
+    const double dr = -r2[r];
+    double* out = B + (size_t)(g0 + r) * 2 * Dg;
+    for (int k = lane; k < K; k += 32) {
+      const double v0 = group_val(fx, sp[r], BR, br + k, 5 + k);
+      const double v1 = group_val(fx, sp[r], BR, br + K + k, 5 + K + k);
+      const double v2 = group_val(fx, sp[r], BR, br + 2 * (size_t)K + k, 5 + 2 * K + k);
+      const double v3 = group_val(fx, sp[r], BR, br + 3 * (size_t)K + k, 5 + 3 * K + k);
+      const double dv = adv[k];
+      const double jg = vecmode ? 1.0 : vec[4 + K + k] - bd.beta_info;
+      out[4 + k] = -v0;
+      out[Dg + 4 + k] = -(v1 * dr) * ji[r];
+      out[4 + K + k] = -(v2 * dv) * jg;
+      out[Dg + 4 + K + k] = -(v3 * dv * dr) * jg * ji[r];
+    }
   }
 }
 
@@ -641,14 +782,14 @@ __device__ __forceinline__ void global_post(const double* __restrict__ vec, cons
 
 // ------------------------------------------------------------------------------------------
 // One launch for the finishing passes (round 1: k_obs_fixup, k_finish and the first half of k_global):
-// block 0 runs global_pre; blocks [1, 1 + n_loc) the group-level chain rule, the next n_bor the border
-// rows, the next n_gf the Gram finish (block-uniform roles).
+// block 0 runs global_pre; the next n_gf blocks the Gram finish, the next n_loc the group-level chain rule,
+// the last n_bor the border rows (block-uniform roles).
 template <int ORDER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const double* __restrict__ BR,
          double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ B,
          double* locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
-         const GbSlot* __restrict__ slots, double* A, int K, int G, int n_loc, int n_bor,
+         const GbSlot* __restrict__ slots, double* A, int K, int G, int n_loc, int n_bor, int n_gf,
          int gram_small, int NT, int gram_groups, int gram_chunks, lrvb_glmm_bounds bd, int vecmode,
          GroupFix fx, GlobalArgs ga) {
   // wait first: the dependent (k_global_post) signals ITS dependents after its own wait, so whoever follows
@@ -656,18 +797,18 @@ k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const d
   pdl_wait();
   pdl_launch_dependents();
   const int Dg = 4 + 2 * K;
+  // the few blocks with long serial chains (special functions, the sums over the per-CTA Gram partials)
+  // come first, so that they run under the stream of border blocks instead of after it
   const int bid = (int)blockIdx.x - 1;
   if (bid < 0) {
     global_pre<ORDER>(vec, ga, K);
-  } else if (bid < n_loc) {
-    local_body<ORDER>(bid, n_loc, vec, gsc, gradl, L, locpart, K, G, bd, vecmode, fx);
-  } else if (bid < n_loc + n_bor) {
-    border_body(bid - n_loc, vec, BR, B, K, G, bd, vecmode, fx);
-  } else if (gram_small) {
-    gram_small_finish_body(bid - n_loc - n_bor, grampart, vec, A, K, Dg, NT, gram_chunks, bd, vecmode);
+  } else if (bid < n_gf) {
+    if (gram_small) gram_small_finish_body(bid, grampart, vec, A, K, Dg, NT, gram_chunks, bd, vecmode);
+    else gram_big_finish_body(bid, grampart, jobs, slots, vec, A, K, Dg, gram_groups, gram_chunks, bd, vecmode);
+  } else if (bid < n_gf + n_loc) {
+    local_body<ORDER>(bid - n_gf, n_loc, vec, gsc, gradl, L, locpart, K, G, bd, vecmode, fx);
   } else {
-    gram_big_finish_body(bid - n_loc - n_bor, grampart, jobs, slots, vec, A, K, Dg, gram_groups, gram_chunks,
-                         bd, vecmode);
+    border_body(bid - n_gf - n_loc, vec, BR, B, K, G, bd, vecmode, fx);
   }
 }
 
@@ -806,7 +947,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     const int packed_gram = (h->gram_small || h->gram_mid || one_pass) ? 1 : 0;   // partial layout (n_cta, NT, 64)
     const int packed_ctas = one_pass ? h->fu_grid : h->gram_grid_x;
     if (order >= 2) {
-      if (G > 0) n_bor = cdiv(G, 8);
+      if (G > 0) n_bor = cdiv(G, 8 * border_groups_per_warp(G));
       if (N > 0) {
         if (packed_gram) { NT = gram_small_shape(K).NT; n_gf = NT; }
         else n_gf = h->gram_jobs * 16;
@@ -819,6 +960,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
       // no observation kernel ran: every group is empty, which the readers must see as zeros
       fx.rpw = 32;
     }
+    fx.inv_rpw = fx.rpw ? 1.0 / (double)fx.rpw : 0.0;
     GlobalArgs ga;
     ga.klpart = h->klpart; ga.n_kl = n_obs_cta; ga.gradpart = h->gradpart; ga.n_gp = n_obs_cta;
     ga.n_lp = h->loc_grid; ga.out = outp; ga.pr = h->prior; ga.include_global = h->include_global;
@@ -828,7 +970,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
 #define LRVB_FIN(O)                                                                              \
   LRVB_CUDA(launch_pdl(k_finish<O>, dim3(n_work + 1), dim3(256), 0, st, h->vec, h->gsc, h->BR, gl, h->L, h->B, \
                        h->locpart, h->grampart, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,   \
-                       outp + 1 + Dg, K, G, n_loc, n_bor, packed_gram, NT, h->gram_grid_y,         \
+                       outp + 1 + Dg, K, G, n_loc, n_bor, n_gf, packed_gram, NT, h->gram_grid_y,         \
                        packed_gram ? packed_ctas : h->gram_grid_x / (h->gram_grid_y > 0 ? h->gram_grid_y : 1), \
                        h->bounds, h->vecmode, fx, ga));                                            \
   LRVB_CHECK_LAUNCH();                                                                           \

@@ -45,9 +45,14 @@ __host__ __device__ inline int obs_fused_warp_elems(int K, int slots = kOfStages
 // One-slot variant (SLOTS = 1): from K ~ 36 on a two-slot ring leaves room for fewer than 10 warps per SM
 // (7 at K = 50) and the pass is latency-bound; with ONE slot per warp -- the next stage is requested when
 // the current one is finished, the other warps cover the copy -- up to 14 warps fit.
-constexpr int kOfMaxWarps1 = 14;
+constexpr int kOfMaxWarps1 = 16;
 inline int obs_fused_warps(int K, int slots = kOfStages) {
-  int w = (int)((200 * 1024) / (sizeof(double) * obs_fused_warp_elems(K, slots)));
+  // all of the 227 KB a CTA may own (one CTA per SM): per warp its ring, weights, gradient partials (2K), KL
+  // partial and mbarriers; 2K + 2Q shared by the CTA (Q <= 64 assumed for the budget)
+  const size_t per_warp = sizeof(double) * ((size_t)obs_fused_warp_elems(K, slots) + 2 * K + 1) +
+                          sizeof(unsigned long long) * slots;
+  const size_t fixed = sizeof(double) * (2 * (size_t)K + 2 * 64);
+  int w = (int)((227 * 1024 - fixed) / per_warp);
   const int cap = slots == 1 ? kOfMaxWarps1 : kOfMaxWarps;
   if (w > cap) w = cap;
   return w < 1 ? 1 : w;
