@@ -221,21 +221,20 @@ __device__ __forceinline__ void csr_refill_chunk_body(int chunk, const double* _
   bool uniform = true;
   for (int t = tid; t < ncol; t += 256) sseg[t] = segbase[(size_t)chunk * ncol + t];
   {
+    // every recorded mask word of the chunk's local rows in ONE round trip (one word per thread at Dg <= 128)
     const uint32_t* mfirst0 = mask + ((size_t)Dg + g0) * WA;                  // first row of side 0 / 1
     const uint32_t* mfirst1 = mask + ((size_t)Dg + (size_t)G + g0) * WA;
-    const int32_t* ip0 = indptr + (size_t)Dg + g0;
-    const int32_t* ip1 = ip0 + G;
-    for (int rr = warp; rr < 2 * ng; rr += 8) {
-      const int side = rr >= ng ? 1 : 0, gl = rr - side * ng;
+    const int nw = ng * WA;                  // words per side (consecutive in memory: rows g0 .. g0 + ng - 1)
+    for (int t = tid; t < 2 * nw; t += 256) {
+      const int side = t >= nw ? 1 : 0, o = t - side * nw;
       const uint32_t* mf = side ? mfirst1 : mfirst0;
-      const uint32_t* mr = mf + (size_t)gl * WA;
-      for (int k = lane; k < WA; k += 32) {
-        const uint32_t m = mr[k];
-        uniform &= (m == mf[k]);
-        if (gl == 0) spm[side * WA + k] = m;
-      }
-      if (lane == 31) sbase[rr] = (side ? ip1 : ip0)[gl];
+      const uint32_t m = mf[o];
+      const int k = o % WA;
+      uniform &= (m == mf[k]);
+      if (o < WA) spm[side * WA + o] = m;
     }
+    const int32_t* ip0 = indptr + (size_t)Dg + g0;
+    for (int t = tid; t < 2 * ng; t += 256) sbase[t] = (t >= ng) ? ip0[(size_t)G + t - ng] : ip0[t];
   }
   {
     const uint32_t lm0 = mask[maskL + g0];
@@ -285,20 +284,22 @@ __device__ __forceinline__ void csr_refill_chunk_body(int chunk, const double* _
     const uint32_t lm = spm[2 * WA];
     int nzs[2] = {0, 0};                       // recorded border entries per local row of side 0 / 1
     for (int w = 0; w < WA; ++w) { nzs[0] += __popc(spm[w]); nzs[1] += __popc(spm[WA + w]); }
-    for (int rr = warp; rr < 2 * ng; rr += 8) {
-      const int side = rr >= ng ? 1 : 0, gl = rr - side * ng;
-      double* drow = data + sbase[rr];
-      const double* b = tile + gl * ld + side * Dg;
-      const int32_t* pc = spos + side * Dg;
-      const int nz = side ? nzs[1] : nzs[0];
-      for (int j = lane; j < nz; j += 32) drow[j] = b[pc[j]];
-      if (lane < 2) {
-        // side 0: (mm, mi) = bits 0, 1 of the 3-bit mask; side 1: (mi, ii) = bits 1, 2
-        const double v = sl[gl * 4 + side + lane];
-        const bool rec = (lm >> (side + lane)) & 1u;
-        const int before = (lane == 1) ? (int)((lm >> side) & 1u) : 0;
-        bad |= ((v != 0.0) != rec);
-        if (rec) drow[nz + before] = v;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int nz = nzs[side];
+      const bool rec = (lm >> (side + (lane & 1))) & 1u;
+      const int lpos = nz + ((lane == 1) ? (int)((lm >> side) & 1u) : 0);
+      for (int gl = warp; gl < ng; gl += 8) {
+        double* d = data + sbase[side * ng + gl];
+        const double* b = tile + gl * ld + side * Dg;
+        const int32_t* pc = spos + side * Dg;
+        for (int j = lane; j < nz; j += 32) d[j] = b[pc[j]];
+        if (lane < 2) {
+          // side 0: (mm, mi) = bits 0, 1 of the 3-bit mask; side 1: (mi, ii) = bits 1, 2
+          const double v = sl[gl * 4 + side + lane];
+          bad |= ((v != 0.0) != rec);
+          if (rec) d[lpos] = v;
+        }
       }
     }
   } else {

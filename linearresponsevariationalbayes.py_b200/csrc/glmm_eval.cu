@@ -785,7 +785,7 @@ __device__ __forceinline__ void global_post(const double* __restrict__ vec, cons
 // block 0 runs global_pre; the next n_gf blocks the Gram finish, the next n_loc the group-level chain rule,
 // the last n_bor the border rows (block-uniform roles).
 template <int ORDER>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_finish(const double* __restrict__ vec, const double* __restrict__ gsc, const double* __restrict__ BR,
          double* __restrict__ gradl, double* __restrict__ L, double* __restrict__ B,
          double* locpart, const double* __restrict__ grampart, const GbJob* __restrict__ jobs,
