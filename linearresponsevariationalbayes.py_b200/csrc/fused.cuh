@@ -74,7 +74,43 @@ struct FusedArgs {
   double* bval; double* grampart; int64_t N; int K, G, Q; int64_t rows_per_q;   // rows per Q warp (multiple of 32)
 };
 
+// The bulk copies of a Q warp's first SLOTS stages (X rows, y, g, w: inputs no kernel of the chain writes),
+// issued AHEAD of the kernel's programmatic-launch wait: they fly while k_prep finishes.
+template <int SLOTS>
+__device__ __forceinline__ void fused_q_issue_first(const FusedArgs& a, unsigned ring_u, unsigned full_u, int64_t gw) {
+  const int lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int64_t N = a.N;
+  const int slot_elems = fused_slot_elems(K);
+  const int64_t rs = gw * a.rows_per_q;
+  const int64_t re = (rs + a.rows_per_q < N) ? rs + a.rows_per_q : N;
+  const int nst = (rs < re) ? (int)((re - rs + kFuRows - 1) / kFuRows) : 0;
+  const unsigned xbytes = (unsigned)(kFuRows * K * sizeof(double));
+  const unsigned vbytes = (unsigned)(kFuRows * sizeof(double));
+  const unsigned gbytes = (unsigned)(kFuRows * sizeof(int32_t));
+  const unsigned nops = a.w ? 4u : 3u;
+#pragma unroll
+  for (int st = 0; st < SLOTS; ++st) {
+    const int64_t n0 = rs + (int64_t)st * kFuRows;
+    if (st < nst && n0 + kFuRows <= N && lane < (int)nops) {
+      const unsigned bar = full_u + 8 * st;
+      const unsigned dst = ring_u + (unsigned)(st * slot_elems * sizeof(double));
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, xbytes + (a.w ? 2 : 1) * vbytes + gbytes);
+        bulk_g2s(dst, a.X + n0 * K, xbytes, bar);
+      } else if (lane == 1) {
+        bulk_g2s(dst + xbytes, a.y + n0, vbytes, bar);
+      } else if (lane == 2) {
+        bulk_g2s(dst + xbytes + 2 * vbytes, a.g + n0, gbytes, bar);
+      } else {
+        bulk_g2s(dst + xbytes + vbytes, a.w + n0, vbytes, bar);
+      }
+    }
+  }
+}
+
 // ---- the Q warp: k_obs_fused's stage loop on the team's ring ------------------------------------------
+// (the first SLOTS stages were requested by fused_q_issue_first)
 template <int NCH, int SLOTS>
 __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, unsigned ring_u, unsigned full_u,
                                             unsigned ready_u, unsigned empty_u, const double* bm, const double* bv,
@@ -165,9 +201,6 @@ __device__ __forceinline__ void fused_q_run(const FusedArgs& a, double* ring, un
       q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = q5[c] = 0.0;
     }
   };
-
-#pragma unroll
-  for (int p = 0; p < kFuStages; ++p) issue(p, p);
 
   int slot = 0, pslot = 0;
   unsigned phase = 0, pphase = 0;
@@ -491,7 +524,7 @@ __device__ __forceinline__ void fused_d_dispatch(int role, const FusedArgs& a, u
 template <int T2, int T0, bool HAS_M, int NCH, int TEAMS, int NQ, int P, int WARPS, int SLOTS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_fused_eval(const FusedArgs a) {
-  pdl_sync();
+  pdl_launch_dependents();
   constexpr int NT = T2 * (T2 + 1) / 2;
   constexpr int NQW = TEAMS * NQ;
   extern __shared__ __align__(16) double sm[];
@@ -516,23 +549,30 @@ k_fused_eval(const FusedArgs a) {
   const int role = is_q ? -1 : dw / TEAMS;
   const bool active = is_q || role < P;
 
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    bm[k] = a.vec[4 + k];
-    bv[k] = 1.0 / a.vec[4 + K + k];
+  // ahead of the wait for k_prep: barriers and the first stages of every Q warp's ring (static inputs only)
+  if (is_q) {
+    const unsigned full_u = bars_u + 8u * (unsigned)(warp * SLOTS * 3);
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < SLOTS; ++p) {
+        mbar_init(full_u + 8 * p, 1);
+        mbar_init(full_u + 8 * SLOTS + 8 * p, 1);
+        mbar_init(full_u + 16 * SLOTS + 8 * p, 1 + P);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    fused_q_issue_first<SLOTS>(a, smem_u32(sm + (size_t)warp * SLOTS * slot_elems), full_u,
+                               (int64_t)blockIdx.x * NQW + warp);
   }
   for (int q = threadIdx.x; q < Q; q += blockDim.x) {
     ghc[q] = a.gh[q];
     ghw[q] = a.gh[Q + q];
   }
-  if (is_q && lane == 0) {
-    const unsigned full_u = bars_u + 8u * (unsigned)(warp * SLOTS * 3);
-#pragma unroll
-    for (int p = 0; p < SLOTS; ++p) {
-      mbar_init(full_u + 8 * p, 1);
-      mbar_init(full_u + 8 * SLOTS + 8 * p, 1);
-      mbar_init(full_u + 16 * SLOTS + 8 * p, 1 + P);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  pdl_wait();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    bm[k] = a.vec[4 + k];
+    bv[k] = 1.0 / a.vec[4 + K + k];
   }
   __syncthreads();
 
