@@ -344,6 +344,25 @@ __device__ __forceinline__ void csr_refill_chunk_body(int chunk, const double* _
   }
 }
 
+// The three block-uniform roles of a count (FILL = 0) or fill (FILL = 1) pass, walked with a grid stride (a
+// conditional export is launched with a capped grid: its usual fate is an early return).
+template <int FILL>
+__device__ __forceinline__ void csr_roles(const double* A, const double* B, const double* L, int Dg, int G, int CG, int nA,
+           int nB, int32_t* cntA, int32_t* chunkcnt, const int32_t* chunkoff, const int32_t* coltot, int32_t* rowcnt,
+           const int32_t* indptr, int32_t* indices, double* data, uint32_t* mask, const MismatchFlag mismatch) {
+  const int total = nA + nB + (int)((2 * (int64_t)G + 7) / 8);
+  for (int vb = blockIdx.x; vb < total; vb += gridDim.x) {
+    if (vb < nA) {
+      csr_A_rows_body<FILL>(vb, A, Dg, cntA, indptr, indices, data, mask, mismatch);
+    } else if (vb < nA + nB) {
+      csr_B_cols_body<FILL>(vb - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
+      __syncthreads();      // the staging tile is reused by the next role of this CTA
+    } else {
+      csr_local_rows_body<FILL>(vb - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
+    }
+  }
+}
+
 // One launch per phase: blocks [0, nA) take the rows of A, the next nB blocks a chunk of B each,
 // the rest the local rows (block-uniform roles; only the B role uses the dynamic shared memory).
 // FILL = 0 count, 1 fill (and record the zero mask), 2 refill: data only with the cached offsets, the
@@ -380,29 +399,23 @@ k_csr_pass(const double* __restrict__ A, const double* __restrict__ B, const dou
   }
   pdl_sync();
   if (run_if && *run_if == 0) return;
-  // a conditional export is launched with a capped grid (its usual fate is the early return above): the
-  // CTAs then walk the block-uniform roles with a grid stride
-  const int total = nA + nB + (int)((2 * (int64_t)G + 7) / 8);
-  for (int vb = bid; vb < total; vb += gridDim.x) {
-    if (vb < nA) {
-      csr_A_rows_body<FILL>(vb, A, Dg, cntA, indptr, indices, data, mask, mismatch);
-    } else if (vb < nA + nB) {
-      csr_B_cols_body<FILL>(vb - nA, B, Dg, G, CG, chunkcnt, chunkoff, cntA, coltot, indptr, indices, data);
-      __syncthreads();      // the staging tile is reused by the next role of this CTA
-    } else {
-      csr_local_rows_body<FILL>(vb - nA - nB, B, L, Dg, G, rowcnt, indptr, indices, data, mask, mismatch);
-    }
-  }
+  csr_roles<FILL>(A, B, L, Dg, G, CG, nA, nB, cntA, chunkcnt, chunkoff, coltot, rowcnt, indptr, indices, data, mask,
+                  mismatch);
 }
 
 // exclusive scan of chunkcnt over chunks, one CTA per column; coltot[c] = column total
+__device__ __forceinline__ void csr_colscan_body(int c, const int32_t* chunkcnt, int32_t* chunkoff, int32_t* coltot,
+                                                 int nchunk, int ncol);
 __global__ void __launch_bounds__(256)
 k_csr_colscan(const int32_t* __restrict__ chunkcnt, int32_t* __restrict__ chunkoff,
               int32_t* __restrict__ coltot, int nchunk, int ncol, const int* __restrict__ run_if) {
   pdl_sync();
   if (run_if && *run_if == 0) return;
+  csr_colscan_body(blockIdx.x, chunkcnt, chunkoff, coltot, nchunk, ncol);
+}
+__device__ __forceinline__ void csr_colscan_body(int c, const int32_t* chunkcnt, int32_t* chunkoff, int32_t* coltot,
+                                                 int nchunk, int ncol) {
   __shared__ int wsum[8];
-  const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int carry = 0;
   for (int s0 = 0; s0 < nchunk; s0 += 256) {
@@ -440,25 +453,35 @@ __global__ void k_csr_global_rowcnt(const int32_t* __restrict__ cntA,
 }
 
 // ---- exclusive scan of rowcnt (n entries) into indptr (n+1 entries), 3 phases --------------------
+__device__ __forceinline__ void scan_sum_body(int vb, const int32_t* cnt, int64_t n, int64_t* blk);
+__device__ __forceinline__ void scan_apply_body(int vb, int nblk, const int32_t* cnt, int64_t n, const int64_t* blk,
+                                                const int64_t* total, int32_t* indptr);
 __global__ void __launch_bounds__(256)
 k_scan_sum(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ blk, const int* __restrict__ run_if) {
   pdl_sync();
   if (run_if && *run_if == 0) return;
+  scan_sum_body(blockIdx.x, cnt, n, blk);
+}
+__device__ __forceinline__ void scan_sum_body(int vb, const int32_t* cnt, int64_t n, int64_t* blk) {
   __shared__ double red[32];
-  const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
+  const int64_t b0 = (int64_t)vb * kScanChunk;
   long long s = 0;
   for (int i = threadIdx.x; i < kScanChunk; i += blockDim.x)
     if (b0 + i < n) s += cnt[b0 + i];
   // counts < 2^31 each and at most 2048 per chunk: exact in double
   const double t = block_sum((double)s, red);
-  if (threadIdx.x == 0) blk[blockIdx.x] = (int64_t)t;
+  if (threadIdx.x == 0) blk[vb] = (int64_t)t;
 }
 
+__device__ __forceinline__ void scan_top_body(int64_t* blk, int nblk, int64_t* total, int64_t* nnz_out);
 __global__ void k_scan_top(int64_t* __restrict__ blk, int nblk, int64_t* __restrict__ total,
                            int64_t* __restrict__ nnz_out, const int* __restrict__ run_if) {
   pdl_sync();
   if (run_if && *run_if == 0) return;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  scan_top_body(blk, nblk, total, nnz_out);
+}
+__device__ __forceinline__ void scan_top_body(int64_t* blk, int nblk, int64_t* total, int64_t* nnz_out) {
   int64_t run = 0;
   for (int i = 0; i < nblk; ++i) {
     const int64_t c = blk[i];
@@ -475,10 +498,14 @@ k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restri
              const int* __restrict__ run_if) {
   pdl_sync();
   if (run_if && *run_if == 0) return;
+  scan_apply_body(blockIdx.x, gridDim.x, cnt, n, blk, total, indptr);
+}
+__device__ __forceinline__ void scan_apply_body(int vb, int nblk, const int32_t* cnt, int64_t n, const int64_t* blk,
+                                                const int64_t* total, int32_t* indptr) {
   __shared__ int wsum[8];
-  const int64_t b0 = (int64_t)blockIdx.x * kScanChunk;
+  const int64_t b0 = (int64_t)vb * kScanChunk;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int64_t carry = blk[blockIdx.x];
+  int64_t carry = blk[vb];
   for (int s0 = 0; s0 < kScanChunk; s0 += 256) {
     const int64_t i = b0 + s0 + threadIdx.x;
     const int c = (i < n) ? cnt[i] : 0;
@@ -500,7 +527,77 @@ k_scan_apply(const int32_t* __restrict__ cnt, int64_t n, const int64_t* __restri
     if (i < n) indptr[i] = (int32_t)(carry + off + v - c);
     carry += tot;
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) indptr[n] = (int32_t)(*total);
+  if (vb == nblk - 1 && threadIdx.x == 0) indptr[n] = (int32_t)(*total);
+}
+
+// ---- the whole export as ONE launch: the conditional export behind a refill ---------------------------
+// A refill is followed by a full export that runs only if the refill found the zero pattern changed.  As four
+// dependent launches its usual fate -- four early returns -- still costs four launch hops per evaluation; as
+// one launch of co-resident CTAs (2 per SM) that walk the same phases between grid-wide barriers it costs one.
+// bar[0]: arrivals (monotonic over the phases of one launch), bar[1]: CTAs that left; the last one resets both.
+// A barrier that does not complete within ~2 s gives up (the export is then wrong, which the caller's
+// status check reports: mismatch stays raised) instead of hanging the device.
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
+  __shared__ int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned seen = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (seen >= target) break;
+      __nanosleep(100);
+    } while (++spins < (1u << 24));
+    ok = (seen >= target);
+    __threadfence();
+  }
+  __syncthreads();
+  return ok != 0;
+}
+__global__ void __launch_bounds__(256)
+k_csr_export_coop(const double* A, const double* B, const double* L, int Dg, int G, int CG, int nA, int nB,
+                  int32_t* cntA, int32_t* chunkcnt, int32_t* chunkoff, int32_t* coltot, int32_t* segbase,
+                  int32_t* rowcnt, int64_t D, int64_t* blk, int nblk, int32_t* indptr, int32_t* indices, double* data,
+                  int64_t* nnz_out, uint32_t* mask, unsigned* bar, const int* __restrict__ run_if) {
+  pdl_sync();
+  if (*run_if == 0) return;
+  const unsigned nc = gridDim.x;
+  unsigned phase = 0;
+  const MismatchFlag none{nullptr, nullptr};
+  bool ok = true;
+  // counts
+  csr_roles<0>(A, B, L, Dg, G, CG, nA, nB, cntA, chunkcnt, nullptr, nullptr, rowcnt, nullptr, nullptr, nullptr, nullptr, none);
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  // column scans (or no groups: zero column totals)
+  if (G > 0) {
+    for (int c = blockIdx.x; c < 2 * Dg; c += nc) { csr_colscan_body(c, chunkcnt, chunkoff, coltot, nB, 2 * Dg); __syncthreads(); }
+  } else if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < 2 * Dg; c += blockDim.x) coltot[c] = 0;
+  }
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  if (blockIdx.x == 0)
+    for (int r = threadIdx.x; r < Dg; r += blockDim.x) rowcnt[r] = cntA[r] + coltot[r] + coltot[Dg + r];
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  for (int vb = blockIdx.x; vb < nblk; vb += nc) { scan_sum_body(vb, rowcnt, D, blk); __syncthreads(); }
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scan_top_body(blk, nblk, blk + nblk, nnz_out);
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  for (int vb = blockIdx.x; vb < nblk; vb += nc) { scan_apply_body(vb, nblk, rowcnt, D, blk, blk + nblk, indptr); __syncthreads(); }
+  ok = ok && grid_barrier(bar, ++phase * nc);
+  // fill (records the zero mask and the segment bases for later refills)
+  if (ok)
+    csr_roles<1>(A, B, L, Dg, G, CG, nA, nB, cntA, segbase, chunkoff, coltot, nullptr, indptr, indices, data, mask, none);
+  // leave: the last CTA resets the barrier words for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(bar + 1, 1u) == nc - 1) {
+      bar[0] = 0;
+      bar[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // Small problems (D <= kIndptrOneCta): row counts of the global rows + exclusive scan + nnz in ONE
@@ -587,6 +684,9 @@ static int ensure_csr_scratch(lrvb_glmm* h) {
   cudaFuncSetAttribute(k_csr_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_csr_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_csr_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_refill_smem(Dg, CG));
+  cudaFuncSetAttribute(k_csr_export_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the grid-barrier words of the one-launch export (the four spare words behind the scan scratch)
+  LRVB_CUDA(cudaMemset(h->csrwork + (size_t)3 * Dg + (size_t)6 * Dg * nchunk, 0, sizeof(int32_t) * 4));
   return LRVB_OK;
 }
 
@@ -627,6 +727,18 @@ static int csr_full_export(lrvb_glmm* h, int32_t* indptr_dev, int32_t* indices_d
   const size_t smem = sizeof(double) * (size_t)CG * (2 * Dg + 1);
 
   const int nA = cdiv(Dg, 8), nB = (G > 0) ? nchunk : 0, nL = (G > 0) ? cdiv(2 * (int64_t)G, 8) : 0;
+  if (run_if && !(getenv("LRVB_CSR_COOP") && getenv("LRVB_CSR_COOP")[0] == '0')) {
+    // the conditional export behind a refill: one launch of co-resident CTAs (two per SM)
+    int32_t* segb = chunkoff + (size_t)2 * Dg * nchunk;
+    unsigned* bar = (unsigned*)(segb + (size_t)2 * Dg * nchunk);
+    LRVB_CUDA(launch_pdl(k_csr_export_coop, dim3(2 * kNumSMs), dim3(256), smem, st, (const double*)h->A,
+                         (const double*)h->B, (const double*)h->L, Dg, G, CG, nA, nB, cntA, chunkcnt, chunkoff, coltot,
+                         segb, h->rowcnt, (int64_t)D, blk, nblk, indptr_dev, indices_dev, data_dev, (int64_t*)nnz_dev,
+                         h->csrmask, bar, run_if));
+    LRVB_CHECK_LAUNCH();
+    h->csr_pattern_valid = 1;
+    return LRVB_OK;
+  }
   // ---- counts: rows of A, columns of B (per chunk) and local rows in one launch ----
   int pass_grid = nA + nB + nL;
   if (run_if && pass_grid > 4 * kNumSMs) pass_grid = 4 * kNumSMs;

@@ -662,6 +662,123 @@ k_spd_inverse(double* __restrict__ S, int n, int* __restrict__ info, int use_sme
 // to n = 234 (K = 115).  The sweep operator keeps the matrix symmetric at every step:
 //   SWP(k):  A_kk <- -1 / A_kk,   A_ik <- A_ik / A_kk,   A_ij <- A_ij - A_ik A_jk / A_kk   (i, j != k)
 // and after all n sweeps A = -S^-1.  Two barriers per pivot, every element touched once per pivot.
+// ---- SPD inverse on many CTAs: blocked Gauss-Jordan sweeps (n > kSpdBlockedMin) ------------------------
+// (profiles/r02_spd_inverse_blocked.log)
+// The one-CTA kernels above are bound by one SM (its registers up to n = 128, its shared memory up to 234,
+// global memory beyond: 5.5 ms at n = 264, ~20 ms at n = 404 = the LRVB covariance of K = 200).  Here the
+// matrix is cut into 32 x 32 tiles and pivot block kb is swept by ONE launch of T x T CTAs, out of place
+// (X -> Y, two buffers in turn; the matrix is at most 2 MB, so it lives in the L2):
+//     Y_kk = P^-1        Y_kj = P^-1 X_kj        Y_ik = -X_ik P^-1        Y_ij = X_ij - X_ik P^-1 X_kj
+// with P = X_kk inverted by one warp of every CTA (lane = row, the block in registers: redundant, but a
+// launch round trip cheaper than publishing it).  After the T sweeps the buffer holds X^-1 (the sweep
+// operator); a last launch symmetrises it into the caller's matrix.  The scalar pivots are those of the
+// unblocked elimination, so "info = k: leading minor k not positive" keeps its meaning.  Indices >= n are
+// padded with the identity.
+constexpr int kSpdBlockedMin = 104;     // measured: equal at n = 104 (158 us), 1.5x at 128, 3.6x at 204, 44x at 404
+__device__ __forceinline__ int gj_invert_block(double (&r)[32], int lane) {
+  int bad = 0;
+#pragma unroll
+  for (int p = 0; p < 32; ++p) {
+    const double d = __shfl_sync(0xffffffffu, r[p], p);
+    if (!(d > 0.0) && !bad) bad = p + 1;      // the same value in every lane
+    const double ip = 1.0 / d;
+    const double f = r[p];                    // a_ip of this lane's row
+    const bool me = (lane == p);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j == p) continue;
+      const double rj = __shfl_sync(0xffffffffu, r[j], p) * ip;     // scaled pivot row
+      r[j] = me ? rj : fma(-f, rj, r[j]);
+    }
+    r[p] = me ? ip : -f * ip;
+  }
+  return bad;
+}
+
+__global__ void __launch_bounds__(256)
+k_spd_gj_step(const double* __restrict__ X, double* __restrict__ Y, int n, int kb, int* __restrict__ info) {
+  pdl_sync();
+  __shared__ double sP[32][33], sA[32][33], sR[32][33], sM[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = kb * 32, i0 = bi * 32, j0 = bj * 32;
+  auto ldx = [&](int i, int j) { return (i < n && j < n) ? X[(size_t)i * n + j] : (i == j ? 1.0 : 0.0); };
+  double c[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = warp * 4 + q;
+    sP[r][lane] = ldx(k0 + r, k0 + lane);
+    sA[r][lane] = ldx(i0 + r, k0 + lane);     // X_ik
+    sR[r][lane] = ldx(k0 + r, j0 + lane);     // X_kj
+    c[q] = ldx(i0 + r, j0 + lane);            // X_ij
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = sP[lane][j];
+    const int bad = gj_invert_block(r, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sP[lane][j] = r[j];
+    if (bad && bi == 0 && bj == 0 && lane == 0 && k0 + bad <= n) atomicCAS(info, 0, k0 + bad);
+  }
+  __syncthreads();
+  double o[4];
+  if (bi == kb && bj == kb) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = sP[warp * 4 + q][lane];
+  } else if (bi == kb) {            // P^-1 X_kj
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const double b = sR[t][lane];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = fma(sP[warp * 4 + q][t], b, o[q]);
+    }
+  } else {
+    double m[4] = {0.0, 0.0, 0.0, 0.0};       // M = X_ik P^-1
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const double b = sP[t][lane];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m[q] = fma(sA[warp * 4 + q][t], b, m[q]);
+    }
+    if (bj == kb) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = -m[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sM[warp * 4 + q][lane] = m[q];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = c[q];
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) {
+        const double b = sR[t][lane];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = fma(-sM[warp * 4 + q][t], b, o[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + warp * 4 + q, j = j0 + lane;
+    if (i < n && j < n) Y[(size_t)i * n + j] = o[q];
+  }
+}
+
+// S = (Z + Z^T) / 2, one thread per pair i <= j (works in place: a pair is read and written by one thread)
+__global__ void __launch_bounds__(256)
+k_spd_gj_finish(const double* Z, double* S, int n) {
+  pdl_sync();
+  const int i = blockIdx.y * 16 + (threadIdx.x >> 4), j = blockIdx.x * 16 + (threadIdx.x & 15);
+  if (i >= n || j >= n || i > j) return;
+  const double v = 0.5 * (Z[(size_t)i * n + j] + Z[(size_t)j * n + i]);
+  S[(size_t)i * n + j] = v;
+  S[(size_t)j * n + i] = v;
+}
+
 constexpr int kSpdPackedMax = 234;
 // One SM's shared-memory bandwidth bounds this kernel (every element is read and written once per
 // pivot: ~n^2 / 2 * 24 B at 128 B / clock); rows are striped over groups of 8 lanes so that the pivot
@@ -1104,16 +1221,25 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
   // (a stream-ordered cudaMallocAsync / cudaFreeAsync pair costs ~0.4 ms here: the default pool returns its
   // memory at every synchronisation)
   int* dinfo = nullptr;
+  double* scratch = nullptr;        // second matrix buffer of the blocked sweeps: 8 per device, round-robin
+  const bool blocked = n > kSpdBlockedMin && !(getenv("LRVB_SPD_BLOCKED") && getenv("LRVB_SPD_BLOCKED")[0] == '0');
   {
     static std::mutex mu;
     static int* words[64] = {nullptr};          // per device: 64 ints
     static unsigned next[64] = {0};
+    static double* bufs[64] = {nullptr};        // per device: 8 matrices of the largest n
     int dev = 0;
     LRVB_CUDA(cudaGetDevice(&dev));
     LRVB_REQUIRE(dev >= 0 && dev < 64, "lrvb_spd_inverse: device ordinal %d not supported", dev);
     std::lock_guard<std::mutex> lock(mu);
     if (!words[dev]) LRVB_CUDA(cudaMalloc((void**)&words[dev], sizeof(int) * 64));
-    dinfo = words[dev] + (next[dev]++ & 63u);
+    const unsigned slot = next[dev]++;
+    dinfo = words[dev] + (slot & 63u);
+    if (blocked) {
+      const size_t nmax = 4 + 2 * (size_t)kMaxK;
+      if (!bufs[dev]) LRVB_CUDA(cudaMalloc((void**)&bufs[dev], sizeof(double) * 8 * nmax * nmax));
+      scratch = bufs[dev] + (size_t)(slot & 7u) * nmax * nmax;
+    }
   }
   size_t smem = sizeof(double) * (2 * (size_t)n + (size_t)n * n);
   int use_smem = 1;
@@ -1121,7 +1247,18 @@ int lrvb_spd_inverse(double* S_dev, int32_t n, int32_t* info_host, void* stream)
     use_smem = 0;
     smem = sizeof(double) * 2 * (size_t)n;
   }
-  if (n <= 128) {
+  if (blocked) {
+    const int T = (n + 31) / 32;
+    LRVB_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), st));
+    double* cur = S_dev;
+    double* oth = scratch;
+    for (int kb = 0; kb < T; ++kb) {
+      LRVB_CUDA(launch_pdl(k_spd_gj_step, dim3(T, T), dim3(256), 0, st, (const double*)cur, oth, (int)n, kb, dinfo));
+      double* t = cur; cur = oth; oth = t;
+    }
+    LRVB_CUDA(launch_pdl(k_spd_gj_finish, dim3((n + 15) / 16, (n + 15) / 16), dim3(256), 0, st, (const double*)cur,
+                         S_dev, (int)n));
+  } else if (n <= 128) {
     const int threads = 8 * ((n + 3) / 4 * 4);     // whole warps: 4 rows of 8 lanes each
     const int nq = (n + 7) / 8;
     cudaError_t le;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes, torch
 from lrvb_b200 import _native as nat
 lib = nat.load()
-for n in (12, 44, 64, 104, 128, 129, 144, 167, 204, 212, 234, 264):
+for n in (12, 44, 64, 65, 104, 128, 129, 144, 167, 204, 212, 234, 264, 300, 404, 516):
     A = torch.randn(n, n, dtype=torch.float64, device="cuda")
     S0 = A @ A.T + n * torch.eye(n, dtype=torch.float64, device="cuda")
     info = ctypes.c_int32()
