@@ -414,6 +414,9 @@ def rooflines(res, wl, peak_tf, traffic):
     else:
         gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
                        "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
+                       "lrvb::k_gram_wide (DMMA.8x8x4, 4-5 tile column blocks against each other, 8 warps x 25 "
+                       "accumulator tiles)" if (K % 8 == 0 and 176 <= K <= 240
+                                                and os.environ.get("LRVB_GRAM_WIDE", "1") != "0") else
                        "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
         roof_gram = {"bound": "tensor", "kernel": gram_kernel,
                      "achieved": N * flops_per_obs / (gms * 1e-3) / 1e12 if gms > 0 else None, "peak": peak_tf,

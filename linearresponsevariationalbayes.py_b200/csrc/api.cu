@@ -9,6 +9,7 @@
 #include "obs_fused.cuh"
 #include "gram_mid.cuh"
 #include "gram_big.cuh"
+#include "gram_wide.cuh"
 #include "fused.cuh"
 
 namespace lrvb {
@@ -250,6 +251,26 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
       h->gram_mid = 1;
       h->gram_grid_x = kNumSMs;
       h->gram_grid_y = 1;
+      npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;
+    } else if (gram_wide_eligible(K) &&
+               (getenv("LRVB_GRAM_WIDE") ? getenv("LRVB_GRAM_WIDE")[0] != '0' : (K >= 176 && K <= 240))) {
+      // default range = where it beats the rectangle kernel (profiles/r02_gram_wide.md: 56 - 66 % against
+      // 49 - 55 % of the DMMA peak for K = 176 .. 240; below, the 4-tile blocks starve the warps and the
+      // staged bytes per DMMA grow; LRVB_GRAM_WIDE=1 forces it for every K >= 96 with K % 8 == 0)
+      // large K, no straddle tile: block-against-block jobs (16 - 25 tiles per warp), 8 warps per SM, only the
+      // column blocks of a job group staged (gram_wide.cuh)
+      const GwPlan pl = gram_wide_plan(K);
+      h->gram_wide = 1;
+      h->gram_grid_x = (int)pl.ctas.size();
+      h->gram_grid_y = (int)pl.groups.size();
+      h->gram_smem = pl.smem;
+      CREATE_TRY(dev_alloc((char**)&h->jobs, sizeof(GwGroup) * pl.groups.size()));
+      CREATE_TRY(dev_alloc((char**)&h->gslots, sizeof(GwCta) * pl.ctas.size()));
+      CREATE_CUDA(cudaMemcpyAsync(h->jobs, pl.groups.data(), sizeof(GwGroup) * pl.groups.size(),
+                                  cudaMemcpyHostToDevice, st));
+      CREATE_CUDA(cudaMemcpyAsync(h->gslots, pl.ctas.data(), sizeof(GwCta) * pl.ctas.size(),
+                                  cudaMemcpyHostToDevice, st));
+      CREATE_CUDA(cudaStreamSynchronize(st));   // pl goes out of scope
       npart = (size_t)h->gram_grid_x * gram_small_shape(K).NT * 64;
     } else {
       // rectangles of the packed triangle dealt to 16-warp CTAs (gram_big.cuh)

@@ -20,6 +20,8 @@
 #include "gram_mid.cuh"
 #define LRVB_GRAM_BIG_KERNELS
 #include "gram_big.cuh"
+#define LRVB_GRAM_WIDE_KERNELS
+#include "gram_wide.cuh"
 #include "fused.cuh"
 
 namespace lrvb {
@@ -931,6 +933,10 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
           set_error("launch_eval: mid-K Gram kernel rejected K = %d / alignment", K);
           return LRVB_ESTATE;
         }
+      } else if (h->gram_wide) {
+        LRVB_CUDA(launch_pdl(k_gram_wide, dim3(h->gram_grid_x), dim3(32 * kGwWarps), h->gram_smem, st,
+            h->X, h->W + 2 * h->ldw, h->ldw, (const GwGroup*)h->jobs, (const GwCta*)h->gslots,
+            h->grampart, N, K, gram_small_shape(K).NT));
       } else {
         LRVB_CUDA(launch_pdl(k_gram_big, dim3(h->gram_grid_x), dim3(32 * kGbWarps), h->gram_smem, st,
             h->X, h->W + 2 * h->ldw, h->ldw, (const GbJob*)h->jobs, (const GbSlot*)h->gslots,
@@ -944,7 +950,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   {
     const int n_loc = h->loc_grid;
     int n_bor = 0, n_gf = 0, NT = 0;
-    const int packed_gram = (h->gram_small || h->gram_mid || one_pass) ? 1 : 0;   // partial layout (n_cta, NT, 64)
+    const int packed_gram = (h->gram_small || h->gram_mid || h->gram_wide || one_pass) ? 1 : 0;   // partial layout (n_cta, NT, 64)
     const int packed_ctas = one_pass ? h->fu_grid : h->gram_grid_x;
     if (order >= 2) {
       if (G > 0) n_bor = cdiv(G, 8 * border_groups_per_warp(G));
@@ -1027,6 +1033,7 @@ void configure_kernels(size_t obs_smem, size_t gram_smem) {
   cudaFuncSetAttribute(k_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
   cudaFuncSetAttribute(k_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, o);
   if (gsm > 0) cudaFuncSetAttribute(k_gram_big, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm);
+  if (gsm > 0) cudaFuncSetAttribute(k_gram_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm);
   cudaGetLastError();
 }
 }  // namespace lrvb
