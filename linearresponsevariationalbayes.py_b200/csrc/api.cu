@@ -151,17 +151,15 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   h->ldw = (N + 7) / 8 * 8;
   CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)h->ldw));
 
-  // observation pass geometry
-  h->obs_tn = (K <= 27) ? 256 : (K <= 54 ? 128 : 64);
-  h->obs_smem = sizeof(double) * ((size_t)h->obs_tn * K + 2 * K + 2 * Q + 2 * h->obs_tn + 32);
+  // observation pass geometry (k_obs, K > 62: 64-row tiles; obs_tn = tile buffers, two when they fit;
+  // LRVB_OBS_NBUF=1 forces one)
   {
-    int per_sm = (int)(220 * 1024 / h->obs_smem);
-    if (per_sm > 768 / h->obs_tn) per_sm = 768 / h->obs_tn;   // __launch_bounds__(256, 3)
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int64_t nt = (N + h->obs_tn - 1) / h->obs_tn;
-    int64_t gmax = (int64_t)kNumSMs * per_sm;
-    h->obs_grid = (int)(nt < gmax ? nt : gmax);
+    const size_t tile = sizeof(double) * 64 * (size_t)K, extra = sizeof(double) * (2 * (size_t)Q + 32);
+    h->obs_tn = (2 * tile + extra <= 220 * 1024) ? 2 : 1;
+    if (getenv("LRVB_OBS_NBUF") && getenv("LRVB_OBS_NBUF")[0] == '1') h->obs_tn = 1;
+    h->obs_smem = h->obs_tn * tile + extra;
+    int64_t nt = (N + 63) / 64;
+    h->obs_grid = (int)(nt < kNumSMs ? nt : kNumSMs);
     if (h->obs_grid < 1) h->obs_grid = 1;
   }
   if (K <= kOfMaxK) {

@@ -99,151 +99,226 @@ __device__ __forceinline__ void gh_node(double t, double c, double wq, GHSums& s
   }
 }
 
-// One thread per observation of a TN-row tile staged in shared memory (blockDim.x == TN).
+// Observation pass for K > 62 (the fused kernels of obs_fused.cuh / fused.cuh cover K <= 62).  A CTA of 8
+// warps walks 64-row tiles of X, double-buffered in shared memory with cp.async (tile t + 1 is in flight while
+// tile t is computed; one buffer when two do not fit, K > 214).  Per tile every warp owns 8 rows:
+//   A. z_mean / z_var dot products with lane = column (coalesced, conflict-free), then ONE transposing
+//      butterfly (16 exchanges instead of 16 x 5) that leaves row rr's two sums in lanes 4 rr .. 4 rr + 3;
+//   B. quadrature with lane = (row, node slot): the 4 lanes of a row split the Q nodes (branch-free exp /
+//      log1p / reciprocal of obs_fused.cuh), two exchanges combine the six sums; lane 4 rr writes the row's
+//      weights l_m, l_v, l_mm, l_mv, l_vv;
+//   C. gradient partials X^T l_m, S^T l_v with lane = column again (weights broadcast by shuffle), kept in
+//      registers across tiles; per-CTA fixed-order reduction at the end (no atomics).
+// The first version (one thread per row, 64-thread CTAs, synchronous tile loads) ran at 1.5 TB/s with 4
+// warps per SM; profiles/r02_launches_c4.md.
+constexpr int kObsTile = 64;       // rows per tile
+constexpr int kObsRows = 8;        // rows per warp and tile
+constexpr int kObsMaxChunks = 8;   // 32-column chunks (K <= 256)
+
 template <int ORDER>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 1)
 k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
       const double* __restrict__ w, const double* __restrict__ vec, const double* __restrict__ gh,
       double* __restrict__ W, double* __restrict__ klpart, double* __restrict__ gradpart,
-      int64_t N, int64_t ldw, int K, int G, int Q) {
+      int64_t N, int64_t ldw, int K, int G, int Q, int nbuf) {
   extern __shared__ __align__(16) double sm[];
-  const int TN = blockDim.x;
-  const int tid = threadIdx.x;
-  double* xs = sm;                  // TN*K
-  double* bm = xs + (size_t)TN * K; // K   E[beta]
-  double* bv = bm + K;              // K   Var[beta] = 1/info
-  double* ghc = bv + K;             // Q   sqrt(2) x_q
-  double* ghw = ghc + Q;            // Q   w_q / sqrt(pi)
-  double* lms = ghw + Q;            // TN
-  double* lvs = lms + TN;           // TN
-  double* red = lvs + TN;           // 32
-
-  for (int k = tid; k < K; k += TN) {
-    bm[k] = vec[4 + k];
-    bv[k] = 1.0 / vec[4 + K + k];
-  }
-  for (int q = tid; q < Q; q += TN) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t tile_elems = (size_t)kObsTile * K;
+  double* xs = sm;                          // nbuf x 64 x K
+  double* ghc = xs + nbuf * tile_elems;     // Q   sqrt(2) x_q
+  double* ghw = ghc + Q;                    // Q   w_q / sqrt(pi)
+  double* red = ghw + Q;                    // 32
+  for (int q = tid; q < Q; q += blockDim.x) {
     ghc[q] = gh[q];
     ghw[q] = gh[Q + q];
   }
+  const int nch = (K + 31) >> 5;
+  double bmr[kObsMaxChunks], bvr[kObsMaxChunks];     // E[beta], Var[beta] of this lane's columns
+  double gm[kObsMaxChunks], gv[kObsMaxChunks];
+#pragma unroll
+  for (int c = 0; c < kObsMaxChunks; ++c) {
+    const int k = 32 * c + lane;
+    bmr[c] = (c < nch && k < K) ? vec[4 + k] : 0.0;
+    bvr[c] = (c < nch && k < K) ? 1.0 / vec[4 + K + k] : 0.0;
+    gm[c] = gv[c] = 0.0;
+  }
   const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
-
-  // bank-conflict skew for the row-per-thread reads of the tile (row stride K doubles)
-  int gcd16 = 1;
-  while (gcd16 < 16 && (K % (gcd16 * 2)) == 0) gcd16 *= 2;
-  int skew = ((tid & 15) * gcd16) >> 4;
-  if (skew >= K) skew = 0;
-
-  // gradient column ownership
-  const bool caseA = (K <= TN);
-  const int P = caseA ? TN / K : 1;
-  const int ncol = caseA ? 1 : (K + TN - 1) / TN;
-  const int colA = caseA ? tid % K : tid;
-  const int partA = caseA ? tid / K : 0;
-  double gm[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};
   double klacc = 0.0;
+  const int rr = lane >> 2, ns = lane & 3;          // quadrature role: row of the warp, node slot
 
-  const int64_t ntiles = (N + TN - 1) / TN;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t n0 = tile * TN;
-    const int rows = (int)((N - n0 < TN) ? (N - n0) : TN);
-    __syncthreads();  // previous tile fully consumed (also orders the bm/bv/gh fill)
-    tile_load_async(xs, X + n0 * K, (int64_t)rows * K);
-    cp_async_commit_wait_all();
+  const int64_t ntiles = (N + kObsTile - 1) / kObsTile;
+  auto load_tile = [&](int64_t tile, int buf) {
+    const int64_t n0 = tile * kObsTile;
+    const int rows = (int)((N - n0 < kObsTile) ? (N - n0) : kObsTile);
+    tile_load_async(xs + buf * tile_elems, X + n0 * K, (int64_t)rows * K);
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = (nbuf == 2) ? (it & 1) : 0;
+    const int64_t n0 = tile * kObsTile;
+    const int rows = (int)((N - n0 < kObsTile) ? (N - n0) : kObsTile);
+    // this lane's row of the quadrature phase: its group's random effect, response and weight are requested
+    // now (two dependent global round trips) and consumed after the dot products
+    const int64_t nq = n0 + warp * kObsRows + rr;
+    const bool rvalid = warp * kObsRows + rr < rows;
+    double u_m = 0.0, u_i = 1.0, wn = 0.0, yn = 0.0;
+    if (rvalid) {
+      const int gi = g[nq];
+      u_m = vec[um0 + gi];
+      u_i = vec[ui0 + gi];
+      wn = w ? w[nq] : 1.0;
+      yn = y[nq];
+    }
+    if (nbuf == 2) {
+      if (tile + gridDim.x < ntiles) load_tile(tile + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      if (it > 0) load_tile(tile, 0);      // the end-of-tile barrier of the previous iteration freed the buffer
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    }
     __syncthreads();
+    const double* xb = xs + buf * tile_elems + (size_t)(warp * kObsRows) * K;
+    const int wrows = rows - warp * kObsRows;       // valid rows of this warp (may be <= 0)
 
+    // A. partial dot products of 8 rows; v[2 r] = z_mean part, v[2 r + 1] = z_var part
+    double v[2 * kObsRows];
+#pragma unroll
+    for (int r = 0; r < kObsRows; ++r) {
+      double am = 0.0, av = 0.0;
+      if (r < wrows) {
+        const double* xr = xb + (size_t)r * K + lane;
+#pragma unroll
+        for (int c = 0; c < kObsMaxChunks; ++c)
+          if (c < nch && 32 * c + lane < K) {
+            const double x = xr[32 * c];
+            am = fma(x, bmr[c], am);
+            av = fma(x * x, bvr[c], av);
+          }
+      }
+      v[2 * r] = am;
+      v[2 * r + 1] = av;
+    }
+    // transposing butterfly: after the step with mask m a lane keeps the half of its values selected by
+    // (lane & m); value index bits 3..0 follow lane bits 4..1, so lane L ends with value (L >> 1) & 15
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool hi = lane & 16;
+      const double send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool hi = lane & 8;
+      const double send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool hi = lane & 4;
+      const double send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+      const bool hi = lane & 2;
+      const double send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    // lanes with ns < 2 hold row rr's z_mean sum, the others its z_var sum: swap across the pair
+    const double other = __shfl_xor_sync(0xffffffffu, v[0], 2);
+    double zm = (ns < 2) ? v[0] : other, zv = (ns < 2) ? other : v[0];
+
+    // B. quadrature: lane (rr, ns) takes nodes ns, ns + 4, ...
     double lm = 0.0, lv = 0.0;
-    if (tid < rows) {
-      const int64_t n = n0 + tid;
-      const int gi = g[n];
-      double zm = vec[um0 + gi];
-      double zv = 1.0 / vec[ui0 + gi];
-      const double* xr = xs + (size_t)tid * K;
-      for (int k = skew; k < K; ++k) {
-        const double x = xr[k];
-        zm = fma(x, bm[k], zm);
-        zv = fma(x * x, bv[k], zv);
-      }
-      for (int k = 0; k < skew; ++k) {
-        const double x = xr[k];
-        zm = fma(x, bm[k], zm);
-        zv = fma(x * x, bv[k], zv);
-      }
-      const double zs = sqrt(zv);
-      GHSums s = {0, 0, 0, 0, 0, 0};
-      for (int q = 0; q < Q; ++q) {
-        const double c = ghc[q];
-        gh_node<ORDER>(fma(zs, c, zm), c, ghw[q], s);
-      }
-      const double wn = w ? w[n] : 1.0;
-      const double yn = y[n];
-      klacc += wn * (yn * zm - s.A);
-      if (ORDER >= 1) {
-        const double h = 0.5 / zs;
-        lm = wn * (yn - s.Am);
-        lv = -wn * s.As * h;
-        W[n] = lm;
-        W[ldw + n] = lv;
-        if (ORDER >= 2) {
-          W[2 * ldw + n] = -wn * s.Amm;
-          W[3 * ldw + n] = -wn * s.Ams * h;
-          // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
-          W[4 * ldw + n] = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
+    {
+      const int64_t n = nq;
+      GHSumsF s = {0, 0, 0, 0, 0, 0};
+      double zs = 1.0;
+      if (rvalid) {
+        zm += u_m;
+        zv += 1.0 / u_i;
+        zs = sqrt(zv);
+        for (int q = ns; q < Q; q += 4) {
+          const double c = ghc[q];
+          gh_node_f<ORDER>(fma(zs, c, zm), c, ghw[q], s);
         }
       }
-    }
-    if (ORDER >= 1) {
-      lms[tid] = lm;
-      lvs[tid] = lv;
-      __syncthreads();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < ncol) {
-          const int k = colA + c * TN;
-          if (k < K && partA < P) {
-            double am = 0.0, av = 0.0;
-            for (int r = partA; r < rows; r += P) {
-              const double x = xs[(size_t)r * K + k];
-              am = fma(x, lms[r], am);
-              av = fma(x * x, lvs[r], av);
+      for (int m = 1; m <= 2; m <<= 1) {
+        s.A += __shfl_xor_sync(0xffffffffu, s.A, m);
+        if (ORDER >= 1) {
+          s.Am += __shfl_xor_sync(0xffffffffu, s.Am, m);
+          s.As += __shfl_xor_sync(0xffffffffu, s.As, m);
+        }
+        if (ORDER >= 2) {
+          s.Amm += __shfl_xor_sync(0xffffffffu, s.Amm, m);
+          s.Ams += __shfl_xor_sync(0xffffffffu, s.Ams, m);
+          s.Ass += __shfl_xor_sync(0xffffffffu, s.Ass, m);
+        }
+      }
+      if (rvalid) {
+        if (ns == 0) klacc += wn * (yn * zm - s.A);
+        if (ORDER >= 1) {
+          const double h = 0.5 / zs;
+          lm = wn * (yn - s.Am);
+          lv = -wn * s.As * h;
+          if (ns == 0) {
+            W[n] = lm;
+            W[ldw + n] = lv;
+            if (ORDER >= 2) {
+              W[2 * ldw + n] = -wn * s.Amm;
+              W[3 * ldw + n] = -wn * s.Ams * h;
+              // l_vv = -(A_ss / (4 z_v) - A_s / (4 z_s^3))
+              W[4 * ldw + n] = -wn * (s.Ass - s.As / zs) / (4.0 * zv);
             }
-            gm[c] += am;
-            gv[c] += av;
           }
         }
       }
     }
+    // C. gradient partials, lane = column
+    if (ORDER >= 1) {
+#pragma unroll
+      for (int r = 0; r < kObsRows; ++r) {
+        const double lmr = __shfl_sync(0xffffffffu, lm, 4 * r), lvr = __shfl_sync(0xffffffffu, lv, 4 * r);
+        if (r < wrows) {
+          const double* xr = xb + (size_t)r * K + lane;
+#pragma unroll
+          for (int c = 0; c < kObsMaxChunks; ++c)
+            if (c < nch && 32 * c + lane < K) {
+              const double x = xr[32 * c];
+              gm[c] = fma(x, lmr, gm[c]);
+              gv[c] = fma(x * x, lvr, gv[c]);
+            }
+        }
+      }
+    }
+    __syncthreads();   // the buffer is refilled by the next iteration's load
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 
   const double kl = block_sum(klacc, red);
   if (tid == 0) klpart[blockIdx.x] = kl;
   if (ORDER >= 1) {
-    // layout (2K, n_cta): column-major over CTAs so the finishing reduce reads contiguously
-    double* gp = gradpart + blockIdx.x;
-    const size_t gs = gridDim.x;
-    if (caseA) {
-      __syncthreads();
-      double* buf = xs;  // P*K*2 <= TN*K*... needs 2*P*K <= TN*K  (K >= 2) or falls in lms
-      // stage [part][2][K]; for K == 1 use lms/lvs-sized scratch carefully
-      if (partA < P) {
-        buf[(size_t)partA * 2 * K + colA] = gm[0];
-        buf[(size_t)partA * 2 * K + K + colA] = gv[0];
-      }
-      __syncthreads();
-      for (int k = tid; k < 2 * K; k += TN) {   // 2K may exceed the CTA size (K in 33..64, TN = 64)
-        double s = 0.0;
-        for (int p = 0; p < P; ++p) s += buf[(size_t)p * 2 * K + k];
-        gp[(size_t)k * gs] = s;
-      }
-    } else {
+    // per-warp partials -> shared memory -> fixed-order sum over the 8 warps; layout (2K, n_cta)
+    __syncthreads();
+    double* buf = xs;      // 8 x 2K <= 64 x K
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k = tid + c * TN;
-        if (c < ncol && k < K) {
-          gp[(size_t)k * gs] = gm[c];
-          gp[(size_t)(K + k) * gs] = gv[c];
-        }
+    for (int c = 0; c < kObsMaxChunks; ++c) {
+      const int k = 32 * c + lane;
+      if (c < nch && k < K) {
+        buf[(size_t)warp * 2 * K + k] = gm[c];
+        buf[(size_t)warp * 2 * K + K + k] = gv[c];
       }
+    }
+    __syncthreads();
+    const size_t gs = gridDim.x;
+    for (int k = tid; k < 2 * K; k += blockDim.x) {
+      double s = 0.0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) s += buf[(size_t)p * 2 * K + k];
+      gradpart[(size_t)k * gs + blockIdx.x] = s;
     }
   }
 }
@@ -899,8 +974,8 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   if (N > 0) {
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
 #define LRVB_OBS(O)                                                                          \
-  k_obs<O><<<h->obs_grid, h->obs_tn, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
-                                                         h->W, h->klpart, h->gradpart, N, h->ldw, K, G, Q)
+  k_obs<O><<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
+                                                   h->W, h->klpart, h->gradpart, N, h->ldw, K, G, Q, h->obs_tn)
     if (order == 0) LRVB_OBS(0);
     else if (order == 1) LRVB_OBS(1);
     else LRVB_OBS(2);

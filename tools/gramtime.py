@@ -7,7 +7,7 @@ import torch
 import lrvb_b200 as vb
 from lrvb_b200 import _native as nat
 
-def run(N, K, G=1000, Q=4):
+def run(N, K, G=1000, Q=int(os.environ.get("GT_Q", "4"))):
     X = torch.randn(N, K, dtype=torch.float64, device="cuda")
     g = torch.repeat_interleave(torch.arange(G), N // G).cuda()
     y = (torch.rand(N, device="cuda") < 0.5).double()
