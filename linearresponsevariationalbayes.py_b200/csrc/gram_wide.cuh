@@ -28,7 +28,10 @@
 namespace lrvb {
 
 constexpr int kGwWarps = 8;
-constexpr int kGwMaxBlk = 8;       // distinct column blocks a CTA may stage
+#ifndef LRVB_GW_MAXBLK
+#define LRVB_GW_MAXBLK 8
+#endif
+constexpr int kGwMaxBlk = LRVB_GW_MAXBLK;   // distinct column blocks a CTA may stage
 constexpr int kGwBuffers = 3;
 constexpr int kGwBlkTiles = 5;     // largest block (tiles); a job has <= 5 x 5 accumulator tiles
 constexpr size_t kGwSmemCap = 225 * 1024;
