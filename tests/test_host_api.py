@@ -258,3 +258,24 @@ def test_ef_numeric_integration_helpers_host():
     assert abs(ef.dirichlet_prior(np.array([2.0, 3.0]), np.array([-1.0, -0.5])) - (-1.0 - 1.0)) < 1e-15
     dp = ef.get_e_dp_prior_logitnorm_approx(3.0, means, infos, gx, gw)
     np.testing.assert_allclose(dp, 2.0 * el1)
+
+
+def test_gram_wide_plan_covers_every_packed_tile_once(tmp_path):
+    """The host planner of k_gram_wide (csrc/gram_wide.cuh): for every K it can serve (96 .. 256, K % 8 == 0)
+    each tile (i <= j) of the packed [x | s] triangle belongs to exactly one warp job, the staged column
+    offsets of a job point at blocks with the right X columns / class, the weight row follows the classes,
+    and every job group fits its shared-memory budget.  Host-only: the checker is compiled with nvcc here and
+    launches nothing."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "gwplan")
+    subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                    os.path.join(root, "tools", "gram_wide_plan_check.cu")], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "plan ok" in out.stdout
+    assert "K=200 T2=50 groups= 7 ctas=148 live=1275" in out.stdout
