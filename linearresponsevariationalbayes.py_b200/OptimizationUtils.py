@@ -158,6 +158,7 @@ def minimize_objective_newton(objective, init_x, maxiter=50, gtol=1e-8, disp=Fal
             break
         x = xn
     objective._set_par(x, "free")
+    objective.par        # an optimiser leaves the optimum in par (read here once: the only host copy of the run)
     res = sp.optimize.OptimizeResult(
         x=x if want_torch else x.cpu().numpy(), fun=kl, success=converged, message=message, nit=it,
         nfev=nfev, njev=njev, nhev=nhev, grad_inf_norm=gmax)

@@ -106,12 +106,33 @@ class Objective(object):
                 "lrvb_b200.Objective differentiates device models only (e.g. GLMM.LogisticGLMM); "
                 "got %r. Arbitrary Python callables need autograd, which this CUDA library "
                 "does not provide (no CPU fallback)." % (fun,))
-        self.par = par
+        self._par = par
+        self._pending = None        # (device copy of the point, coords): par is filled in on first access
         self.fun = fun
         self.model = fun
         self.preconditioner = None
         self.logger = Logger()
         self._par_key, self._par_coords = None, None
+
+    @property
+    def par(self):
+        """The ModelParamsDict, holding the last evaluation point (:142-150).  For CUDA-tensor input the point
+        stays on the device (a device-side copy is kept) and is brought to the host only when ``par`` is
+        read: an optimiser or CG loop over device tensors never synchronises for it."""
+        if self._pending is not None:
+            x, coords = self._pending
+            self._pending = None
+            xh = _host(x).reshape(-1)
+            if coords == "free":
+                self._par.set_free(xh)
+            else:
+                self._par.set_vector(xh)
+        return self._par
+
+    @par.setter
+    def par(self, value):
+        self._par = value
+        self._pending = None
 
     def invalidate(self):
         """Forget the cached evaluation.  The "already evaluated at this point?" check compares numpy input
@@ -130,11 +151,15 @@ class Objective(object):
         key = getattr(self.model, "_cache", {}).get("x")
         if key is not None and self._par_key is key and self._par_coords == coords:
             return
-        xh = _host(x).reshape(-1)
-        if coords == "free":
-            self.par.set_free(xh)
+        if is_torch(x) and x.is_cuda:
+            self._pending = (x.detach().clone(), coords)
         else:
-            self.par.set_vector(xh)
+            self._pending = None
+            xh = _host(x).reshape(-1)
+            if coords == "free":
+                self._par.set_free(xh)
+            else:
+                self._par.set_vector(xh)
         self._par_key, self._par_coords = key, coords
 
     def _value(self, x, coords):

@@ -296,3 +296,22 @@ def test_no_observations(vb):
     np.testing.assert_array_equal(H.indices, He.indices)
     assert_close(H.data, He.data, scale=np.abs(He.data).max() * 1e-6, what="hessian data")
     assert np.all(model.weight_cross_matvec(np.zeros(0)).cpu().numpy() == 0.0)
+
+
+def test_par_follows_a_device_point_lazily(vb):
+    """For CUDA-tensor input the evaluation point stays on the device; ``objective.par`` is filled in when
+    it is read (the reference contract -- par equals the last evaluation point, SparseObjectives.py:142-150
+    -- holds at every read)."""
+    import torch
+    case = make_case(**CASES["c1"])
+    model = make_model(vb, case)
+    obj = vb.Objective(model.glmm_par, model)
+    x = case["free"]
+    xt = torch.from_numpy(x).cuda()
+    obj.fun_free_grad(xt)
+    assert obj._pending is not None                      # nothing was copied to the host yet
+    assert_close(obj.par.get_free(), x, what="par.get_free after a device evaluation")
+    assert obj._pending is None
+    x2 = x + 0.01
+    obj.fun_free(x2)                                     # host input: par is set immediately
+    assert_close(model.glmm_par.get_free(), x2, what="par.get_free after a host evaluation")
