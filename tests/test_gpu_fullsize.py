@@ -1,7 +1,7 @@
 """GPU parity at the sizes bench.py actually runs: BASELINE.json configs[1] at
 its full size (C2: N=1M, K=20, G=10k), a slice of configs[2] wide enough for the three-phase row-pointer
-scan of the CSR export (D > 256k), and a K=200 case (configs[3]'s width: rectangle Gram kernel, separate
-observation / group kernels, global-memory SPD inverse).  Same tolerance as everywhere: 1e-9 relative /
+scan of the CSR export (D > 256k), and a K=200 case (configs[3]'s width: k_gram_wide, the wide-model
+observation kernel + k_group, blocked multi-CTA SPD inverse).  Same tolerance as everywhere: 1e-9 relative /
 1e-12 absolute, sparsity pattern bit-exact."""
 import numpy as np
 import pytest

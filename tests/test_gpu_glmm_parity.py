@@ -63,6 +63,11 @@ CASES = {
     "k128_wide_ring_wrap": dict(N=40013, K=128, G=40, Q=4, seed=40),
     "k200_wide_ragged": dict(N=3010, K=200, G=30, Q=4, seed=41, ragged=True, weights=True),
     "k184_wide_default": dict(N=2400, K=184, G=24, Q=4, seed=42),
+    # wide-model observation kernel (K > 62): node slots with unequal node counts (Q = 6: 2, 2, 1, 1), an empty
+    # slot (Q = 3), more than two nodes per slot (Q = 13); ragged tiles, weights
+    "k80_q6": dict(N=1003, K=80, G=10, Q=6, seed=43, weights=True),
+    "k65_q3": dict(N=700, K=65, G=7, Q=3, seed=44),
+    "k96_q13": dict(N=1500, K=96, G=15, Q=13, seed=45, ragged=True),
 }
 
 
