@@ -259,6 +259,7 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
       // column blocks of a job group staged (gram_wide.cuh)
       const GwPlan pl = gram_wide_plan(K);
       h->gram_wide = 1;
+      if (getenv("LRVB_GROUP_OVERLAP") && getenv("LRVB_GROUP_OVERLAP")[0] == '0') h->group_overlap = 0;
       h->gram_grid_x = (int)pl.ctas.size();
       h->gram_grid_y = (int)pl.groups.size();
       h->gram_smem = pl.smem;

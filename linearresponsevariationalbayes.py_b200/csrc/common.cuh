@@ -255,6 +255,7 @@ struct lrvb_glmm {
   int gram_tn = 0, gram_grid_x = 0, gram_grid_y = 0, gram_jobs = 0;   // grid_y = job groups
   size_t gram_smem = 0;
   int gram_small = 0;         // K <= 20: packed whole-triangle-per-warp kernel (gram_small.cuh)
+  int group_overlap = 1;      // k_group on the side stream behind k_gram_wide (LRVB_GROUP_OVERLAP=0: serial)
   int gram_wide = 0;          // K >= 96, K % 8 == 0: block jobs of 4-5 tiles, 8 warps x 255 registers (gram_wide.cuh);
                               // jobs = GwGroup[], gslots = GwCta[gram_grid_x]
   void* jobs = nullptr;            // device GbJob[gram_jobs]   (gram_big.cuh, K > 20)

@@ -959,6 +959,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   LRVB_CHECK_LAUNCH();
 
   int n_obs_cta = 0;
+  bool group_overlap = false;
   int64_t fix_rpw = 0;       // rows per warp of the fused producer whose straddling-group pieces sit in bval
   const bool one_pass = h->fused2 && order >= 2 && N > 0;
   h->ev_gram = 0;
@@ -1027,8 +1028,15 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
   }
   n_obs_cta = (N > 0) ? h->obs_grid : 0;
 
-  // (the Gram kernel fills every SM, so the per-group pass runs before it on the same stream)
-  if (order >= 1 && G > 0) {
+  // The per-group pass runs before the Gram kernel on the same stream -- except under k_gram_wide: its CTA (256
+  // threads x 200 registers, one per SM) leaves room for exactly one k_group CTA (48 registers, no shared
+  // memory) per SM, and the two kernels want different things (DMMA pipe at 22 % of the issue slots against
+  // L2 / HBM latency), so k_group goes to the handle's side stream, is launched AFTER the Gram kernel and hides
+  // behind it (C4: 4.8 ms of the step; LRVB_GROUP_OVERLAP=0 restores the serial order)
+  group_overlap = h->gram_wide && order >= 2 && N > 0 && G > 0 && h->group_overlap;
+  if (group_overlap) {
+    LRVB_CUDA(cudaEventRecord(h->ev_fork, st));       // k_obs has written W
+  } else if (order >= 1 && G > 0) {
     const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
     cudaStream_t gs = st;
     if (order == 1) k_group<1><<<ggrid, 256, 0, gs>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
@@ -1060,6 +1068,14 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
             h->grampart, N, K, h->gram_tn, h->gram_grid_y, h->gram_grid_x / h->gram_grid_y));
       }
       LRVB_CHECK_LAUNCH();
+      if (group_overlap) {
+        const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
+        LRVB_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        k_group<2><<<ggrid, 256, 0, h->side>>>(h->X, h->W, h->gptr, h->gsc, h->BR, h->ldw, K, G);
+        LRVB_CHECK_LAUNCH();
+        LRVB_CUDA(cudaEventRecord(h->ev_join, h->side));
+        LRVB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+      }
       if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[3], st));
     }
   }
