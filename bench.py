@@ -415,7 +415,7 @@ def rooflines(res, wl, peak_tf, traffic):
         gram_kernel = ("lrvb::k_gram_small (DMMA.8x8x4, packed [x|s] triangle per warp)" if K < 16 else
                        "lrvb::k_gram_mid (DMMA.8x8x4, packed [x|s] triangle per warp / warp team)" if K <= 104 else
                        "lrvb::k_gram_wide (DMMA.8x8x4, 4-5 tile column blocks against each other, 8 warps x 25 "
-                       "accumulator tiles)" if (K % 8 == 0 and 176 <= K <= 240
+                       "accumulator tiles; k_group runs beside it on a side stream and is inside kernel_ms)" if (K % 8 == 0 and 176 <= K <= 240
                                                 and os.environ.get("LRVB_GRAM_WIDE", "1") != "0") else
                        "lrvb::k_gram_big (DMMA.8x8x4, packed [x|s] rectangles)")
         roof_gram = {"bound": "tensor", "kernel": gram_kernel,
@@ -756,7 +756,9 @@ def run_ours(args, wl):
         cov["cg"] = cov_cg_entry(ctx, res)
     # warm-up of the host path: the pinned staging blocks of torch's caching host allocator (three 14 MB
     # blocks rotate at C2) are created by cudaHostAlloc calls of several milliseconds each the first time
-    e2e = e2e_measure(ctx, res, min(args.steps, 50 if K <= 64 else 2), max(args.warmup, 10) if K <= 64 else 1)
+    # wide models move GBs per step: fewer steps, but enough warm-up that the rotating pinned result blocks
+    # (one is created while the previous result is still alive) exist before the timed steps
+    e2e = e2e_measure(ctx, res, min(args.steps, 50 if K <= 64 else 3), max(args.warmup, 10) if K <= 64 else 3)
     parity = parity_single(ctx, res, wl) if world == 1 else parity_sharded(ctx, res)
 
     line = None
