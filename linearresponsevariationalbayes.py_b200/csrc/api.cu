@@ -61,7 +61,7 @@ int lrvb_version(void) { return 100; }
 int lrvb_glmm_destroy(lrvb_glmm* h) {
   if (!h) return LRVB_OK;
   void* ptrs[] = {h->gh, h->gptr, h->vec, h->W, h->klpart, h->gradpart, h->gsc, h->BR, h->locpart, h->fin_counter, h->fin_pre,
-                  h->jobs, h->gslots, h->grampart, h->bval, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork, h->csrmask,
+                  h->jobs, h->gslots, h->grampart, h->bval, h->wc_scratch, h->B, h->L, h->gradl, h->outg, h->rowcnt, h->scanblk, h->csrwork, h->csrmask,
                   h->cgbuf, h->hvppart, h->dotpart, h->scal, h->flags, h->Linv, h->T,
                   h->schurpart};
   for (void* p : ptrs)

@@ -236,6 +236,7 @@ struct lrvb_glmm {
   size_t of_smem = 0;
   int64_t of_rows_per_warp = 0;
   double* bval = nullptr;     // (of_grid * of_warps, 2, 5 + 4K) head / tail pieces of straddling groups
+  double* wc_scratch = nullptr;   // (2, ldw) l_m, l_v of a weight-cross-Hessian pass for K > 62 (allocated on first use)
   // one-slot variant of the fused observation pass for the evaluation (larger K: more warps per SM)
   int of1_grid = 0, of1_warps = 0;
   size_t of1_smem = 0;

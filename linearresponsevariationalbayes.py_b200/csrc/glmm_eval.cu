@@ -362,6 +362,127 @@ k_obs(const double* __restrict__ X, const double* __restrict__ y, const int32_t*
   }
 }
 
+// Influence of every observation for wide models (K > 62): out[n] = (C^T v)_n = -(l_m dm_n + l_v dv_n) with unit
+// weight (sensitivity.cu: lrvb_glmm_weight_cross_rmatvec), dm_n = x_n . v_bm + v_um[g_n], dv_n = x_n^2 . (v_bi
+// dvar/dfree) + v_ui[g_n] dvar_u/dfree.  The tile walk of k_obs with FOUR dot products per row: the transposing
+// butterfly takes 8 rows x 4 sums = 32 values to one per lane (31 exchanges), lane 4 rr + i ends with sum i of
+// row rr, and the four lanes of a row share them by three shuffles; then the order-1 quadrature of k_obs.
+__global__ void __launch_bounds__(256, 1)
+k_obs_influence_wide(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ g,
+                     const double* __restrict__ vec, const double* __restrict__ gh, const double* __restrict__ v,
+                     double* __restrict__ out, int64_t N, int K, int G, int Q, int nbuf,
+                     lrvb_glmm_bounds bd, int vecmode) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t tile_elems = (size_t)kObsTile * K;
+  double* xs = sm;
+  double* ghc = xs + nbuf * tile_elems;
+  double* ghw = ghc + 4 * ((Q + 3) >> 2);
+  const int npl = (Q + 3) >> 2;
+  for (int q = tid; q < Q; q += blockDim.x) {
+    const int at = (q & 3) * npl + (q >> 2);
+    ghc[at] = gh[q];
+    ghw[at] = gh[Q + q];
+  }
+  const int nch = (K + 31) >> 5;
+  double bmr[kObsMaxChunks], bvr[kObsMaxChunks], vmr[kObsMaxChunks], vvr[kObsMaxChunks];
+#pragma unroll
+  for (int c = 0; c < kObsMaxChunks; ++c) {
+    const int k = 32 * c + lane;
+    const bool in = c < nch && k < K;
+    const double ik = in ? vec[4 + K + k] : 1.0;
+    bmr[c] = in ? vec[4 + k] : 0.0;
+    bvr[c] = in ? 1.0 / ik : 0.0;
+    vmr[c] = in ? v[4 + k] : 0.0;
+    vvr[c] = in ? v[4 + K + k] * (-1.0 / (ik * ik)) * (vecmode ? 1.0 : ik - bd.beta_info) : 0.0;
+  }
+  const int64_t um0 = 4 + 2 * (int64_t)K, ui0 = um0 + G;
+  const int rr = lane >> 2, ns = lane & 3;
+  const int64_t ntiles = (N + kObsTile - 1) / kObsTile;
+  auto load_tile = [&](int64_t tile, int buf) {
+    const int64_t n0 = tile * kObsTile;
+    const int rows = (int)((N - n0 < kObsTile) ? (N - n0) : kObsTile);
+    tile_load_async(xs + buf * tile_elems, X + n0 * K, (int64_t)rows * K);
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  __syncthreads();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = (nbuf == 2) ? (it & 1) : 0;
+    const int64_t n0 = tile * kObsTile;
+    const int rows = (int)((N - n0 < kObsTile) ? (N - n0) : kObsTile);
+    if (nbuf == 2) {
+      if (tile + gridDim.x < ntiles) load_tile(tile + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      if (it > 0) load_tile(tile, 0);
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    const double* xb = xs + buf * tile_elems + (size_t)(warp * kObsRows) * K;
+    const int wrows = rows - warp * kObsRows;
+    double t[4 * kObsRows];
+#pragma unroll
+    for (int r = 0; r < kObsRows; ++r) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (r < wrows) {
+        const double* xr = xb + (size_t)r * K + lane;
+#pragma unroll
+        for (int c = 0; c < kObsMaxChunks; ++c)
+          if (c < nch && 32 * c + lane < K) {
+            const double x = xr[32 * c], xx = x * x;
+            a0 = fma(x, bmr[c], a0);
+            a1 = fma(xx, bvr[c], a1);
+            a2 = fma(x, vmr[c], a2);
+            a3 = fma(xx, vvr[c], a3);
+          }
+      }
+      t[4 * r] = a0; t[4 * r + 1] = a1; t[4 * r + 2] = a2; t[4 * r + 3] = a3;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const bool hi = lane & m;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < m) {
+          const double send = hi ? t[i] : t[i + m], keep = hi ? t[i + m] : t[i];
+          t[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    // lane 4 rr + i holds sum i of row rr
+    const int base = lane & ~3;
+    double zm = __shfl_sync(0xffffffffu, t[0], base), zv = __shfl_sync(0xffffffffu, t[0], base + 1);
+    double dm = __shfl_sync(0xffffffffu, t[0], base + 2), dv = __shfl_sync(0xffffffffu, t[0], base + 3);
+    const int64_t n = n0 + warp * kObsRows + rr;
+    const bool rvalid = rr < wrows;
+    GHSumsF s = {0, 0, 0, 0, 0, 0};
+    double zs = 1.0, yn = 0.0;
+    if (rvalid) {
+      const int gi = g[n];
+      const double uinfo = vec[ui0 + gi];
+      zm += vec[um0 + gi];
+      zv += 1.0 / uinfo;
+      dm += v[um0 + gi];
+      dv += v[ui0 + gi] * (-1.0 / (uinfo * uinfo)) * (vecmode ? 1.0 : uinfo - bd.u_info);
+      zs = sqrt(zv);
+      yn = y[n];
+      gh_all_nodes_f<1, 2>(zm, zs, ghc + ns * npl, ghw + ns * npl, (Q - ns + 3) >> 2, s);
+    }
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+      s.Am += __shfl_xor_sync(0xffffffffu, s.Am, m);
+      s.As += __shfl_xor_sync(0xffffffffu, s.As, m);
+    }
+    if (rvalid && ns == 0) {
+      const double lm = yn - s.Am, lv = -s.As * (0.5 / zs);
+      out[n] = -(lm * dm + lv * dv);
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-group segmented sums.  One warp per group (grid-stride); observations of a group are
 // the contiguous range [gptr[g], gptr[g+1]) so no atomics are needed and the summation order
@@ -432,6 +553,35 @@ k_group(const double* __restrict__ X, const double* __restrict__ W,
       }
     }
   }
+}
+
+// Launchers for sensitivity.cu (K > 62): the data terms of the gradient with dw as the weights -- k_obs<1>
+// writing l_m, l_v into a scratch W (the cached evaluation's W stays intact) + k_group<1> on it -- and the
+// influence pass.
+int launch_wide_weight_pass(lrvb_glmm* h, const double* dw, double* scratchW, cudaStream_t st) {
+  const int K = h->K, G = h->G, Q = h->Q;
+  if (h->N > 0) {
+    k_obs<1><<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, dw, h->vec, h->gh, scratchW, h->klpart,
+                                                    h->gradpart, h->N, h->ldw, K, G, Q, h->obs_tn);
+    LRVB_CHECK_LAUNCH();
+  }
+  if (G > 0) {
+    const int ggrid = (int)((G + 7) / 8 < 148 * 8 ? (G + 7) / 8 : 148 * 8);
+    k_group<1><<<ggrid, 256, 0, st>>>(h->X, scratchW, h->gptr, h->gsc, h->BR, h->ldw, K, G);
+    LRVB_CHECK_LAUNCH();
+  }
+  return LRVB_OK;
+}
+int launch_wide_influence(lrvb_glmm* h, const double* v, double* out, cudaStream_t st) {
+  static size_t configured = 48 * 1024;
+  if (h->obs_smem > configured) {
+    LRVB_CUDA(cudaFuncSetAttribute(k_obs_influence_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obs_smem));
+    configured = h->obs_smem;
+  }
+  k_obs_influence_wide<<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, h->vec, h->gh, v, out, h->N, h->K,
+                                                             h->G, h->Q, h->obs_tn, h->bounds, h->vecmode);
+  LRVB_CHECK_LAUNCH();
+  return LRVB_OK;
 }
 
 // Finish of the small-K packed Gram (gram_small.cuh): fixed-order sum of the per-CTA partials of

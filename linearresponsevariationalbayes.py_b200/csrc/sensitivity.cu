@@ -15,6 +15,10 @@
 
 namespace lrvb {
 
+// K > 62 (glmm_eval.cu): k_obs<1> + k_group<1> with dw as the weights; the influence pass on the k_obs tile walk
+int launch_wide_weight_pass(lrvb_glmm* h, const double* dw, double* scratchW, cudaStream_t st);
+int launch_wide_influence(lrvb_glmm* h, const double* v, double* out, cudaStream_t st);
+
 // out = C dw from the sums of the fused pass run with weights dw (gradpart: X^T l_m, S^T l_v per
 // CTA; gsc: per-group sum l_m, sum l_v).  Signs / Jacobians as in k_global / k_local (data terms only).
 __global__ void __launch_bounds__(256)
@@ -187,14 +191,27 @@ int lrvb_glmm_weight_cross_matvec(lrvb_glmm* h, const double* dw_dev, double* ou
     set_error("lrvb_glmm_weight_cross_matvec: no evaluation cached (call lrvb_glmm_eval first)");
     return LRVB_ESTATE;
   }
-  if (!h->obs_fused) {
-    set_error("lrvb_glmm_weight_cross_matvec: K = %d > %d is not supported", h->K, kOfMaxK);
-    return LRVB_ESTATE;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   const int K = h->K, G = h->G, Q = h->Q;
   const int64_t N = h->N;
   int n_gp = 0;
+  if (!h->obs_fused) {
+    // K > 62: the wide-model observation kernel + k_group with dw as the weights; l_m, l_v go to a scratch
+    // block so that the cached evaluation's W (lrvb_glmm_obs_weights) stays intact
+    if (!h->wc_scratch && N > 0) {
+      if (cudaMalloc(&h->wc_scratch, sizeof(double) * 2 * (size_t)h->ldw) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("lrvb_glmm_weight_cross_matvec: out of device memory (%zu bytes of scratch)",
+                  sizeof(double) * 2 * (size_t)h->ldw);
+        return LRVB_ECUDA;
+      }
+    }
+    LRVB_TRY(launch_wide_weight_pass(h, dw_dev, h->wc_scratch, st));
+    k_wc_finish<<<cdiv(h->D, 256), 256, 0, st>>>(h->vec, h->gradpart, N > 0 ? h->obs_grid : 0, h->gsc, out_dev, K, G,
+                                                 h->bounds, h->vecmode);
+    LRVB_CHECK_LAUNCH();
+    return LRVB_OK;
+  }
   {
     // this translation unit has its own instantiations of the fused kernel: raise their limits too
     static size_t configured = 48 * 1024;
@@ -234,11 +251,8 @@ int lrvb_glmm_weight_cross_rmatvec(lrvb_glmm* h, const double* v_dev, double* ou
     set_error("lrvb_glmm_weight_cross_rmatvec: no evaluation cached (call lrvb_glmm_eval first)");
     return LRVB_ESTATE;
   }
-  if (!h->obs_fused) {
-    set_error("lrvb_glmm_weight_cross_rmatvec: K = %d > %d is not supported", h->K, kOfMaxK);
-    return LRVB_ESTATE;
-  }
   if (h->N == 0) return LRVB_OK;
+  if (!h->obs_fused) return launch_wide_influence(h, v_dev, out_dev, (cudaStream_t)stream);
   const size_t smem = h->of_smem + sizeof(double) * (2 * (size_t)h->K + 2);
   static size_t configured = 48 * 1024;
   if (smem > configured) {

@@ -13,6 +13,10 @@ CASES = {
     "small_shuffled": dict(N=257, K=5, G=9, Q=6, seed=31, ragged=True, shuffle=True, weights=True),
     "k33_bounds": dict(N=300, K=33, G=7, Q=8, seed=32, bounds=0.05),
     "multistage": dict(N=70001, K=12, G=40, Q=4, seed=33, ragged=True),
+    # K > 62: the wide-model observation kernel (lane = column dot products, transposing butterflies)
+    "k80_wide": dict(N=903, K=80, G=10, Q=6, seed=34, weights=True, bounds=0.05),
+    "k200_wide_ragged": dict(N=777, K=200, G=9, Q=8, seed=35, ragged=True),
+    "k65_odd": dict(N=300, K=65, G=5, Q=5, seed=36),
 }
 
 
