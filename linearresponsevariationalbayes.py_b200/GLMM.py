@@ -15,6 +15,7 @@ accepts it in place of ``fun``.
 """
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -61,11 +62,26 @@ class _Pattern(object):
     """One exported sparsity pattern: device ``crow`` (D+1) / ``col`` (capacity) int32, the nnz (device
     scalar, read once when first needed) and, once some caller has asked for a host matrix, the host
     copies of the index arrays (read-only, shared by the scipy matrices handed out)."""
-    __slots__ = ("crow", "col", "nnz_dev", "_nnz", "shape", "host_template")
+    __slots__ = ("crow", "col", "nnz_dev", "_nnz", "shape", "host_template", "host_blocks")
 
     def __init__(self, crow, col, nnz_dev, shape):
         self.crow, self.col, self.nnz_dev, self._nnz, self.shape = crow, col, nnz_dev, None, tuple(shape)
         self.host_template = None
+        self.host_blocks = []      # [pinned tensor, weakref to the ndarray handed out on it (or None)]
+
+    def host_block(self, torch, nnz, dtype):
+        """A pinned host block for ``data``: one whose previous ndarray is gone is used again, otherwise a new
+        one is pinned (milliseconds).  The pattern owns its blocks, so in steady state a caller that drops --
+        or still holds -- the previous matrix when it asks for the next one rotates between the same two
+        blocks and no step ever waits for ``cudaHostAlloc`` (torch's caching host allocator hands a freed
+        block out again only once the event of its last copy has been seen complete: sporadic re-pinning,
+        2 ms steps among 0.6 ms ones)."""
+        for ent in self.host_blocks:
+            if (ent[1] is None or ent[1]() is None) and ent[0].numel() >= nnz and ent[0].dtype == dtype:
+                return ent
+        ent = [torch.empty(nnz, dtype=dtype, pin_memory=True), None]
+        self.host_blocks.append(ent)
+        return ent
 
     @property
     def nnz(self):
@@ -146,7 +162,8 @@ class DeviceCSR(object):
         torch = nat.require_cuda()
         pat = self._resolve()
         nnz = pat.nnz
-        hv = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
+        ent = pat.host_block(torch, nnz, self._val.dtype)
+        hv = ent[0][:nnz]
         hv.copy_(self._val[:nnz], non_blocking=True)
         if pat.host_template is None:
             hc = torch.empty(nnz, dtype=torch.int32, pin_memory=True)
@@ -157,10 +174,12 @@ class DeviceCSR(object):
                 # a caller that still holds the previous matrix when it asks for the next one needs TWO value
                 # blocks in rotation; pinning a block costs milliseconds (8 ms for 16 MB), so the second one
                 # is created now, next to the pattern download, and parked in the host allocator's cache
-                spare = torch.empty(nnz, dtype=self._val.dtype, pin_memory=True)
-                del spare
+                ent[1] = lambda: True                # (marks this block as taken while the spare is made)
+                pat.host_block(torch, nnz, self._val.dtype)
             torch.cuda.current_stream().synchronize()
-            m = scipy.sparse.csr_matrix((hv.numpy(), hc.numpy(), hr.numpy()), shape=self.shape, copy=False)
+            data = hv.numpy()
+            ent[1] = weakref.ref(data)
+            m = scipy.sparse.csr_matrix((data, hc.numpy(), hr.numpy()), shape=self.shape, copy=False)
             m.has_sorted_indices = True
             m.indices.flags.writeable = False     # shared with later matrices of the same pattern
             m.indptr.flags.writeable = False
@@ -171,7 +190,9 @@ class DeviceCSR(object):
         torch.cuda.current_stream().synchronize()
         m = scipy.sparse.csr_matrix.__new__(scipy.sparse.csr_matrix)
         m.__dict__.update(pat.host_template)
-        m.data = hv.numpy()
+        data = hv.numpy()
+        ent[1] = weakref.ref(data)
+        m.data = data
         return m
 
     def toarray(self):
