@@ -1,5 +1,5 @@
-// Weighted Grams of the beta block for LARGE K (K >= 96, K % 8 == 0; BASELINE configs[3]: K = 200) on the
-// FP64 tensor cores (DMMA.8x8x4), sm_100a.
+// Weighted Grams of the beta block for LARGE K (K >= 96, K % 8 == 0; default K = 176 .. 240; BASELINE configs[3]:
+// K = 200) on the FP64 tensor cores (DMMA.8x8x4), sm_100a.
 //
 // Same packed formulation as gram_small / gram_mid / gram_big: one weighted Gram of z_n = [x_n | s_n]
 // (2K columns, T2 = K/4 tiles of 8), upper triangle only; with K % 8 == 0 no tile straddles the x | s
@@ -8,17 +8,25 @@
 // every CTA stages all 2K columns -> 16 rows per stage at K = 200, 51 % of the DGEMM peak):
 //   * the measured rule of this pipe (tools/dmma_probe4.cu, gram_mid.cuh): a warp needs >= ~24 independent
 //     accumulator tiles per k-step and every warp of a CTA the SAME work.  Each half of the packed columns
-//     is cut into blocks of 4 or 5 tiles; a warp job is one block against another (16 - 25 tiles, 255
+//     is cut into blocks of 4 or 5 tiles; a warp job is one block against another (16 - 25 tiles, 200
 //     registers, 8 warps per SM) or a block against itself (a "stair": 10 / 15 live tiles);
-//   * a CTA (job group) runs 8 jobs and stages ONLY the column blocks its jobs touch (4 - 7 of the 2K/40
-//     blocks) by bulk async copies (TMA) into a 3-slot ring: 24 - 40 rows per stage instead of 16, and the
-//     groups that share rows run at the same time, so the re-reads of X are L2 hits;
+//   * a CTA (job group) runs 8 jobs and stages ONLY the column blocks its jobs touch (4 - 8 of the 2K/40
+//     blocks) by bulk async copies (TMA, one per row and run of adjacent blocks) into a 3-slot ring: 28 - 56
+//     rows per stage instead of 16, and the groups that share rows run at the same time, so the re-reads of
+//     X are L2 hits (ncu: DRAM read 1.18 GB for 0.8 GB of X);
+//   * the s = x * x blocks of stage j + 1 are squared in place DURING the k-steps of stage j (two pairs per
+//     k-step: loads ahead of the DMMAs, stores behind) -- as a separate pass between stages it cost 20 % of
+//     the kernel;
 //   * groups are composed so that the two warps of every SM sub-partition carry the same DMMA count
-//     (4 full + 4 stair jobs, or 8 full jobs), and the 148 CTAs are dealt to the groups in proportion to
-//     their load (a group with lighter jobs gets fewer CTAs, i.e. more rows each);
+//     (4 rectangle + 4 stair jobs, or 8 rectangle jobs), and the 148 CTAs are dealt to the groups in
+//     proportion to their load (a group with lighter jobs gets fewer CTAs, i.e. more rows each);
 //   * partials go to the packed layout (n_cta, NT, 64) of gram_small / gram_mid (slot j (j+1)/2 + i), a CTA
 //     writes the tiles of its jobs and never touches the others (zero since creation), so the finishing
-//     pass is gram_small_finish_body unchanged.
+//     pass is gram_small_finish_body unchanged;
+//   * at 200 registers x 256 threads the CTA leaves room for one 48-register CTA per SM: launch_eval runs
+//     k_group beside it on a side stream.
+// Measured (profiles/r02_gram_wide.md, every step incl. the failed ones): K = 200: 0.68 of the DGEMM peak
+// (DMMA pipe 69 % active; rectangle kernel 0.51); faster than the rectangle kernel for K = 176 .. 240.
 #pragma once
 #include <algorithm>
 #include <vector>
