@@ -151,13 +151,13 @@ int lrvb_glmm_create(lrvb_glmm** out, int64_t N, int32_t K, int32_t G, int32_t Q
   h->ldw = (N + 7) / 8 * 8;
   CREATE_TRY(dev_alloc(&h->W, 5 * (size_t)h->ldw));
 
-  // observation pass geometry (k_obs, K > 62: 64-row tiles; obs_tn = tile buffers, two when they fit;
+  // observation pass geometry (k_obs, K > 62: 64-row tiles; obs_nbuf = tile buffers, two when they fit;
   // LRVB_OBS_NBUF=1 forces one)
   {
     const size_t tile = sizeof(double) * 64 * (size_t)K, extra = sizeof(double) * (2 * (size_t)(Q + 3) + 32 + 2);
-    h->obs_tn = (2 * tile + extra <= 220 * 1024) ? 2 : 1;
-    if (getenv("LRVB_OBS_NBUF") && getenv("LRVB_OBS_NBUF")[0] == '1') h->obs_tn = 1;
-    h->obs_smem = h->obs_tn * tile + extra;
+    h->obs_nbuf = (2 * tile + extra <= 220 * 1024) ? 2 : 1;
+    if (getenv("LRVB_OBS_NBUF") && getenv("LRVB_OBS_NBUF")[0] == '1') h->obs_nbuf = 1;
+    h->obs_smem = h->obs_nbuf * tile + extra;
     int64_t nt = (N + 63) / 64;
     h->obs_grid = (int)(nt < kNumSMs ? nt : kNumSMs);
     if (h->obs_grid < 1) h->obs_grid = 1;

@@ -226,7 +226,7 @@ struct lrvb_glmm {
   double* vec = nullptr;      // (D) constrained values
   double* W = nullptr;        // (5, ldw) per-observation derivative weights
   // observation pass
-  int obs_tn = 0, obs_grid = 0;   // k_obs (K > 62): number of tile buffers, CTAs
+  int obs_nbuf = 0, obs_grid = 0;   // k_obs (K > 62): number of tile buffers, CTAs
   size_t obs_smem = 0;
   double* klpart = nullptr;   // (obs_grid) per-CTA partials of sum w*l
   double* gradpart = nullptr; // (obs_grid, 2, K) per-CTA partials of X^T l_m , S^T l_v

@@ -562,7 +562,7 @@ int launch_wide_weight_pass(lrvb_glmm* h, const double* dw, double* scratchW, cu
   const int K = h->K, G = h->G, Q = h->Q;
   if (h->N > 0) {
     k_obs<1><<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, dw, h->vec, h->gh, scratchW, h->klpart,
-                                                    h->gradpart, h->N, h->ldw, K, G, Q, h->obs_tn);
+                                                    h->gradpart, h->N, h->ldw, K, G, Q, h->obs_nbuf);
     LRVB_CHECK_LAUNCH();
   }
   if (G > 0) {
@@ -579,7 +579,7 @@ int launch_wide_influence(lrvb_glmm* h, const double* v, double* out, cudaStream
     configured = h->obs_smem;
   }
   k_obs_influence_wide<<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, h->vec, h->gh, v, out, h->N, h->K,
-                                                             h->G, h->Q, h->obs_tn, h->bounds, h->vecmode);
+                                                             h->G, h->Q, h->obs_nbuf, h->bounds, h->vecmode);
   LRVB_CHECK_LAUNCH();
   return LRVB_OK;
 }
@@ -1168,7 +1168,7 @@ int launch_eval(lrvb_glmm* h, const double* free_dev, int order, double* out_glo
     if (h->timing) LRVB_CUDA(cudaEventRecord(h->ev[0], st));
 #define LRVB_OBS(O)                                                                          \
   k_obs<O><<<h->obs_grid, 256, h->obs_smem, st>>>(h->X, h->y, h->g, h->w, h->vec, h->gh, \
-                                                   h->W, h->klpart, h->gradpart, N, h->ldw, K, G, Q, h->obs_tn)
+                                                   h->W, h->klpart, h->gradpart, N, h->ldw, K, G, Q, h->obs_nbuf)
     if (order == 0) LRVB_OBS(0);
     else if (order == 1) LRVB_OBS(1);
     else LRVB_OBS(2);
