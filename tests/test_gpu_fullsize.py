@@ -144,3 +144,26 @@ def test_moment_covariance_at_scale(vb):
         assert_close(blk[k], ref_row, rtol=1e-8, scale=np.abs(ref_row).max() * 1e-3, what="row %d" % r)
         assert abs(diag[r] - ref_row[r]) <= 1e-8 * abs(ref_row[r]) + 1e-14
     assert (diag > 0).all()
+
+
+def test_group_pass_beside_the_wide_gram_is_bitwise_the_serial_order(vb):
+    """Under k_gram_wide the per-group pass (k_group) runs on the handle's side stream beside the Gram kernel
+    (launch_eval); LRVB_GROUP_OVERLAP=0 restores the serial order.  Same kernels, same inputs: the Hessian,
+    gradient and KL must be bitwise identical, over several evaluations at different points (the fork / join
+    events are reused)."""
+    import os
+    case = make_case(N=20_003, K=200, G=40, Q=8, seed=4002)
+    m1 = make_model(vb, case)
+    os.environ["LRVB_GROUP_OVERLAP"] = "0"
+    try:
+        m0 = make_model(vb, case)
+    finally:
+        os.environ.pop("LRVB_GROUP_OVERLAP", None)
+    o1, o0 = vb.Objective(m1.glmm_par, m1), vb.Objective(m0.glmm_par, m0)
+    for shift in (0.0, 0.01, -0.02):
+        x = case["free"] + shift
+        H1, H0 = o1.fun_free_hessian(x), o0.fun_free_hessian(x)
+        np.testing.assert_array_equal(H1.indices, H0.indices)
+        np.testing.assert_array_equal(H1.data, H0.data)
+        np.testing.assert_array_equal(o1.fun_free_grad(x), o0.fun_free_grad(x))
+        assert o1.fun_free(x) == o0.fun_free(x)
