@@ -25,7 +25,10 @@
 
 namespace lrvb {
 
-constexpr int kGmRows = 16;       // rows per stage (4 k-steps)
+// rows per stage: 32 (8 k-steps between two ring hand-overs) wherever three slots of them fit beside the
+// other teams' rings -- from T2 = 9 on (<= 6 teams per CTA); measured 0.7 - 3.5 % faster than 16 for K = 36 .. 104
+// (K = 50: 3.680 -> 3.654 ms at N = 10M); the 12 - 16 single-warp teams of T2 <= 8 stay at 16 rows
+__host__ __device__ constexpr int gram_mid_rows(int T2) { return T2 >= 9 ? 32 : 16; }
 constexpr int kGmStages = 3;      // ring depth per team
 constexpr int kGmMaxK = 104;      // T2 = ceil(2K / 8) <= 26
 
@@ -67,11 +70,13 @@ __host__ __device__ constexpr int gram_mid_bound(int T2, int T0, bool has_m, int
   }
   return NT;
 }
-__host__ __device__ inline size_t gram_mid_stage_elems(int K) { return (size_t)kGmRows * K + 3 * kGmRows; }
+__host__ __device__ inline size_t gram_mid_stage_elems(int K, int T2) {
+  return (size_t)gram_mid_rows(T2) * K + 3 * gram_mid_rows(T2);
+}
 inline size_t gram_mid_smem(int K, int T2) {
   const GramMidGeom g = gram_mid_geom(T2);
   const int teams = g.warps / g.P;
-  const size_t ring = sizeof(double) * teams * kGmStages * gram_mid_stage_elems(K) +
+  const size_t ring = sizeof(double) * teams * kGmStages * gram_mid_stage_elems(K, T2) +
                       sizeof(unsigned long long) * teams * kGmStages * 2;
   const size_t red = sizeof(double) * (size_t)(T2 * (T2 + 1) / 2) * 64;
   return ring > red ? ring : red;
@@ -90,10 +95,11 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
   constexpr int T_LO = TLO;
   constexpr int NTL = THI - TLO;                       // accumulator tiles of this warp
   auto mine = [](int i, int j) constexpr { return j * (j + 1) / 2 + i >= TLO && j * (j + 1) / 2 + i < THI; };
-  constexpr int KSTEPS = kGmRows / 4;
+  constexpr int ROWS = gram_mid_rows(T2);
+  constexpr int KSTEPS = ROWS / 4;
   const int lane = threadIdx.x & 31;
   const int lr = lane & 3, lc = lane >> 2;
-  const int stage_elems = kGmRows * K + 3 * kGmRows;
+  const int stage_elems = ROWS * K + 3 * ROWS;
 
   // packed column `col = 8 t + lc` of tile t sits at x column `col` (x class) or `col - K` (s class)
   // of the staged row: compile-time per tile except in the straddle tile and beyond 2K in the last
@@ -117,16 +123,16 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
   for (int t = 0; t < NTL; ++t) acc[t][0] = acc[t][1] = 0.0;
 
   // 32-bit stage counters (N < 2^35): registers are the scarce resource of this kernel
-  const int nstage = (int)((N + kGmRows - 1) / kGmRows);
-  const int nfull = (int)(N / kGmRows);
-  const unsigned xbytes = (unsigned)(kGmRows * K * sizeof(double));
-  const unsigned wbytes = (unsigned)(kGmRows * sizeof(double));
+  const int nstage = (int)((N + ROWS - 1) / ROWS);
+  const int nfull = (int)(N / ROWS);
+  const unsigned xbytes = (unsigned)(ROWS * K * sizeof(double));
+  const unsigned wbytes = (unsigned)(ROWS * sizeof(double));
 
   auto issue = [&](int s, int slot) {
     if (s < nfull && lane < 4) {
       const unsigned bar = full_u + 8 * slot;
       const unsigned dst = ring_u + (unsigned)(slot * stage_elems * sizeof(double));
-      const int64_t n0 = (int64_t)s * kGmRows;
+      const int64_t n0 = (int64_t)s * ROWS;
       if (lane == 0) {
         mbar_arrive_expect_tx(bar, xbytes + 3 * wbytes);
         bulk_g2s(dst, X + n0 * K, xbytes, bar);
@@ -151,12 +157,12 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
     } else if (PRODUCER) {   // ragged last stage: filled by the producer warp itself, zero rows beyond N
       if (P > 1 && (s - gt) / tt >= kGmStages) mbar_wait(empty_u + 8 * slot, phase ^ 1u);   // previous use released
       double* xs = ring + (size_t)slot * stage_elems;
-      double* ws = xs + kGmRows * K;
-      const int64_t n0 = (int64_t)s * kGmRows;
+      double* ws = xs + ROWS * K;
+      const int64_t n0 = (int64_t)s * ROWS;
       const int rows = (int)(N - n0);
-      for (int e = lane; e < kGmRows * K; e += 32) xs[e] = (e < rows * K) ? X[n0 * K + e] : 0.0;
-      for (int e = lane; e < 3 * kGmRows; e += 32) {
-        const int f = e / kGmRows, r = e % kGmRows;
+      for (int e = lane; e < ROWS * K; e += 32) xs[e] = (e < rows * K) ? X[n0 * K + e] : 0.0;
+      for (int e = lane; e < 3 * ROWS; e += 32) {
+        const int f = e / ROWS, r = e % ROWS;
         ws[e] = (r < rows) ? Wabc[(int64_t)f * ldw + n0 + r] : 0.0;
       }
       __syncwarp();
@@ -165,7 +171,7 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
       mbar_wait(full_u + 8 * slot, phase);
     }
     const unsigned xs_u = ring_u + (unsigned)(slot * stage_elems * sizeof(double));
-    const unsigned ws_u = xs_u + 8u * (unsigned)(kGmRows * K + lr);
+    const unsigned ws_u = xs_u + 8u * (unsigned)(ROWS * K + lr);
 #pragma unroll 1
     for (int ks = 0; ks < KSTEPS; ++ks) {
       const unsigned row_u = xs_u + 8u * (unsigned)(4 * ks * K);
@@ -179,8 +185,8 @@ __device__ __forceinline__ void gram_mid_run(const double* __restrict__ X, const
         z[t] = lds_f64(row_u + 8u * (unsigned)o);
       }
       const double wa = lds_f64(ws_u + 8u * (unsigned)(4 * ks));
-      const double wb = lds_f64(ws_u + 8u * (unsigned)(kGmRows + 4 * ks));
-      const double wc = lds_f64(ws_u + 8u * (unsigned)(2 * kGmRows + 4 * ks));
+      const double wb = lds_f64(ws_u + 8u * (unsigned)(ROWS + 4 * ks));
+      const double wc = lds_f64(ws_u + 8u * (unsigned)(2 * ROWS + 4 * ks));
 #pragma unroll
       for (int t = 0; t < JHI; ++t) {
         if (t == TS) {
@@ -289,9 +295,10 @@ k_gram_mid(const double* __restrict__ X, const double* __restrict__ Wabc, double
   constexpr int NT = T2 * (T2 + 1) / 2;
   constexpr int TEAMS = WARPS / P;
   extern __shared__ __align__(16) double sm[];
+  constexpr int ROWS = gram_mid_rows(T2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp % TEAMS, role = warp / TEAMS;      // partners sit on the same sub-partition
-  const int stage_elems = kGmRows * K + 3 * kGmRows;
+  const int stage_elems = ROWS * K + 3 * ROWS;
   double* ring = sm + (size_t)team * kGmStages * stage_elems;
   unsigned long long* bars =
       reinterpret_cast<unsigned long long*>(sm + (size_t)TEAMS * kGmStages * stage_elems) + team * kGmStages * 2;
