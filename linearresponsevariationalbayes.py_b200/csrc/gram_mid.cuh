@@ -4,8 +4,8 @@
 // the T2 x T2 tile grid, tile classes pure-x / straddle / pure-s) and the same execution model:
 // the WHOLE TRIANGLE is owned, for a set of rows, by one warp -- or by a TEAM of 2 / 4 / 8 warps when
 // its NT = T2 (T2 + 1) / 2 accumulator tiles do not fit the registers of one (2 registers per tile and
-// thread; 255 registers per thread at 8 warps per SM).  A team streams its own 16-row stages through
-// a private shared-memory ring filled by bulk async copies, and all teams of all CTAs do identical
+// thread; 255 registers per thread at 8 warps per SM).  A team streams its own 16- / 32-row stages (gram_mid_rows)
+// through a private shared-memory ring filled by bulk async copies, and all teams of all CTAs do identical
 // work, so the four FP64 pipes of an SM are evenly loaded -- which the rectangle jobs of gram_big.cuh
 // never quite achieve (0.29 - 0.63 of the DMMA peak on the same sizes, 0.73 - 0.85 here).
 //   * Roles: the tiles in column-major order are cut into P contiguous ranges of equal DMMA count

@@ -40,8 +40,8 @@ CASES = {
     "k130_job_groups": dict(N=1100, K=130, G=11, Q=4, seed=23),
     "k21_odd_rows_not_tma": dict(N=2100, K=21, G=20, Q=8, seed=24, weights=True),
     # k_gram_mid: every tile-grid size of the two-warp teams (T2 = 9 .. 13, with and without a straddle
-    # tile), ragged last stage (N not a multiple of 16), and enough rows that a team's 3-slot ring wraps
-    # (148 SMs x 4 teams x 16 rows x 3 slots = 28k rows) with the producer one stage ahead of its partner
+    # tile), ragged last stage (N not a multiple of the 32-row stage), and enough rows that a team's 3-slot ring wraps
+    # (148 SMs x 4 teams x 32 rows x 3 slots = 57k rows) with the producer one stage ahead of its partner
     "k36_team": dict(N=2501, K=36, G=25, Q=8, seed=25),
     "k37_team": dict(N=2500, K=37, G=25, Q=6, seed=26, weights=True),
     "k40_team": dict(N=2503, K=40, G=20, Q=8, seed=27),
@@ -55,7 +55,8 @@ CASES = {
     "k56_team4": dict(N=1503, K=56, G=15, Q=4, seed=34),
     "k72_team4": dict(N=1200, K=72, G=12, Q=4, seed=35, weights=True),
     "k77_team8": dict(N=1101, K=77, G=11, Q=4, seed=36),
-    "k104_team8_ring_wrap": dict(N=10007, K=104, G=10, Q=4, seed=37),
+    "k104_team8_ring_wrap": dict(N=30011, K=104, G=30, Q=4, seed=37),
+    "k72_team4_ring_wrap": dict(N=40009, K=72, G=40, Q=4, seed=46, weights=True),
     # k_gram_wide (K >= 112, K % 8 == 0): blocks of 5,5,4 tiles (mixed 5x4 / 4x5 / 4x4 jobs), of 5 only, of 4
     # only (K = 128); ragged last stage; enough rows that every CTA's 3-slot ring wraps
     "k112_wide": dict(N=2503, K=112, G=20, Q=4, seed=38, weights=True),
